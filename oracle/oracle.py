@@ -1,0 +1,230 @@
+"""TEST INFRASTRUCTURE ONLY — Python face of the CPU oracle.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this module.  The product path
+(``libperseus-sdr_b200/``) never does.
+
+Three independent statements of the reference's I/Q unpack
+(``/root/reference/examples/perseustest.c:432-460`` int32, ``:466-502`` float;
+duplicate int32 callback ``examples/simple.c:33-61``):
+
+* ``Ref``     – the reference's own callbacks compiled verbatim (``oracle/_ref``,
+                built by ``oracle/Makefile`` from ``/root/reference`` where it lies);
+* ``COracle`` – our C restatement (``oracle/perseus_oracle.c``), also the timed CPU port;
+* ``np_*``    – a numpy restatement, used to cross-check the other two.
+
+Parity pinning: the reference has no golden vectors for this path; the restatements
+are pinned against ``Ref`` over all 2**24 codes (tests/test_oracle.py) and against
+``tests/golden/`` fixtures generated from ``Ref`` (tests/golden/make_golden.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+LIB_ORACLE = HERE / "liboracle.so"
+LIB_REF = HERE / "_ref" / "libperseus_ref.so"
+
+MODE_I32, MODE_F32, MODE_F32_POW2 = 0, 1, 2
+#: (float)(INT_MAX - 256), perseustest.c:496 — exactly representable in binary32.
+REF_DIVISOR = np.float32(2147483392.0)
+SYNTH_SEED = 0x5045525345555300  # "PERSEUS\0", SURVEY.md §8(d)
+
+
+def build(force: bool = False) -> None:
+    """Compile liboracle.so (and _ref/ when /root/reference is mounted); make decides staleness."""
+    subprocess.run(["make", "-s", "-C", str(HERE)] + (["-B"] if force else []), check=True)
+
+
+def _u8(a) -> np.ndarray:
+    a = np.ascontiguousarray(a)
+    return a.view(np.uint8).reshape(-1)
+
+
+class COracle:
+    """ctypes binding of oracle/perseus_oracle.c."""
+
+    def __init__(self) -> None:
+        build()
+        L = C.CDLL(str(LIB_ORACLE))
+        vp, sz, u64 = C.c_void_p, C.c_size_t, C.c_uint64
+        L.perseus_oracle_unpack.restype = sz
+        L.perseus_oracle_unpack.argtypes = [C.c_int, vp, sz, vp]
+        L.perseus_oracle_unpack_mt.restype = sz
+        L.perseus_oracle_unpack_mt.argtypes = [C.c_int, vp, sz, vp, C.c_int]
+        L.perseus_oracle_fnv1a64.restype = u64
+        L.perseus_oracle_fnv1a64.argtypes = [vp, sz, u64]
+        L.perseus_oracle_checksum32.restype = u64
+        L.perseus_oracle_checksum32.argtypes = [vp, sz, u64]
+        L.perseus_oracle_synth_random.restype = None
+        L.perseus_oracle_synth_random.argtypes = [vp, sz, u64, u64]
+        L.perseus_oracle_synth_ramp.restype = None
+        L.perseus_oracle_synth_ramp.argtypes = [vp, sz, u64]
+        self.L = L
+
+    def unpack(self, buf, mode: int = MODE_I32, nthreads: int = 1, out: np.ndarray | None = None) -> np.ndarray:
+        b = _u8(buf)
+        ns = b.size // 6
+        dt = np.int32 if mode == MODE_I32 else np.float32
+        if out is None:
+            out = np.empty((ns, 2), dtype=dt)
+        assert out.nbytes >= ns * 8 and out.flags.c_contiguous
+        n = self.L.perseus_oracle_unpack_mt(mode, b.ctypes.data, b.size, out.ctypes.data, nthreads)
+        assert n == ns, (n, ns)
+        return out
+
+    def unpack_raw(self, mode: int, in_ptr: int, nbytes: int, out_ptr: int, nthreads: int) -> int:
+        return self.L.perseus_oracle_unpack_mt(mode, in_ptr, nbytes, out_ptr, nthreads)
+
+    def fnv1a64(self, data, h: int = 0) -> int:
+        b = _u8(data)
+        return int(self.L.perseus_oracle_fnv1a64(b.ctypes.data, b.size, h))
+
+    def checksum32(self, words, first_index: int = 0) -> int:
+        w = np.ascontiguousarray(words).view(np.uint32).reshape(-1)
+        return int(self.L.perseus_oracle_checksum32(w.ctypes.data, w.size, first_index))
+
+    def synth_random(self, nbytes: int, seed: int = SYNTH_SEED, byte_offset: int = 0) -> np.ndarray:
+        out = np.empty(nbytes, dtype=np.uint8)
+        self.L.perseus_oracle_synth_random(out.ctypes.data, nbytes, seed, byte_offset)
+        return out
+
+    def synth_ramp(self, nsamples: int, first_sample: int = 0) -> np.ndarray:
+        out = np.empty(nsamples * 6, dtype=np.uint8)
+        self.L.perseus_oracle_synth_ramp(out.ctypes.data, nsamples, first_sample)
+        return out
+
+
+class Ref:
+    """The reference's own callbacks (verbatim), when oracle/_ref was built."""
+
+    @staticmethod
+    def available() -> bool:
+        if not LIB_REF.exists() and Path("/root/reference/examples/perseustest.c").exists():
+            try:
+                build()
+            except Exception:
+                return False
+        return LIB_REF.exists()
+
+    def __init__(self) -> None:
+        if not self.available():
+            raise FileNotFoundError(f"{LIB_REF} not built (needs /root/reference at build time)")
+        L = C.CDLL(str(LIB_REF))
+        vp, sz = C.c_void_p, C.c_size_t
+        for f in (L.perseus_ref_unpack_i32, L.perseus_ref_unpack_f32):
+            f.restype = sz
+            f.argtypes = [vp, sz, sz, vp, sz]
+        L.perseus_ref_unpack_mt.restype = sz
+        L.perseus_ref_unpack_mt.argtypes = [C.c_int, vp, sz, sz, vp, sz, C.c_int]
+        L.perseus_ref_build_info.restype = C.c_char_p
+        self.L = L
+
+    def unpack(self, buf, mode: int = MODE_I32, chunk: int = 6144) -> np.ndarray:
+        """Feed `buf` to the reference callback `chunk` bytes per call (one USB transfer
+        per call, perseus-in.c:206-207) and return what it wrote to its FILE*."""
+        assert mode in (MODE_I32, MODE_F32)
+        b = _u8(buf)
+        # samples are counted per call: a short last call drops its own remainder
+        full, rem = divmod(b.size, chunk)
+        ns = full * (chunk // 6) + rem // 6
+        out = np.empty((ns, 2), dtype=np.int32 if mode == MODE_I32 else np.float32)
+        fn = self.L.perseus_ref_unpack_i32 if mode == MODE_I32 else self.L.perseus_ref_unpack_f32
+        n = fn(b.ctypes.data, b.size, chunk, out.ctypes.data, out.nbytes)
+        assert n == out.nbytes, (n, out.nbytes)
+        return out
+
+    def unpack_mt_raw(self, want_float: bool, in_ptr: int, nbytes: int, chunk: int, out_ptr: int, out_cap: int,
+                      nthreads: int) -> int:
+        n = self.L.perseus_ref_unpack_mt(int(want_float), in_ptr, nbytes, chunk, out_ptr, out_cap, nthreads)
+        if n == C.c_size_t(-1).value:
+            raise RuntimeError("reference callback sink overflow")
+        return n
+
+    def build_info(self) -> str:
+        return self.L.perseus_ref_build_info().decode()
+
+
+# --------------------------------------------------------------------------- numpy
+
+def np_unpack_i32(buf) -> np.ndarray:
+    """perseustest.c:447-457 in numpy: bytes (b0,b1,b2) -> b0<<8 | b1<<16 | b2<<24."""
+    b = _u8(buf)
+    ns = b.size // 6
+    f = b[: ns * 6].reshape(ns, 2, 3).astype(np.uint32)
+    u = (f[..., 0] << np.uint32(8)) | (f[..., 1] << np.uint32(16)) | (f[..., 2] << np.uint32(24))
+    return u.view(np.int32)
+
+
+def np_unpack_f32(buf) -> np.ndarray:
+    """perseustest.c:496-497: (float)x / (INT_MAX-256), IEEE round-to-nearest."""
+    return np_unpack_i32(buf).astype(np.float32) / REF_DIVISOR
+
+
+def np_unpack_f32_pow2(buf) -> np.ndarray:
+    return np_unpack_i32(buf).astype(np.float32) * np.float32(2.0 ** -31)
+
+
+def np_unpack(buf, mode: int) -> np.ndarray:
+    return (np_unpack_i32, np_unpack_f32, np_unpack_f32_pow2)[mode](buf)
+
+
+def _splitmix64(x: np.ndarray) -> np.ndarray:
+    with np.errstate(over="ignore"):
+        x = x + np.uint64(0x9E3779B97F4A7C15)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return x ^ (x >> np.uint64(31))
+
+
+def np_synth_random(nbytes: int, seed: int = SYNTH_SEED, byte_offset: int = 0) -> np.ndarray:
+    """64-bit LE word w of the stream = splitmix64(seed + w)."""
+    w0 = byte_offset >> 3
+    w1 = (byte_offset + nbytes + 7) >> 3
+    with np.errstate(over="ignore"):
+        idx = np.arange(w0, w1, dtype=np.uint64) + np.uint64(seed & 0xFFFFFFFFFFFFFFFF)
+    words = _splitmix64(idx).astype("<u8")
+    s = byte_offset - (w0 << 3)
+    return words.view(np.uint8)[s: s + nbytes].copy()
+
+
+def np_synth_ramp(nsamples: int, first_sample: int = 0) -> np.ndarray:
+    """SURVEY.md §0 exhaustive pattern: I = v & 0xFFFFFF, Q = (uint32(v*2654435761)) >> 8."""
+    v = (np.arange(first_sample, first_sample + nsamples, dtype=np.uint64) & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    with np.errstate(over="ignore"):
+        q = (v * np.uint32(2654435761)) >> np.uint32(8)
+    i = v & np.uint32(0xFFFFFF)
+    out = np.empty((nsamples, 6), dtype=np.uint8)
+    for k in range(3):
+        out[:, k] = (i >> np.uint32(8 * k)).astype(np.uint8)
+        out[:, 3 + k] = (q >> np.uint32(8 * k)).astype(np.uint8)
+    return out.reshape(-1)
+
+
+def np_checksum32(words, first_index: int = 0) -> int:
+    w = np.ascontiguousarray(words).view(np.uint32).reshape(-1).astype(np.uint64)
+    with np.errstate(over="ignore"):
+        idx = np.arange(w.size, dtype=np.uint64) + np.uint64(first_index)
+        m = _splitmix64(idx) | np.uint64(1)
+        return int((m * (w + np.uint64(1))).sum(dtype=np.uint64))
+
+
+def fnv1a64_py(data: bytes, h: int = 0) -> int:
+    """Pure-Python FNV-1a-64 (small inputs only)."""
+    if h == 0:
+        h = 0xCBF29CE484222325
+    for byte in data:
+        h = ((h ^ byte) * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:  # pragma: no cover
+        return os.cpu_count() or 1
