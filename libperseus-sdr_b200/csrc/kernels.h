@@ -1,0 +1,51 @@
+// Internal interface between the C-ABI layer (perseus_gpu.cu) and the sm_100a kernels
+// (unpack_kernels.cu).  Not installed; the public surface is include/perseus-gpu.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+
+namespace pg {
+
+// output-format bits, same values as PERSEUS_GPU_OUT_* in include/perseus-gpu.h
+enum : unsigned { FMT_I32 = 1u, FMT_F32 = 2u, FMT_POW2 = 4u };
+
+constexpr int kConsumerThreads = 256;                  // threads that convert + store, per CTA
+constexpr int kProducerThreads = 32;                   // one warp; lane 0 issues the bulk copies
+constexpr int kMaxStages       = 8;
+constexpr int kDefaultTile     = 12288;                // two 6144-byte transfers per stage
+constexpr int kDefaultStages   = 4;
+constexpr int kDefaultCtasPerSm = 3;
+
+struct Tuning {            // resolved (no zeros) copy of perseus_gpu_tuning
+	int variant, tile_bytes, stages, ctas_per_sm, store_mode;
+};
+
+// One tile of a batched launch: which segment, which tile of it.
+struct TileRef { uint32_t seg, tile; };
+// Device-side copy of a perseus_gpu_seg.
+struct SegDesc { const uint8_t *in; uint64_t nbytes; void *out_i32; void *out_f32; };
+
+// Flat unpack of nbytes/6 samples.  Picks the kernel from `t.variant` and the pointers'
+// alignment; returns the number of kernels it launched through *launches.
+cudaError_t launch_unpack(const void *in, size_t nbytes, void *out_i32, void *out_f32, unsigned fmt,
+                          const Tuning &t, int sm_count, cudaStream_t stream, int *launches);
+
+// Batched unpack over nseg segments described on the device; tile map built by the caller
+// with tile size `t.tile_bytes`.  `all_aligned` = every in/out pointer is 16-byte aligned.
+cudaError_t launch_unpack_batch(const SegDesc *d_segs, const TileRef *d_tiles, uint64_t ntiles, unsigned fmt,
+                                bool all_aligned, const Tuning &t, int sm_count, cudaStream_t stream, int *launches);
+
+cudaError_t launch_generate(void *dst, size_t nbytes, int pattern, uint64_t seed, uint64_t byte_offset,
+                            cudaStream_t stream);
+// *d_sum (device, zeroed by the callee) += checksum of nwords 32-bit words
+cudaError_t launch_checksum(const void *words, size_t nwords, uint64_t first_index, unsigned long long *d_sum,
+                            cudaStream_t stream);
+// d_result[0] = mismatching words, d_result[1] = lowest mismatching word index (callee initialises)
+cudaError_t launch_verify(const void *in, size_t nbytes, const void *out_i32, const void *out_f32, unsigned fmt,
+                          unsigned long long *d_result, cudaStream_t stream);
+
+// Host mirror of the device generator (bit-identical), for perseus_synth_fill and the virtual receiver.
+void host_generate(uint8_t *dst, size_t nbytes, int pattern, uint64_t seed, uint64_t byte_offset);
+
+}  // namespace pg

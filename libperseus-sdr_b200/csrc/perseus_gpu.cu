@@ -1,0 +1,899 @@
+// C-ABI layer of libperseus_gpu.so (include/perseus-gpu.h): handle, streams, staging of host
+// buffers, the perseus_input_callback trampoline with its pinned slab ring, batched plans,
+// and the small device utilities.  All sample arithmetic lives in unpack_kernels.cu.
+//
+// Reference anchors: the callback contract is perseus-sdr.h:81 / perseus-in.c:204-207,263
+// (buffer valid only during the call, return value ignored, strictly serial, in ring order);
+// the error convention mirrors perseus-sdr.h:317-366 + perseuserr.c:36-42.
+#include "../../include/perseus-gpu.h"
+#include "kernels.h"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace {
+
+thread_local char g_errstr[1024] = "";
+
+int fail(int code, const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_errstr, sizeof(g_errstr), fmt, ap);
+	va_end(ap);
+	return code;
+}
+inline int ok(int v = 0) { return v; }
+
+constexpr int kMaxStreams = 8;
+constexpr int kMaxSlabs = 64;
+constexpr int kEventSlots = 32;
+
+struct Slab {
+	uint8_t *host = nullptr;       // pinned wire bytes being filled by the callback
+	uint8_t *dev_in = nullptr;     // device copy
+	uint8_t *dev_i32 = nullptr;    // device outputs of this slab
+	uint8_t *dev_f32 = nullptr;
+	uint8_t *host_out = nullptr;   // pinned copy of the output, only with a file sink
+	cudaEvent_t done = nullptr;    // recorded after the slab's last operation
+	uint64_t first_sample = 0;
+	size_t out_bytes = 0;          // bytes to write to the file sink once `done`
+	bool busy = false;
+};
+
+}  // namespace
+
+struct perseus_gpu {
+	int device = 0;
+	int sm_count = 0;
+	perseus_gpu_config cfg{};
+	pg::Tuning tune{};
+	int nstreams = 0;
+	cudaStream_t streams[kMaxStreams]{};
+	cudaEvent_t events[kEventSlots]{};
+	unsigned long long *d_scratch = nullptr;   // 2 x u64: checksum / verify results
+	unsigned long long *h_scratch = nullptr;   // pinned mirror
+	// staging for perseus_gpu_unpack with host pointers (one slot per stream)
+	size_t chunk_bytes = 0;
+	uint8_t *stage_in[kMaxStreams]{};
+	uint8_t *stage_out[kMaxStreams][2]{};
+	// streaming (callback) path
+	unsigned stream_fmt = 0;
+	size_t slab_bytes = 0;
+	int nslabs = 0;
+	Slab slabs[kMaxSlabs];
+	int cur = 0;               // slab being filled
+	size_t fill = 0;           // bytes in it
+	int next_to_write = 0;     // oldest slab whose output has not reached the file sink
+	bool streaming_ready = false;
+	uint64_t samples_submitted = 0;
+	perseus_gpu_sink sink = nullptr;
+	void *sink_extra = nullptr;
+	FILE *fout = nullptr;
+	// bookkeeping
+	perseus_gpu_stats stats{};
+	int latched = 0;           // first asynchronous error (surfaced at flush/sync/close)
+	char latched_msg[512] = "";
+};
+
+struct perseus_gpu_plan {
+	pg::SegDesc *d_segs = nullptr;
+	pg::TileRef *d_tiles = nullptr;
+	uint64_t ntiles = 0, nsamples = 0, nbytes = 0;
+	unsigned fmt = 0;
+	int tile_bytes = 0;
+	bool all_aligned = false;
+};
+
+namespace {
+
+#define CU(h, call)                                                                                               \
+	do {                                                                                                          \
+		cudaError_t e__ = (call);                                                                                 \
+		if (e__ != cudaSuccess)                                                                                   \
+			return fail(PERSEUS_GPU_CUDAERR, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+	} while (0)
+
+void latch(perseus_gpu *h, int code)
+{
+	if (h && !h->latched) {
+		h->latched = code;
+		snprintf(h->latched_msg, sizeof(h->latched_msg), "%.*s", (int)sizeof(h->latched_msg) - 1, g_errstr);
+	}
+}
+
+int surface_latched(perseus_gpu *h)
+{
+	if (!h->latched) return 0;
+	const int c = h->latched;
+	fail(c, "%s", h->latched_msg);
+	h->latched = 0;
+	return c;
+}
+
+pg::Tuning resolve_tuning(const perseus_gpu_tuning *t)
+{
+	pg::Tuning r{};
+	r.variant = t ? t->variant : 0;
+	r.tile_bytes = t && t->tile_bytes ? t->tile_bytes : pg::kDefaultTile;
+	r.stages = t && t->stages ? t->stages : pg::kDefaultStages;
+	r.ctas_per_sm = t && t->ctas_per_sm ? t->ctas_per_sm : pg::kDefaultCtasPerSm;
+	r.store_mode = t && t->store_mode ? t->store_mode : 1;
+	return r;
+}
+
+int check_tuning(const pg::Tuning &t)
+{
+	if (t.variant < 0 || t.variant > 2) return fail(PERSEUS_GPU_ERRPARAM, "tuning.variant %d not in 0..2", t.variant);
+	if (t.tile_bytes != 6144 && t.tile_bytes != 12288 && t.tile_bytes != 24576)
+		return fail(PERSEUS_GPU_ERRPARAM, "tuning.tile_bytes %d must be 6144, 12288 or 24576", t.tile_bytes);
+	if (t.stages < 2 || t.stages > pg::kMaxStages) return fail(PERSEUS_GPU_ERRPARAM, "tuning.stages %d not in 2..%d", t.stages, pg::kMaxStages);
+	if ((size_t)t.stages * t.tile_bytes > 200 * 1024)
+		return fail(PERSEUS_GPU_ERRPARAM, "tuning: stages*tile_bytes = %zu exceeds 200 KiB of shared memory", (size_t)t.stages * t.tile_bytes);
+	if (t.ctas_per_sm < 1 || t.ctas_per_sm > 8) return fail(PERSEUS_GPU_ERRPARAM, "tuning.ctas_per_sm %d not in 1..8", t.ctas_per_sm);
+	// what actually fits: 227 KiB of shared memory and 2048 threads per SM
+	const int by_smem = (int)((227 * 1024) / ((size_t)t.stages * t.tile_bytes + 1024));
+	const int by_threads = 2048 / (pg::kConsumerThreads + pg::kProducerThreads);
+	if (t.ctas_per_sm > by_smem || t.ctas_per_sm > by_threads)
+		return fail(PERSEUS_GPU_ERRPARAM, "tuning: %d CTAs/SM do not fit (shared memory allows %d, threads allow %d)", t.ctas_per_sm, by_smem, by_threads);
+	if (t.store_mode < 1 || t.store_mode > 2) return fail(PERSEUS_GPU_ERRPARAM, "tuning.store_mode %d not in 0..2", t.store_mode);
+	return 0;
+}
+
+// flags -> format bits; 0 means "whatever output pointers are non-NULL"
+int resolve_fmt(unsigned flags, const void *out_i32, const void *out_f32, unsigned *fmt)
+{
+	unsigned f = flags & (PERSEUS_GPU_OUT_INT32 | PERSEUS_GPU_OUT_FLOAT | PERSEUS_GPU_OUT_FLOAT_POW2);
+	if (f == 0) f = (out_i32 ? PERSEUS_GPU_OUT_INT32 : 0u) | (out_f32 ? PERSEUS_GPU_OUT_FLOAT : 0u);
+	if ((f & PERSEUS_GPU_OUT_FLOAT) && (f & PERSEUS_GPU_OUT_FLOAT_POW2))
+		return fail(PERSEUS_GPU_ERRPARAM, "OUT_FLOAT and OUT_FLOAT_POW2 are mutually exclusive");
+	if (f == 0) return fail(PERSEUS_GPU_ERRPARAM, "no output requested");
+	if ((f & PERSEUS_GPU_OUT_INT32) && !out_i32) return fail(PERSEUS_GPU_ERRPARAM, "OUT_INT32 requested but out_i32 is NULL");
+	if ((f & (PERSEUS_GPU_OUT_FLOAT | PERSEUS_GPU_OUT_FLOAT_POW2)) && !out_f32)
+		return fail(PERSEUS_GPU_ERRPARAM, "float output requested but out_f32 is NULL");
+	*fmt = f;
+	return 0;
+}
+
+enum class Mem { Device, PinnedHost, PageableHost };
+
+Mem classify(const void *p)
+{
+	cudaPointerAttributes a{};
+	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+		cudaGetLastError();
+		return Mem::PageableHost;
+	}
+	switch (a.type) {
+	case cudaMemoryTypeDevice: return Mem::Device;
+	case cudaMemoryTypeManaged: return Mem::Device;
+	case cudaMemoryTypeHost: return Mem::PinnedHost;
+	default: return Mem::PageableHost;
+	}
+}
+
+int bind(perseus_gpu *h)
+{
+	if (!h) return fail(PERSEUS_GPU_NULLHANDLE, "null handle");
+	CU(h, cudaSetDevice(h->device));
+	return 0;
+}
+
+int ensure_staging(perseus_gpu *h, bool need_in, bool need_i32, bool need_f32)
+{
+	for (int s = 0; s < h->nstreams; ++s) {
+		if (need_in && !h->stage_in[s]) CU(h, cudaMalloc(&h->stage_in[s], h->chunk_bytes));
+		if (need_i32 && !h->stage_out[s][0]) CU(h, cudaMalloc(&h->stage_out[s][0], h->chunk_bytes / 6 * 8));
+		if (need_f32 && !h->stage_out[s][1]) CU(h, cudaMalloc(&h->stage_out[s][1], h->chunk_bytes / 6 * 8));
+	}
+	return 0;
+}
+
+int do_launch(perseus_gpu *h, const void *in, size_t nbytes, void *o_i32, void *o_f32, unsigned fmt, cudaStream_t st)
+{
+	int n = 0;
+	cudaError_t e = pg::launch_unpack(in, nbytes, o_i32, o_f32, fmt, h->tune, h->sm_count, st, &n);
+	if (e != cudaSuccess) return fail(PERSEUS_GPU_CUDAERR, "unpack kernel launch failed: %s", cudaGetErrorString(e));
+	h->stats.kernel_launches += (uint64_t)n;
+	h->stats.samples += nbytes / 6;
+	h->stats.bytes_in += nbytes / 6 * 6;
+	return 0;
+}
+
+// ---- streaming path -------------------------------------------------------------------------
+
+int ensure_streaming(perseus_gpu *h)
+{
+	if (h->streaming_ready) return 0;
+	const bool want_i32 = h->stream_fmt & PERSEUS_GPU_OUT_INT32;
+	const bool want_f32 = h->stream_fmt & (PERSEUS_GPU_OUT_FLOAT | PERSEUS_GPU_OUT_FLOAT_POW2);
+	for (int k = 0; k < h->nslabs; ++k) {
+		Slab &s = h->slabs[k];
+		CU(h, cudaHostAlloc(&s.host, h->slab_bytes, cudaHostAllocDefault));
+		CU(h, cudaMalloc(&s.dev_in, h->slab_bytes));
+		if (want_i32) CU(h, cudaMalloc(&s.dev_i32, h->slab_bytes / 6 * 8));
+		if (want_f32) CU(h, cudaMalloc(&s.dev_f32, h->slab_bytes / 6 * 8));
+		CU(h, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+	}
+	h->streaming_ready = true;
+	return 0;
+}
+
+// Writes finished slabs to the file sink, oldest first, up to and including `upto` (ring order).
+int drain_file(perseus_gpu *h, int count)
+{
+	for (int n = 0; n < count; ++n) {
+		Slab &s = h->slabs[h->next_to_write];
+		if (s.busy) {
+			CU(h, cudaEventSynchronize(s.done));
+			if (h->fout && s.out_bytes) {
+				if (fwrite(s.host_out, 1, s.out_bytes, h->fout) != s.out_bytes)
+					return fail(PERSEUS_GPU_IOERROR, "short write to stream file");
+			}
+			s.out_bytes = 0;
+			s.busy = false;
+		}
+		h->next_to_write = (h->next_to_write + 1) % h->nslabs;
+	}
+	return 0;
+}
+
+int submit_slab(perseus_gpu *h)
+{
+	Slab &s = h->slabs[h->cur];
+	const size_t nbytes = h->fill;
+	if (nbytes == 0) return 0;
+	cudaStream_t st = h->streams[h->cur % h->nstreams];
+	s.first_sample = h->samples_submitted;
+	CU(h, cudaMemcpyAsync(s.dev_in, s.host, nbytes, cudaMemcpyHostToDevice, st));
+	h->stats.h2d_bytes += nbytes;
+	int rc = do_launch(h, s.dev_in, nbytes, s.dev_i32, s.dev_f32, h->stream_fmt, st);
+	if (rc) return rc;
+	const uint64_t ns = nbytes / 6;
+	if (h->sink) {
+		perseus_gpu_block b{s.first_sample, ns, s.dev_i32, s.dev_f32, (void *)st};
+		h->sink(&b, h->sink_extra);
+	}
+	if (h->fout) {
+		// perseustest writes ONE format per run (-p selects float, perseustest.c:348-352)
+		const uint8_t *src = (h->stream_fmt & PERSEUS_GPU_OUT_INT32) ? s.dev_i32 : s.dev_f32;
+		if (!s.host_out) CU(h, cudaHostAlloc(&s.host_out, h->slab_bytes / 6 * 8, cudaHostAllocDefault));
+		CU(h, cudaMemcpyAsync(s.host_out, src, ns * 8, cudaMemcpyDeviceToHost, st));
+		h->stats.d2h_bytes += ns * 8;
+		s.out_bytes = ns * 8;
+	}
+	CU(h, cudaEventRecord(s.done, st));
+	s.busy = true;
+	h->samples_submitted += ns;
+	h->stats.slabs++;
+	h->fill = 0;
+	h->cur = (h->cur + 1) % h->nslabs;
+	// the slab we are about to fill must be free: back-pressure only when the ring is full
+	Slab &next = h->slabs[h->cur];
+	if (next.busy) {
+		if (cudaEventQuery(next.done) == cudaErrorNotReady) h->stats.stalls++;
+		cudaGetLastError();
+		// everything older than `next` (inclusive) completes in order
+		int count = (h->cur - h->next_to_write + h->nslabs) % h->nslabs + 1;
+		rc = drain_file(h, count);
+		if (rc) return rc;
+	}
+	return 0;
+}
+
+int stream_push(perseus_gpu *h, const uint8_t *buf, size_t nbytes)
+{
+	int rc = ensure_streaming(h);
+	if (rc) return rc;
+	while (nbytes) {
+		size_t room = h->slab_bytes - h->fill;
+		size_t n = nbytes < room ? nbytes : room;
+		memcpy(h->slabs[h->cur].host + h->fill, buf, n);
+		h->fill += n;
+		buf += n;
+		nbytes -= n;
+		if (h->fill == h->slab_bytes) {
+			rc = submit_slab(h);
+			if (rc) return rc;
+		}
+	}
+	return 0;
+}
+
+}  // namespace
+
+// =============================================================================== C ABI
+
+extern "C" {
+
+const char *perseus_gpu_errorstr(void) { return g_errstr; }
+
+const char *perseus_gpu_version(void) { return "perseus-gpu abi 1, sm_100a, " __DATE__; }
+
+int perseus_gpu_device_count(void)
+{
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess) {
+		cudaGetLastError();
+		return fail(PERSEUS_GPU_NODEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+	}
+	return n;
+}
+
+int perseus_gpu_device_info(int device, char *name, size_t name_len, int *sm_count, int *cc_major, int *cc_minor, uint64_t *total_mem)
+{
+	cudaDeviceProp p{};
+	cudaError_t e = cudaGetDeviceProperties(&p, device);
+	if (e != cudaSuccess) {
+		cudaGetLastError();
+		return fail(PERSEUS_GPU_NODEVICE, "cudaGetDeviceProperties(%d): %s", device, cudaGetErrorString(e));
+	}
+	if (name && name_len) snprintf(name, name_len, "%s", p.name);
+	if (sm_count) *sm_count = p.multiProcessorCount;
+	if (cc_major) *cc_major = p.major;
+	if (cc_minor) *cc_minor = p.minor;
+	if (total_mem) *total_mem = p.totalGlobalMem;
+	return 0;
+}
+
+int perseus_gpu_open(perseus_gpu **out, const perseus_gpu_config *ucfg)
+{
+	if (!out) return fail(PERSEUS_GPU_ERRPARAM, "null handle pointer");
+	*out = nullptr;
+	perseus_gpu_config cfg{};
+	if (ucfg) {
+		if (ucfg->struct_size < 8 || ucfg->struct_size > sizeof(cfg))
+			return fail(PERSEUS_GPU_ERRPARAM, "perseus_gpu_config.struct_size %u not understood (this library: %zu)", ucfg->struct_size, sizeof(cfg));
+		memcpy(&cfg, ucfg, ucfg->struct_size);
+	}
+	int ndev = perseus_gpu_device_count();
+	if (ndev <= 0) return ndev < 0 ? ndev : fail(PERSEUS_GPU_NODEVICE, "no CUDA device");
+	if (cfg.device < 0 || cfg.device >= ndev) return fail(PERSEUS_GPU_ERRPARAM, "device %d out of range (0..%d)", cfg.device, ndev - 1);
+	cudaDeviceProp prop{};
+	CU(nullptr, cudaGetDeviceProperties(&prop, cfg.device));
+	if (prop.major != 10)
+		return fail(PERSEUS_GPU_BADARCH, "device %d (%s) is sm_%d%d; this library carries sm_100a code only and has no fallback", cfg.device, prop.name,
+		            prop.major, prop.minor);
+
+	pg::Tuning tune = resolve_tuning(&cfg.tuning);
+	int rc = check_tuning(tune);
+	if (rc) return rc;
+	unsigned sfmt = cfg.stream_flags ? cfg.stream_flags : PERSEUS_GPU_OUT_INT32;
+	if (sfmt & ~(PERSEUS_GPU_OUT_INT32 | PERSEUS_GPU_OUT_FLOAT | PERSEUS_GPU_OUT_FLOAT_POW2))
+		return fail(PERSEUS_GPU_ERRPARAM, "stream_flags 0x%x has unknown bits", sfmt);
+	if ((sfmt & PERSEUS_GPU_OUT_FLOAT) && (sfmt & PERSEUS_GPU_OUT_FLOAT_POW2))
+		return fail(PERSEUS_GPU_ERRPARAM, "stream_flags: OUT_FLOAT and OUT_FLOAT_POW2 are mutually exclusive");
+	const uint32_t nslabs = cfg.nslabs ? cfg.nslabs : 4;
+	if (nslabs < 2 || nslabs > (uint32_t)kMaxSlabs) return fail(PERSEUS_GPU_ERRPARAM, "nslabs %u not in 2..%d", nslabs, kMaxSlabs);
+	const uint32_t nstreams = cfg.nstreams ? cfg.nstreams : 2;
+	if (nstreams < 1 || nstreams > (uint32_t)kMaxStreams) return fail(PERSEUS_GPU_ERRPARAM, "nstreams %u not in 1..%d", nstreams, kMaxStreams);
+	uint64_t slab = cfg.slab_bytes ? cfg.slab_bytes : (8ull << 20);
+	slab -= slab % 48;
+	uint64_t chunk = cfg.chunk_bytes ? cfg.chunk_bytes : (32ull << 20);
+	chunk -= chunk % 48;
+	if (slab < 48 || chunk < 48) return fail(PERSEUS_GPU_BUFFERSIZE, "slab_bytes/chunk_bytes must be at least 48");
+
+	perseus_gpu *h = new (std::nothrow) perseus_gpu();
+	if (!h) return fail(PERSEUS_GPU_NOMEM, "out of memory");
+	h->device = cfg.device;
+	h->sm_count = prop.multiProcessorCount;
+	h->cfg = cfg;
+	h->tune = tune;
+	h->stream_fmt = sfmt;
+	h->nslabs = (int)nslabs;
+	h->nstreams = (int)nstreams;
+	h->slab_bytes = (size_t)slab;
+	h->chunk_bytes = (size_t)chunk;
+	auto bail = [&](int code) {   // free what exists, keep the message of the original failure
+		char keep[sizeof(g_errstr)];
+		memcpy(keep, g_errstr, sizeof(keep));
+		perseus_gpu_close(h);
+		memcpy(g_errstr, keep, sizeof(keep));
+		return code;
+	};
+	cudaError_t e = cudaSetDevice(h->device);
+	if (e != cudaSuccess) return bail(fail(PERSEUS_GPU_CUDAERR, "cudaSetDevice(%d): %s", h->device, cudaGetErrorString(e)));
+	for (int s = 0; s < h->nstreams; ++s) {
+		e = cudaStreamCreateWithFlags(&h->streams[s], cudaStreamNonBlocking);
+		if (e != cudaSuccess) return bail(fail(PERSEUS_GPU_CUDAERR, "cudaStreamCreate: %s", cudaGetErrorString(e)));
+	}
+	for (int k = 0; k < kEventSlots; ++k) {
+		e = cudaEventCreate(&h->events[k]);
+		if (e != cudaSuccess) return bail(fail(PERSEUS_GPU_CUDAERR, "cudaEventCreate: %s", cudaGetErrorString(e)));
+	}
+	e = cudaMalloc(&h->d_scratch, 2 * sizeof(unsigned long long));
+	if (e == cudaSuccess) e = cudaHostAlloc(&h->h_scratch, 2 * sizeof(unsigned long long), cudaHostAllocDefault);
+	if (e != cudaSuccess) return bail(fail(PERSEUS_GPU_CUDAERR, "scratch allocation: %s", cudaGetErrorString(e)));
+	*out = h;
+	return ok();
+}
+
+int perseus_gpu_close(perseus_gpu *h)
+{
+	if (!h) return fail(PERSEUS_GPU_NULLHANDLE, "null handle");
+	int rc = 0;
+	if (cudaSetDevice(h->device) == cudaSuccess) {
+		if (h->streaming_ready) rc = perseus_gpu_flush(h);
+		for (int s = 0; s < h->nstreams; ++s)
+			if (h->streams[s]) cudaStreamSynchronize(h->streams[s]);
+		if (!rc) rc = surface_latched(h);
+		for (int k = 0; k < kMaxSlabs; ++k) {
+			Slab &s = h->slabs[k];
+			if (s.host) cudaFreeHost(s.host);
+			if (s.host_out) cudaFreeHost(s.host_out);
+			if (s.dev_in) cudaFree(s.dev_in);
+			if (s.dev_i32) cudaFree(s.dev_i32);
+			if (s.dev_f32) cudaFree(s.dev_f32);
+			if (s.done) cudaEventDestroy(s.done);
+		}
+		for (int s = 0; s < kMaxStreams; ++s) {
+			if (h->stage_in[s]) cudaFree(h->stage_in[s]);
+			if (h->stage_out[s][0]) cudaFree(h->stage_out[s][0]);
+			if (h->stage_out[s][1]) cudaFree(h->stage_out[s][1]);
+		}
+		if (h->d_scratch) cudaFree(h->d_scratch);
+		if (h->h_scratch) cudaFreeHost(h->h_scratch);
+		for (int k = 0; k < kEventSlots; ++k)
+			if (h->events[k]) cudaEventDestroy(h->events[k]);
+		for (int s = 0; s < h->nstreams; ++s)
+			if (h->streams[s]) cudaStreamDestroy(h->streams[s]);
+		cudaGetLastError();
+	}
+	if (h->fout) {
+		if (fclose(h->fout) != 0 && !rc) rc = fail(PERSEUS_GPU_IOERROR, "closing stream file failed");
+	}
+	delete h;
+	return rc;
+}
+
+int perseus_gpu_sync(perseus_gpu *h)
+{
+	int rc = bind(h);
+	if (rc) return rc;
+	for (int s = 0; s < h->nstreams; ++s) {
+		cudaError_t e = cudaStreamSynchronize(h->streams[s]);
+		if (e != cudaSuccess) {
+			fail(PERSEUS_GPU_CUDAERR, "stream %d: %s", s, cudaGetErrorString(e));
+			latch(h, PERSEUS_GPU_CUDAERR);
+		}
+	}
+	return surface_latched(h);
+}
+
+int64_t perseus_gpu_unpack(perseus_gpu *h, const void *buf, size_t nbytes, void *out_i32, void *out_f32, unsigned flags)
+{
+	int rc = bind(h);
+	if (rc) return rc;
+	if (flags & ~(PERSEUS_GPU_OUT_INT32 | PERSEUS_GPU_OUT_FLOAT | PERSEUS_GPU_OUT_FLOAT_POW2 | PERSEUS_GPU_ASYNC))
+		return fail(PERSEUS_GPU_ERRPARAM, "unknown flag bits 0x%x", flags);
+	unsigned fmt = 0;
+	rc = resolve_fmt(flags, out_i32, out_f32, &fmt);
+	if (rc) return rc;
+	if (!(fmt & PERSEUS_GPU_OUT_INT32)) out_i32 = nullptr;
+	if (!(fmt & (PERSEUS_GPU_OUT_FLOAT | PERSEUS_GPU_OUT_FLOAT_POW2))) out_f32 = nullptr;
+	const uint64_t ns = nbytes / 6;
+	if (ns == 0) return 0;
+	if (!buf) return fail(PERSEUS_GPU_ERRPARAM, "buf is NULL");
+	if ((out_i32 && ((uintptr_t)out_i32 & 3)) || (out_f32 && ((uintptr_t)out_f32 & 3)))
+		return fail(PERSEUS_GPU_ERRPARAM, "output pointers must be 4-byte aligned");
+
+	const Mem min_ = classify(buf);
+	const Mem mi = out_i32 ? classify(out_i32) : Mem::Device;
+	const Mem mf = out_f32 ? classify(out_f32) : Mem::Device;
+	const bool in_dev = min_ == Mem::Device, oi_dev = mi == Mem::Device, of_dev = mf == Mem::Device;
+
+	if (in_dev && oi_dev && of_dev) {
+		rc = do_launch(h, buf, ns * 6, out_i32, out_f32, fmt, h->streams[0]);
+		if (rc) return rc;
+	} else {
+		// staged pipeline: chunk c uses stream/slot c % nstreams; H2D, kernel and D2H of
+		// neighbouring chunks overlap, stream order protects slot reuse.
+		rc = ensure_staging(h, !in_dev, out_i32 && !oi_dev, out_f32 && !of_dev);
+		if (rc) return rc;
+		const uint8_t *src = static_cast<const uint8_t *>(buf);
+		const size_t total = ns * 6;
+		size_t off = 0;
+		for (int c = 0; off < total; ++c) {
+			const int s = c % h->nstreams;
+			cudaStream_t st = h->streams[s];
+			const size_t n = total - off < h->chunk_bytes ? total - off : h->chunk_bytes;
+			const size_t o = off / 6 * 8, on = n / 6 * 8;
+			const uint8_t *kin = src + off;
+			if (!in_dev) {
+				CU(h, cudaMemcpyAsync(h->stage_in[s], src + off, n, cudaMemcpyHostToDevice, st));
+				h->stats.h2d_bytes += n;
+				kin = h->stage_in[s];
+			}
+			uint8_t *ki = out_i32 ? (oi_dev ? static_cast<uint8_t *>(out_i32) + o : h->stage_out[s][0]) : nullptr;
+			uint8_t *kf = out_f32 ? (of_dev ? static_cast<uint8_t *>(out_f32) + o : h->stage_out[s][1]) : nullptr;
+			rc = do_launch(h, kin, n, ki, kf, fmt, st);
+			if (rc) return rc;
+			if (out_i32 && !oi_dev) {
+				CU(h, cudaMemcpyAsync(static_cast<uint8_t *>(out_i32) + o, ki, on, cudaMemcpyDeviceToHost, st));
+				h->stats.d2h_bytes += on;
+			}
+			if (out_f32 && !of_dev) {
+				CU(h, cudaMemcpyAsync(static_cast<uint8_t *>(out_f32) + o, kf, on, cudaMemcpyDeviceToHost, st));
+				h->stats.d2h_bytes += on;
+			}
+			off += n;
+		}
+	}
+	if (!(flags & PERSEUS_GPU_ASYNC)) {
+		rc = perseus_gpu_sync(h);
+		if (rc) return rc;
+	}
+	return (int64_t)ns;
+}
+
+// ---- batched ------------------------------------------------------------------------------------
+
+int perseus_gpu_plan_create(perseus_gpu *h, const perseus_gpu_seg *segs, int nseg, unsigned flags, perseus_gpu_plan **out)
+{
+	int rc = bind(h);
+	if (rc) return rc;
+	if (!out) return fail(PERSEUS_GPU_ERRPARAM, "null plan pointer");
+	*out = nullptr;
+	if (nseg < 0 || (nseg > 0 && !segs)) return fail(PERSEUS_GPU_ERRPARAM, "bad segment table");
+	unsigned fmt = flags & (PERSEUS_GPU_OUT_INT32 | PERSEUS_GPU_OUT_FLOAT | PERSEUS_GPU_OUT_FLOAT_POW2);
+	if (fmt == 0 && nseg > 0) fmt = (segs[0].out_i32 ? PERSEUS_GPU_OUT_INT32 : 0u) | (segs[0].out_f32 ? PERSEUS_GPU_OUT_FLOAT : 0u);
+	if ((fmt & PERSEUS_GPU_OUT_FLOAT) && (fmt & PERSEUS_GPU_OUT_FLOAT_POW2))
+		return fail(PERSEUS_GPU_ERRPARAM, "OUT_FLOAT and OUT_FLOAT_POW2 are mutually exclusive");
+	if (fmt == 0 && nseg > 0) return fail(PERSEUS_GPU_ERRPARAM, "no output requested");
+
+	const int tile = h->tune.tile_bytes;
+	std::vector<pg::SegDesc> hs((size_t)nseg);
+	std::vector<pg::TileRef> ht;
+	bool aligned = true;
+	uint64_t nsamples = 0, nbytes = 0;
+	for (int i = 0; i < nseg; ++i) {
+		const perseus_gpu_seg &s = segs[i];
+		const uint64_t used = (uint64_t)s.nbytes / 6 * 6;
+		if (used && !s.in) return fail(PERSEUS_GPU_ERRPARAM, "segment %d: in is NULL", i);
+		if (used && (fmt & PERSEUS_GPU_OUT_INT32) && !s.out_i32) return fail(PERSEUS_GPU_ERRPARAM, "segment %d: out_i32 is NULL", i);
+		if (used && (fmt & (PERSEUS_GPU_OUT_FLOAT | PERSEUS_GPU_OUT_FLOAT_POW2)) && !s.out_f32)
+			return fail(PERSEUS_GPU_ERRPARAM, "segment %d: out_f32 is NULL", i);
+		if (((uintptr_t)s.out_i32 & 3) || ((uintptr_t)s.out_f32 & 3)) return fail(PERSEUS_GPU_ERRPARAM, "segment %d: outputs must be 4-byte aligned", i);
+		hs[(size_t)i] = pg::SegDesc{static_cast<const uint8_t *>(s.in), s.nbytes, (fmt & PERSEUS_GPU_OUT_INT32) ? s.out_i32 : nullptr,
+		                            (fmt & (PERSEUS_GPU_OUT_FLOAT | PERSEUS_GPU_OUT_FLOAT_POW2)) ? s.out_f32 : nullptr};
+		if (((uintptr_t)s.in | (uintptr_t)hs[(size_t)i].out_i32 | (uintptr_t)hs[(size_t)i].out_f32) & 15) aligned = false;
+		const uint64_t nt = (used + (uint64_t)tile - 1) / (uint64_t)tile;
+		if (nt > 0xFFFFFFFFull) return fail(PERSEUS_GPU_BUFFERSIZE, "segment %d too large", i);
+		for (uint64_t t = 0; t < nt; ++t) ht.push_back(pg::TileRef{(uint32_t)i, (uint32_t)t});
+		nsamples += used / 6;
+		nbytes += used;
+	}
+	perseus_gpu_plan *p = new (std::nothrow) perseus_gpu_plan();
+	if (!p) return fail(PERSEUS_GPU_NOMEM, "out of memory");
+	p->ntiles = ht.size();
+	p->nsamples = nsamples;
+	p->nbytes = nbytes;
+	p->fmt = fmt;
+	p->tile_bytes = tile;
+	p->all_aligned = aligned;
+	cudaError_t e = cudaSuccess;
+	if (nseg) e = cudaMalloc(&p->d_segs, hs.size() * sizeof(pg::SegDesc));
+	if (e == cudaSuccess && !ht.empty()) e = cudaMalloc(&p->d_tiles, ht.size() * sizeof(pg::TileRef));
+	if (e == cudaSuccess && nseg) e = cudaMemcpyAsync(p->d_segs, hs.data(), hs.size() * sizeof(pg::SegDesc), cudaMemcpyHostToDevice, h->streams[0]);
+	if (e == cudaSuccess && !ht.empty())
+		e = cudaMemcpyAsync(p->d_tiles, ht.data(), ht.size() * sizeof(pg::TileRef), cudaMemcpyHostToDevice, h->streams[0]);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(h->streams[0]);   // hs/ht die with this frame
+	if (e != cudaSuccess) {
+		if (p->d_segs) cudaFree(p->d_segs);
+		if (p->d_tiles) cudaFree(p->d_tiles);
+		delete p;
+		return fail(PERSEUS_GPU_CUDAERR, "plan upload failed: %s", cudaGetErrorString(e));
+	}
+	*out = p;
+	return 0;
+}
+
+int64_t perseus_gpu_plan_run(perseus_gpu *h, perseus_gpu_plan *p, unsigned flags)
+{
+	int rc = bind(h);
+	if (rc) return rc;
+	if (!p) return fail(PERSEUS_GPU_ERRPARAM, "null plan");
+	if (p->tile_bytes != h->tune.tile_bytes)
+		return fail(PERSEUS_GPU_ERRPARAM, "plan was built for tile_bytes=%d, handle now uses %d", p->tile_bytes, h->tune.tile_bytes);
+	int n = 0;
+	cudaError_t e = pg::launch_unpack_batch(p->d_segs, p->d_tiles, p->ntiles, p->fmt, p->all_aligned, h->tune, h->sm_count, h->streams[0], &n);
+	if (e != cudaSuccess) return fail(PERSEUS_GPU_CUDAERR, "batched unpack launch failed: %s", cudaGetErrorString(e));
+	h->stats.kernel_launches += (uint64_t)n;
+	h->stats.samples += p->nsamples;
+	h->stats.bytes_in += p->nbytes;
+	if (!(flags & PERSEUS_GPU_ASYNC)) {
+		rc = perseus_gpu_sync(h);
+		if (rc) return rc;
+	}
+	return (int64_t)p->nsamples;
+}
+
+int perseus_gpu_plan_destroy(perseus_gpu *h, perseus_gpu_plan *p)
+{
+	int rc = bind(h);
+	if (rc) return rc;
+	if (!p) return 0;
+	cudaStreamSynchronize(h->streams[0]);
+	if (p->d_segs) cudaFree(p->d_segs);
+	if (p->d_tiles) cudaFree(p->d_tiles);
+	delete p;
+	return 0;
+}
+
+int64_t perseus_gpu_unpack_batch(perseus_gpu *h, const perseus_gpu_seg *segs, int nseg, unsigned flags)
+{
+	perseus_gpu_plan *p = nullptr;
+	int rc = perseus_gpu_plan_create(h, segs, nseg, flags, &p);
+	if (rc) return rc;
+	int64_t n = perseus_gpu_plan_run(h, p, 0);   // the plan is freed below, so always synchronous
+	perseus_gpu_plan_destroy(h, p);
+	return n;
+}
+
+// ---- streaming hand-off -----------------------------------------------------------------------------
+
+int perseus_gpu_input_callback(void *buf, int buf_size, void *extra)
+{
+	perseus_gpu *h = static_cast<perseus_gpu *>(extra);
+	if (!h || !buf || buf_size < 6) return 0;
+	if (h->latched) return 0;                      // a previous failure is waiting to be reported
+	h->stats.callbacks++;
+	if (cudaSetDevice(h->device) != cudaSuccess) { // foreign thread (libusb poll thread): bind first
+		fail(PERSEUS_GPU_CUDAERR, "cudaSetDevice(%d) failed in callback", h->device);
+		latch(h, PERSEUS_GPU_CUDAERR);
+		return 0;
+	}
+	// perseustest.c:443 — only whole samples of THIS transfer count
+	const size_t n = (size_t)buf_size / 6 * 6;
+	int rc = stream_push(h, static_cast<const uint8_t *>(buf), n);
+	if (rc) latch(h, rc);
+	return 0;
+}
+
+int perseus_gpu_set_sink(perseus_gpu *h, perseus_gpu_sink sink, void *extra)
+{
+	if (!h) return fail(PERSEUS_GPU_NULLHANDLE, "null handle");
+	h->sink = sink;
+	h->sink_extra = extra;
+	return 0;
+}
+
+int perseus_gpu_stream_to_file(perseus_gpu *h, const char *path)
+{
+	int rc = bind(h);
+	if (rc) return rc;
+	rc = perseus_gpu_flush(h);
+	if (rc) return rc;
+	if (h->fout) {
+		FILE *f = h->fout;
+		h->fout = nullptr;
+		if (fclose(f) != 0) return fail(PERSEUS_GPU_IOERROR, "closing stream file failed");
+	}
+	if (!path) return 0;
+	const unsigned f = h->stream_fmt;
+	if ((f & PERSEUS_GPU_OUT_INT32) && (f & (PERSEUS_GPU_OUT_FLOAT | PERSEUS_GPU_OUT_FLOAT_POW2)))
+		return fail(PERSEUS_GPU_ERRPARAM, "a stream file holds one format (perseustest -p selects it); open the handle with a single stream format");
+	h->fout = fopen(path, "wb");
+	if (!h->fout) return fail(PERSEUS_GPU_IOERROR, "cannot open %s for writing", path);
+	return 0;
+}
+
+int perseus_gpu_flush(perseus_gpu *h)
+{
+	int rc = bind(h);
+	if (rc) return rc;
+	if (h->streaming_ready) {
+		if (h->fill && !h->latched) {
+			rc = submit_slab(h);
+			if (rc) latch(h, rc);
+		}
+		rc = drain_file(h, h->nslabs);   // oldest first, so the file keeps stream order
+		if (rc) latch(h, rc);
+		h->next_to_write = h->cur;       // nothing in flight: the next slab submitted is the oldest
+		if (h->fout) fflush(h->fout);
+	}
+	return perseus_gpu_sync(h);
+}
+
+int perseus_gpu_get_stats(perseus_gpu *h, perseus_gpu_stats *out)
+{
+	if (!h) return fail(PERSEUS_GPU_NULLHANDLE, "null handle");
+	if (!out) return fail(PERSEUS_GPU_ERRPARAM, "null stats pointer");
+	*out = h->stats;
+	return 0;
+}
+
+int perseus_gpu_set_tuning(perseus_gpu *h, const perseus_gpu_tuning *t)
+{
+	if (!h) return fail(PERSEUS_GPU_NULLHANDLE, "null handle");
+	pg::Tuning r = resolve_tuning(t);
+	int rc = check_tuning(r);
+	if (rc) return rc;
+	h->tune = r;
+	return 0;
+}
+
+int perseus_gpu_get_tuning(perseus_gpu *h, perseus_gpu_tuning *t)
+{
+	if (!h) return fail(PERSEUS_GPU_NULLHANDLE, "null handle");
+	if (!t) return fail(PERSEUS_GPU_ERRPARAM, "null tuning pointer");
+	memset(t, 0, sizeof(*t));
+	t->variant = h->tune.variant;
+	t->tile_bytes = h->tune.tile_bytes;
+	t->stages = h->tune.stages;
+	t->ctas_per_sm = h->tune.ctas_per_sm;
+	t->store_mode = h->tune.store_mode;
+	return 0;
+}
+
+// ---- plumbing ---------------------------------------------------------------------------------------
+
+void *perseus_gpu_dev_alloc(perseus_gpu *h, size_t nbytes)
+{
+	if (bind(h)) return nullptr;
+	void *p = nullptr;
+	cudaError_t e = cudaMalloc(&p, nbytes ? nbytes : 1);
+	if (e != cudaSuccess) {
+		cudaGetLastError();
+		fail(PERSEUS_GPU_NOMEM, "cudaMalloc(%zu): %s", nbytes, cudaGetErrorString(e));
+		return nullptr;
+	}
+	return p;
+}
+
+int perseus_gpu_dev_free(perseus_gpu *h, void *p)
+{
+	int rc = bind(h);
+	if (rc) return rc;
+	CU(h, cudaFree(p));
+	return 0;
+}
+
+void *perseus_gpu_host_alloc(perseus_gpu *h, size_t nbytes)
+{
+	if (bind(h)) return nullptr;
+	void *p = nullptr;
+	cudaError_t e = cudaHostAlloc(&p, nbytes ? nbytes : 1, cudaHostAllocPortable);
+	if (e != cudaSuccess) {
+		cudaGetLastError();
+		fail(PERSEUS_GPU_NOMEM, "cudaHostAlloc(%zu): %s", nbytes, cudaGetErrorString(e));
+		return nullptr;
+	}
+	return p;
+}
+
+int perseus_gpu_host_free(perseus_gpu *h, void *p)
+{
+	int rc = bind(h);
+	if (rc) return rc;
+	CU(h, cudaFreeHost(p));
+	return 0;
+}
+
+int perseus_gpu_memcpy(perseus_gpu *h, void *dst, const void *src, size_t nbytes)
+{
+	int rc = bind(h);
+	if (rc) return rc;
+	if (nbytes == 0) return 0;
+	CU(h, cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDefault, h->streams[0]));
+	CU(h, cudaStreamSynchronize(h->streams[0]));
+	return 0;
+}
+
+int perseus_gpu_memset(perseus_gpu *h, void *dev, int byte, size_t nbytes)
+{
+	int rc = bind(h);
+	if (rc) return rc;
+	if (nbytes == 0) return 0;
+	CU(h, cudaMemsetAsync(dev, byte, nbytes, h->streams[0]));
+	CU(h, cudaStreamSynchronize(h->streams[0]));
+	return 0;
+}
+
+void *perseus_gpu_get_stream(perseus_gpu *h, int idx)
+{
+	if (!h || idx < 0 || idx >= h->nstreams) {
+		fail(PERSEUS_GPU_ERRPARAM, "stream index out of range");
+		return nullptr;
+	}
+	return (void *)h->streams[idx];
+}
+
+int perseus_gpu_event_record(perseus_gpu *h, int slot)
+{
+	int rc = bind(h);
+	if (rc) return rc;
+	if (slot < 0 || slot >= kEventSlots) return fail(PERSEUS_GPU_ERRPARAM, "event slot %d not in 0..%d", slot, kEventSlots - 1);
+	CU(h, cudaEventRecord(h->events[slot], h->streams[0]));
+	return 0;
+}
+
+int perseus_gpu_event_elapsed_ms(perseus_gpu *h, int a, int b, float *ms)
+{
+	int rc = bind(h);
+	if (rc) return rc;
+	if (a < 0 || a >= kEventSlots || b < 0 || b >= kEventSlots || !ms) return fail(PERSEUS_GPU_ERRPARAM, "bad event slots");
+	CU(h, cudaEventSynchronize(h->events[b]));
+	CU(h, cudaEventElapsedTime(ms, h->events[a], h->events[b]));
+	return 0;
+}
+
+// ---- synthetic data / verification --------------------------------------------------------------------
+
+int perseus_gpu_generate(perseus_gpu *h, void *dev_dst, size_t nbytes, int pattern, uint64_t seed, uint64_t byte_offset)
+{
+	int rc = bind(h);
+	if (rc) return rc;
+	if (pattern != PERSEUS_SYNTH_RANDOM && pattern != PERSEUS_SYNTH_RAMP) return fail(PERSEUS_GPU_ERRPARAM, "unknown pattern %d", pattern);
+	if (pattern == PERSEUS_SYNTH_RAMP && byte_offset % 6) return fail(PERSEUS_GPU_ERRPARAM, "RAMP byte_offset must be a multiple of 6");
+	if (nbytes && !dev_dst) return fail(PERSEUS_GPU_ERRPARAM, "null destination");
+	cudaError_t e = pg::launch_generate(dev_dst, nbytes, pattern, seed, byte_offset, h->streams[0]);
+	if (e != cudaSuccess) return fail(PERSEUS_GPU_CUDAERR, "generate launch failed: %s", cudaGetErrorString(e));
+	h->stats.kernel_launches += nbytes ? 1 : 0;
+	CU(h, cudaStreamSynchronize(h->streams[0]));
+	return 0;
+}
+
+int perseus_synth_fill(void *host_dst, size_t nbytes, int pattern, uint64_t seed, uint64_t byte_offset)
+{
+	if (pattern != PERSEUS_SYNTH_RANDOM && pattern != PERSEUS_SYNTH_RAMP) return fail(PERSEUS_GPU_ERRPARAM, "unknown pattern %d", pattern);
+	if (pattern == PERSEUS_SYNTH_RAMP && byte_offset % 6) return fail(PERSEUS_GPU_ERRPARAM, "RAMP byte_offset must be a multiple of 6");
+	if (nbytes && !host_dst) return fail(PERSEUS_GPU_ERRPARAM, "null destination");
+	pg::host_generate(static_cast<uint8_t *>(host_dst), nbytes, pattern, seed, byte_offset);
+	return 0;
+}
+
+int perseus_gpu_checksum(perseus_gpu *h, const void *dev_words, size_t nwords, uint64_t first_index, uint64_t *sum)
+{
+	int rc = bind(h);
+	if (rc) return rc;
+	if (!sum || (nwords && !dev_words)) return fail(PERSEUS_GPU_ERRPARAM, "null argument");
+	if ((uintptr_t)dev_words & 3) return fail(PERSEUS_GPU_ERRPARAM, "words must be 4-byte aligned");
+	cudaError_t e = pg::launch_checksum(dev_words, nwords, first_index, h->d_scratch, h->streams[0]);
+	if (e != cudaSuccess) return fail(PERSEUS_GPU_CUDAERR, "checksum launch failed: %s", cudaGetErrorString(e));
+	h->stats.kernel_launches += nwords ? 1 : 0;
+	CU(h, cudaMemcpyAsync(h->h_scratch, h->d_scratch, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->streams[0]));
+	CU(h, cudaStreamSynchronize(h->streams[0]));
+	*sum = h->h_scratch[0];
+	return 0;
+}
+
+int perseus_gpu_verify(perseus_gpu *h, const void *dev_in, size_t nbytes, const void *dev_i32, const void *dev_f32, unsigned flags,
+                       uint64_t *nmismatch, uint64_t *first_bad_word)
+{
+	int rc = bind(h);
+	if (rc) return rc;
+	unsigned fmt = 0;
+	rc = resolve_fmt(flags & ~PERSEUS_GPU_ASYNC, dev_i32, dev_f32, &fmt);
+	if (rc) return rc;
+	cudaError_t e = pg::launch_verify(dev_in, nbytes, dev_i32, dev_f32, fmt, h->d_scratch, h->streams[0]);
+	if (e != cudaSuccess) return fail(PERSEUS_GPU_CUDAERR, "verify launch failed: %s", cudaGetErrorString(e));
+	h->stats.kernel_launches += nbytes / 6 ? 1 : 0;
+	CU(h, cudaMemcpyAsync(h->h_scratch, h->d_scratch, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->streams[0]));
+	CU(h, cudaStreamSynchronize(h->streams[0]));
+	if (nmismatch) *nmismatch = h->h_scratch[0];
+	if (first_bad_word) *first_bad_word = h->h_scratch[1];
+	if (h->h_scratch[0])
+		return fail(PERSEUS_GPU_MISMATCH, "%llu output words differ from the per-sample recomputation (first at word %llu)", h->h_scratch[0], h->h_scratch[1]);
+	return 0;
+}
+
+int perseus_gpu_shard_range(uint64_t total, int nshards, int shard, uint64_t *first, uint64_t *count)
+{
+	if (nshards < 1 || shard < 0 || shard >= nshards || !first || !count) return fail(PERSEUS_GPU_ERRPARAM, "bad shard arguments");
+	// floor(shard*total/nshards) without overflowing 64 bits
+	const unsigned __int128 t = total;
+	const uint64_t a = (uint64_t)(t * (unsigned)shard / (unsigned)nshards);
+	const uint64_t b = (uint64_t)(t * (unsigned)(shard + 1) / (unsigned)nshards);
+	*first = a;
+	*count = b - a;
+	return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,659 @@
+// sm_100a kernels for the Perseus 24-bit I/Q unpack.
+//
+// What they compute is fixed by the reference's two example callbacks
+//   /root/reference/examples/perseustest.c:432-460  (int32, MSB aligned:  b0<<8 | b1<<16 | b2<<24)
+//   /root/reference/examples/perseustest.c:466-502  (float: (float)int32 / (INT_MAX-256))
+// How they compute it is B200-first: the stream is pure byte shuffling bound by HBM
+// (6 B read + 8 B written per complex sample), so the design goal is bytes in flight and
+// perfectly coalesced 16-byte traffic, not arithmetic:
+//
+//   unpack24_stream_kernel   persistent CTAs; a producer lane moves 6/12/24 KiB tiles of wire
+//                            bytes HBM -> shared memory with TMA bulk copies (cp.async.bulk,
+//                            mbarrier complete_tx) through a multi-stage ring; 8 consumer warps
+//                            read each 12-byte unit (2 samples) as 3 conflict-free LDS.32
+//                            (stride 3 words is coprime with 32 banks), realign the 3-byte
+//                            fields with funnel shifts, and write one coalesced STG.128 per unit.
+//   unpack24_direct_kernel   register-only fallback for pointers that are not 16-byte aligned
+//                            (legacy 510-byte transfers, ring seams), and an A/B variant.
+//   verify/checksum/generate test + bench plumbing that must run at HBM scale (64 GiB recordings).
+//
+// No tensor cores: there is no multiply-accumulate structure to map onto tcgen05.
+#include "kernels.h"
+
+#include <cstring>
+
+namespace pg {
+namespace {
+
+// ------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+	asm volatile(
+	    "{\n"
+	    ".reg .pred P1;\n"
+	    "LAB_WAIT:\n"
+	    "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+	    "@P1 bra DONE;\n"
+	    "bra LAB_WAIT;\n"
+	    "DONE:\n"
+	    "}" ::"r"(bar), "r"(parity)
+	    : "memory");
+}
+__device__ __forceinline__ uint64_t l2_evict_first_policy()
+{
+	uint64_t pol;
+	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+	return pol;
+}
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t pol)
+{
+	asm volatile(
+	    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+	    "l"(src), "r"(bytes), "r"(bar), "l"(pol)
+	    : "memory");
+}
+
+template <int ST>
+__device__ __forceinline__ void store16(void *p, uint4 v)
+{
+	if (ST == 2) *reinterpret_cast<uint4 *>(p) = v;
+	else __stcs(reinterpret_cast<uint4 *>(p), v);   // st.global.cs: written once, never re-read here
+}
+
+// ------------------------------------------------------------------ the arithmetic
+// (float)int32 / (INT_MAX-256) == (float)int32 * 0x30000001 for every MSB-aligned 24-bit value
+// (re-proved exhaustively on the device by tests/test_gpu_parity.py).
+__device__ __forceinline__ float to_float_ref(uint32_t x) { return __fmul_rn(__int2float_rn((int)x), __uint_as_float(0x30000001u)); }
+__device__ __forceinline__ float to_float_pow2(uint32_t x) { return __fmul_rn(__int2float_rn((int)x), __uint_as_float(0x30000000u)); }
+
+template <unsigned FMT>
+__device__ __forceinline__ float to_float(uint32_t x) { return (FMT & FMT_POW2) ? to_float_pow2(x) : to_float_ref(x); }
+
+// One unit = 12 wire bytes = 2 complex samples, held as three little-endian words:
+//   w0 = I0 I1 I2 Q0   w1 = Q1 Q2 I0' I1'   w2 = I2' Q0' Q1' Q2'
+// Each output word is its 3-byte field moved to bytes 1..3 with byte 0 cleared.
+__device__ __forceinline__ uint4 unit_to_i32(uint32_t w0, uint32_t w1, uint32_t w2)
+{
+	uint4 o;
+	o.x = w0 << 8;
+	o.y = __funnelshift_l(w0, w1, 16) & 0xFFFFFF00u;
+	o.z = __funnelshift_r(w1, w2, 8) & 0xFFFFFF00u;
+	o.w = w2 & 0xFFFFFF00u;
+	return o;
+}
+
+template <unsigned FMT, int ST>
+__device__ __forceinline__ void emit_unit(uint32_t w0, uint32_t w1, uint32_t w2, uint8_t *o_i32, uint8_t *o_f32, size_t unit)
+{
+	const uint4 v = unit_to_i32(w0, w1, w2);
+	if (FMT & FMT_I32) store16<ST>(o_i32 + unit * 16, v);
+	if (FMT & (FMT_F32 | FMT_POW2)) {
+		uint4 f;
+		f.x = __float_as_uint(to_float<FMT>(v.x));
+		f.y = __float_as_uint(to_float<FMT>(v.y));
+		f.z = __float_as_uint(to_float<FMT>(v.z));
+		f.w = __float_as_uint(to_float<FMT>(v.w));
+		store16<ST>(o_f32 + unit * 16, f);
+	}
+}
+
+// Scalar path for the few samples a vector path cannot cover (ragged ends, odd counts).
+template <unsigned FMT>
+__device__ __forceinline__ void emit_sample_bytes(const uint8_t *src, uint8_t *o_i32, uint8_t *o_f32, size_t k)
+{
+	const uint8_t *s = src + 6 * k;
+	const uint32_t i = ((uint32_t)s[0] << 8) | ((uint32_t)s[1] << 16) | ((uint32_t)s[2] << 24);
+	const uint32_t q = ((uint32_t)s[3] << 8) | ((uint32_t)s[4] << 16) | ((uint32_t)s[5] << 24);
+	if (FMT & FMT_I32) {
+		uint32_t *o = reinterpret_cast<uint32_t *>(o_i32) + 2 * k;
+		o[0] = i; o[1] = q;
+	}
+	if (FMT & (FMT_F32 | FMT_POW2)) {
+		float *o = reinterpret_cast<float *>(o_f32) + 2 * k;
+		o[0] = to_float<FMT>(i); o[1] = to_float<FMT>(q);
+	}
+}
+
+// ------------------------------------------------------------------ stream kernel
+struct StreamParams {
+	const uint8_t *in;        // flat: wire bytes (16-byte aligned)
+	uint8_t *out_i32, *out_f32;
+	uint64_t in_bytes;        // flat: 6 * nsamples
+	uint64_t ntiles;
+	const SegDesc *segs;      // batched
+	const TileRef *tiles;
+	int stages;
+};
+
+struct TileHdr {              // written by the producer lane, read by the consumers of that stage
+	const uint8_t *src;
+	uint8_t *o_i32, *o_f32;
+	uint32_t valid;           // wire bytes of this tile that hold whole samples (<= TILE)
+	uint32_t pad;
+};
+
+template <unsigned FMT, int TILE, int ST, bool BATCHED>
+__global__ void __launch_bounds__(kConsumerThreads + kProducerThreads)
+unpack24_stream_kernel(const __grid_constant__ StreamParams p)
+{
+	static_assert(TILE % 48 == 0 && (TILE / 12) % kConsumerThreads == 0, "tile must keep 16-byte phase and split evenly");
+	constexpr int kPasses = TILE / 12 / kConsumerThreads;
+
+	extern __shared__ __align__(128) uint8_t ring[];
+	__shared__ __align__(8) uint64_t full_bar[kMaxStages];
+	__shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+	__shared__ TileHdr hdr[kMaxStages];
+
+	const int tid = threadIdx.x;
+	const int nstages = p.stages;
+
+	if (tid == 0) {
+		for (int s = 0; s < nstages; ++s) {
+			mbar_init(smem_u32(&full_bar[s]), 1);
+			mbar_init(smem_u32(&empty_bar[s]), kConsumerThreads / 32);
+		}
+		fence_mbar_init();
+	}
+	__syncthreads();
+
+	if (tid >= kConsumerThreads) {
+		// ---------------- producer warp: one lane drives the TMA
+		if (tid == kConsumerThreads) {
+			const uint64_t pol = l2_evict_first_policy();   // wire bytes are read exactly once
+			int s = 0;
+			uint32_t phase = 0;
+			for (uint64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+				TileHdr h;
+				if (BATCHED) {
+					const TileRef r = p.tiles[tile];
+					const SegDesc sd = p.segs[r.seg];
+					const uint8_t *seg_in = sd.in;
+					const uint64_t used = sd.nbytes / 6 * 6;
+					uint8_t *oi = static_cast<uint8_t *>(sd.out_i32);
+					uint8_t *of = static_cast<uint8_t *>(sd.out_f32);
+					const uint64_t off = (uint64_t)r.tile * TILE;
+					const uint64_t left = used - off;
+					h.src = seg_in + off;
+					h.o_i32 = oi + off / 6 * 8;
+					h.o_f32 = of + off / 6 * 8;
+					h.valid = left < (uint64_t)TILE ? (uint32_t)left : (uint32_t)TILE;
+				} else {
+					const uint64_t off = tile * TILE;
+					const uint64_t left = p.in_bytes - off;
+					h.src = p.in + off;
+					h.o_i32 = p.out_i32 + off / 6 * 8;
+					h.o_f32 = p.out_f32 + off / 6 * 8;
+					h.valid = left < (uint64_t)TILE ? (uint32_t)left : (uint32_t)TILE;
+				}
+				h.pad = 0;
+				mbar_wait(smem_u32(&empty_bar[s]), phase ^ 1);   // consumers released this stage
+				hdr[s] = h;
+				const uint32_t bulk = h.valid & ~15u;             // bulk copies move multiples of 16 bytes
+				if (bulk) {
+					mbar_arrive_expect_tx(smem_u32(&full_bar[s]), bulk);
+					bulk_g2s(smem_u32(ring + (size_t)s * TILE), h.src, bulk, smem_u32(&full_bar[s]), pol);
+				} else {
+					mbar_arrive(smem_u32(&full_bar[s]));
+				}
+				if (++s == nstages) { s = 0; phase ^= 1; }
+			}
+		}
+		return;
+	}
+
+	// ---------------- consumers: smem -> registers -> coalesced 16-byte stores
+	int s = 0;
+	uint32_t phase = 0;
+	for (uint64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+		mbar_wait(smem_u32(&full_bar[s]), phase);
+		const TileHdr h = hdr[s];
+		const uint32_t *w = reinterpret_cast<const uint32_t *>(ring + (size_t)s * TILE);
+		if (h.valid == (uint32_t)TILE) {
+			uint32_t r[kPasses][3];
+#pragma unroll
+			for (int k = 0; k < kPasses; ++k) {
+				const int u = k * kConsumerThreads + tid;
+				r[k][0] = w[3 * u];
+				r[k][1] = w[3 * u + 1];
+				r[k][2] = w[3 * u + 2];
+			}
+#pragma unroll
+			for (int k = 0; k < kPasses; ++k)
+				emit_unit<FMT, ST>(r[k][0], r[k][1], r[k][2], h.o_i32, h.o_f32, (size_t)(k * kConsumerThreads + tid));
+		} else {
+			// ragged last tile of a buffer/segment: units that lie inside the bulk-copied part
+			// come from smem, the (at most 5) samples after it straight from global memory.
+			const uint32_t nunits = (h.valid & ~15u) / 12;
+			for (uint32_t u = tid; u < nunits; u += kConsumerThreads)
+				emit_unit<FMT, ST>(w[3 * u], w[3 * u + 1], w[3 * u + 2], h.o_i32, h.o_f32, u);
+			const uint32_t ns = h.valid / 6;
+			for (uint32_t k = 2 * nunits + tid; k < ns; k += kConsumerThreads)
+				emit_sample_bytes<FMT>(h.src, h.o_i32, h.o_f32, k);
+		}
+		__syncwarp();
+		if ((tid & 31) == 0) mbar_arrive(smem_u32(&empty_bar[s]));
+		if (++s == nstages) { s = 0; phase ^= 1; }
+	}
+}
+
+// ------------------------------------------------------------------ direct kernel
+struct DirectParams {
+	const uint8_t *in;
+	uint8_t *out_i32, *out_f32;
+	uint64_t nsamples;
+	const SegDesc *segs;      // batched
+	const TileRef *tiles;
+	uint64_t ntiles;
+	int tile_bytes;
+};
+
+__device__ __forceinline__ void load_unit_bytes(const uint8_t *s, uint32_t &w0, uint32_t &w1, uint32_t &w2)
+{
+	w0 = s[0] | (s[1] << 8) | (s[2] << 16) | ((uint32_t)s[3] << 24);
+	w1 = s[4] | (s[5] << 8) | (s[6] << 16) | ((uint32_t)s[7] << 24);
+	w2 = s[8] | (s[9] << 8) | (s[10] << 16) | ((uint32_t)s[11] << 24);
+}
+
+template <unsigned FMT>
+__device__ __forceinline__ void emit_unit_words(uint32_t w0, uint32_t w1, uint32_t w2, uint8_t *o_i32, uint8_t *o_f32, size_t unit)
+{
+	const uint4 v = unit_to_i32(w0, w1, w2);
+	if (FMT & FMT_I32) {
+		uint32_t *o = reinterpret_cast<uint32_t *>(o_i32) + 4 * unit;
+		o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+	}
+	if (FMT & (FMT_F32 | FMT_POW2)) {
+		float *o = reinterpret_cast<float *>(o_f32) + 4 * unit;
+		o[0] = to_float<FMT>(v.x); o[1] = to_float<FMT>(v.y); o[2] = to_float<FMT>(v.z); o[3] = to_float<FMT>(v.w);
+	}
+}
+
+// ALIGNED: in % 4 == 0 and outputs % 16 == 0 -> 3 LDG.32 (a warp reads 384 contiguous bytes)
+// and one STG.128 per unit, four units in flight per thread.  Otherwise byte loads, word stores.
+template <unsigned FMT, int ST, bool ALIGNED>
+__global__ void __launch_bounds__(256) unpack24_direct_kernel(const __grid_constant__ DirectParams p)
+{
+	const uint64_t nunits = p.nsamples / 2;
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (ALIGNED) {
+		const uint32_t *w = reinterpret_cast<const uint32_t *>(p.in);
+		for (; u + 3 * stride < nunits; u += 4 * stride) {
+			uint32_t r[4][3];
+#pragma unroll
+			for (int k = 0; k < 4; ++k) {
+				const uint64_t uu = u + k * stride;
+				r[k][0] = __ldg(w + 3 * uu);
+				r[k][1] = __ldg(w + 3 * uu + 1);
+				r[k][2] = __ldg(w + 3 * uu + 2);
+			}
+#pragma unroll
+			for (int k = 0; k < 4; ++k) emit_unit<FMT, ST>(r[k][0], r[k][1], r[k][2], p.out_i32, p.out_f32, u + k * stride);
+		}
+		for (; u < nunits; u += stride)
+			emit_unit<FMT, ST>(__ldg(w + 3 * u), __ldg(w + 3 * u + 1), __ldg(w + 3 * u + 2), p.out_i32, p.out_f32, u);
+	} else {
+		for (; u < nunits; u += stride) {
+			uint32_t w0, w1, w2;
+			load_unit_bytes(p.in + 12 * u, w0, w1, w2);
+			emit_unit_words<FMT>(w0, w1, w2, p.out_i32, p.out_f32, u);
+		}
+	}
+	if ((p.nsamples & 1) && blockIdx.x == 0 && threadIdx.x == 0)
+		emit_sample_bytes<FMT>(p.in, p.out_i32, p.out_f32, p.nsamples - 1);
+}
+
+// Batched fallback for segments that are not 16-byte aligned: one CTA per tile, byte loads.
+template <unsigned FMT>
+__global__ void __launch_bounds__(256) unpack24_direct_batch_kernel(const __grid_constant__ DirectParams p)
+{
+	for (uint64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+		const TileRef r = p.tiles[tile];
+		const SegDesc sd = p.segs[r.seg];
+		const uint64_t off = (uint64_t)r.tile * p.tile_bytes;
+		const uint64_t left = sd.nbytes / 6 * 6 - off;
+		const uint32_t ns = (uint32_t)((left < (uint64_t)p.tile_bytes ? left : (uint64_t)p.tile_bytes) / 6);
+		uint8_t *oi = reinterpret_cast<uint8_t *>(sd.out_i32) + off / 6 * 8;
+		uint8_t *of = reinterpret_cast<uint8_t *>(sd.out_f32) + off / 6 * 8;
+		for (uint32_t k = threadIdx.x; k < ns; k += blockDim.x) emit_sample_bytes<FMT>(sd.in + off, oi, of, k);
+	}
+}
+
+// ------------------------------------------------------------------ generator / checksum / verify
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x)
+{
+	x += 0x9E3779B97F4A7C15ull;
+	x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+	x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+	return x ^ (x >> 31);
+}
+
+// Stream word w (8 bytes, little endian) = splitmix64(seed + w); dst[i] is stream byte byte_offset + i.
+__global__ void __launch_bounds__(256) generate_random_kernel(uint8_t *dst, uint64_t nbytes, uint64_t seed, uint64_t byte_offset)
+{
+	const uint64_t w_first = byte_offset >> 3;
+	const uint64_t nwords = ((byte_offset + nbytes + 7) >> 3) - w_first;
+	const bool fast = ((byte_offset & 7) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0);
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	for (uint64_t wi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; wi < nwords; wi += stride) {
+		const uint64_t word = splitmix64(seed + w_first + wi);
+		const int64_t base = (int64_t)((w_first + wi) << 3) - (int64_t)byte_offset;   // index of the word's byte 0 in dst
+		if (fast && (uint64_t)base + 8 <= nbytes) {
+			*reinterpret_cast<uint64_t *>(dst + base) = word;
+		} else {
+			for (int b = 0; b < 8; ++b) {
+				const int64_t i = base + b;
+				if (i >= 0 && (uint64_t)i < nbytes) dst[i] = (uint8_t)(word >> (8 * b));
+			}
+		}
+	}
+}
+
+__host__ __device__ __forceinline__ void ramp_sample(uint64_t v64, uint8_t *p)
+{
+	const uint32_t v = (uint32_t)v64;
+	const uint32_t i24 = v & 0xFFFFFFu;
+	const uint32_t q24 = (uint32_t)(v * 2654435761u) >> 8;
+	p[0] = (uint8_t)i24; p[1] = (uint8_t)(i24 >> 8); p[2] = (uint8_t)(i24 >> 16);
+	p[3] = (uint8_t)q24; p[4] = (uint8_t)(q24 >> 8); p[5] = (uint8_t)(q24 >> 16);
+}
+
+__global__ void __launch_bounds__(256) generate_ramp_kernel(uint8_t *dst, uint64_t nsamples, uint64_t first_sample)
+{
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nsamples; k += stride)
+		ramp_sample(first_sample + k, dst + 6 * k);
+}
+
+__global__ void __launch_bounds__(256) checksum32_kernel(const uint32_t *w, uint64_t nwords, uint64_t first_index, unsigned long long *sum)
+{
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	unsigned long long acc = 0;
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += stride)
+		acc += (splitmix64(first_index + i) | 1ull) * ((unsigned long long)__ldg(w + i) + 1ull);
+	for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+	if ((threadIdx.x & 31) == 0 && acc) atomicAdd(sum, acc);
+}
+
+// Independent restatement for on-device verification: one thread per sample, six byte loads,
+// shifts, and a true IEEE division for the reference float scale (not the multiply the product uses).
+__global__ void __launch_bounds__(256) verify_kernel(const uint8_t *in, uint64_t nsamples, const uint32_t *o_i32, const uint32_t *o_f32,
+                                                     unsigned fmt, unsigned long long *result)
+{
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	unsigned long long bad = 0, first = ~0ull;
+	for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nsamples; k += stride) {
+		const uint8_t *s = in + 6 * k;
+		uint32_t f[2];
+		f[0] = ((uint32_t)__ldg(s + 0) << 8) | ((uint32_t)__ldg(s + 1) << 16) | ((uint32_t)__ldg(s + 2) << 24);
+		f[1] = ((uint32_t)__ldg(s + 3) << 8) | ((uint32_t)__ldg(s + 4) << 16) | ((uint32_t)__ldg(s + 5) << 24);
+#pragma unroll
+		for (int c = 0; c < 2; ++c) {
+			const uint64_t idx = 2 * k + c;
+			if ((fmt & FMT_I32) && o_i32[idx] != f[c]) { ++bad; first = first < idx ? first : idx; }
+			if (fmt & (FMT_F32 | FMT_POW2)) {
+				const float x = (float)(int)f[c];
+				const float want = (fmt & FMT_POW2) ? x * 4.656612873077392578125e-10f : __fdiv_rn(x, 2147483392.0f);
+				if (o_f32[idx] != __float_as_uint(want)) { ++bad; first = first < idx ? first : idx; }
+			}
+		}
+	}
+	if (bad) { atomicAdd(&result[0], bad); atomicMin(&result[1], first); }
+}
+
+// ------------------------------------------------------------------ dispatch tables
+template <unsigned FMT, int TILE, int ST, bool BATCHED>
+cudaError_t launch_stream_inst(const StreamParams &p, int grid, cudaStream_t stream)
+{
+	auto kern = unpack24_stream_kernel<FMT, TILE, ST, BATCHED>;
+	const size_t smem = (size_t)p.stages * TILE;
+	static bool configured[64] = {};                      // per instantiation: devices whose smem limit is raised
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (dev < 0 || dev >= 64 || !configured[dev]) {
+		constexpr int kMaxSmem = kMaxStages * TILE > 200 * 1024 ? 200 * 1024 : kMaxStages * TILE;
+		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+		if (e != cudaSuccess) return e;
+		if (dev >= 0 && dev < 64) configured[dev] = true;
+	}
+	if (smem > 200 * 1024) return cudaErrorInvalidValue;
+	kern<<<grid, kConsumerThreads + kProducerThreads, smem, stream>>>(p);
+	return cudaGetLastError();
+}
+
+template <unsigned FMT, int TILE, bool BATCHED>
+cudaError_t launch_stream_st(const StreamParams &p, int st, int grid, cudaStream_t stream)
+{
+	return st == 2 ? launch_stream_inst<FMT, TILE, 2, BATCHED>(p, grid, stream) : launch_stream_inst<FMT, TILE, 1, BATCHED>(p, grid, stream);
+}
+
+template <unsigned FMT, bool BATCHED>
+cudaError_t launch_stream_tile(const StreamParams &p, int tile, int st, int grid, cudaStream_t stream)
+{
+	switch (tile) {
+	case 6144: return launch_stream_st<FMT, 6144, BATCHED>(p, st, grid, stream);
+	case 12288: return launch_stream_st<FMT, 12288, BATCHED>(p, st, grid, stream);
+	case 24576: return launch_stream_st<FMT, 24576, BATCHED>(p, st, grid, stream);
+	default: return cudaErrorInvalidValue;
+	}
+}
+
+template <bool BATCHED>
+cudaError_t launch_stream_fmt(const StreamParams &p, unsigned fmt, int tile, int st, int grid, cudaStream_t stream)
+{
+	switch (fmt) {
+	case FMT_I32: return launch_stream_tile<FMT_I32, BATCHED>(p, tile, st, grid, stream);
+	case FMT_F32: return launch_stream_tile<FMT_F32, BATCHED>(p, tile, st, grid, stream);
+	case FMT_POW2: return launch_stream_tile<FMT_POW2, BATCHED>(p, tile, st, grid, stream);
+	case FMT_I32 | FMT_F32: return launch_stream_tile<FMT_I32 | FMT_F32, BATCHED>(p, tile, st, grid, stream);
+	case FMT_I32 | FMT_POW2: return launch_stream_tile<FMT_I32 | FMT_POW2, BATCHED>(p, tile, st, grid, stream);
+	default: return cudaErrorInvalidValue;
+	}
+}
+
+template <unsigned FMT>
+cudaError_t launch_direct_inst(const DirectParams &p, bool aligned, int st, int grid, cudaStream_t stream)
+{
+	if (aligned) {
+		if (st == 2) unpack24_direct_kernel<FMT, 2, true><<<grid, 256, 0, stream>>>(p);
+		else unpack24_direct_kernel<FMT, 1, true><<<grid, 256, 0, stream>>>(p);
+	} else {
+		unpack24_direct_kernel<FMT, 1, false><<<grid, 256, 0, stream>>>(p);
+	}
+	return cudaGetLastError();
+}
+
+cudaError_t launch_direct_fmt(const DirectParams &p, unsigned fmt, bool aligned, int st, int grid, cudaStream_t stream)
+{
+	switch (fmt) {
+	case FMT_I32: return launch_direct_inst<FMT_I32>(p, aligned, st, grid, stream);
+	case FMT_F32: return launch_direct_inst<FMT_F32>(p, aligned, st, grid, stream);
+	case FMT_POW2: return launch_direct_inst<FMT_POW2>(p, aligned, st, grid, stream);
+	case FMT_I32 | FMT_F32: return launch_direct_inst<FMT_I32 | FMT_F32>(p, aligned, st, grid, stream);
+	case FMT_I32 | FMT_POW2: return launch_direct_inst<FMT_I32 | FMT_POW2>(p, aligned, st, grid, stream);
+	default: return cudaErrorInvalidValue;
+	}
+}
+
+cudaError_t launch_direct_batch_fmt(const DirectParams &p, unsigned fmt, int grid, cudaStream_t stream)
+{
+	switch (fmt) {
+	case FMT_I32: unpack24_direct_batch_kernel<FMT_I32><<<grid, 256, 0, stream>>>(p); break;
+	case FMT_F32: unpack24_direct_batch_kernel<FMT_F32><<<grid, 256, 0, stream>>>(p); break;
+	case FMT_POW2: unpack24_direct_batch_kernel<FMT_POW2><<<grid, 256, 0, stream>>>(p); break;
+	case FMT_I32 | FMT_F32: unpack24_direct_batch_kernel<FMT_I32 | FMT_F32><<<grid, 256, 0, stream>>>(p); break;
+	case FMT_I32 | FMT_POW2: unpack24_direct_batch_kernel<FMT_I32 | FMT_POW2><<<grid, 256, 0, stream>>>(p); break;
+	default: return cudaErrorInvalidValue;
+	}
+	return cudaGetLastError();
+}
+
+inline bool aligned_to(const void *p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+
+inline int persistent_grid(uint64_t ntiles, int sm_count, int ctas_per_sm)
+{
+	const uint64_t want = (uint64_t)sm_count * (uint64_t)ctas_per_sm;
+	return (int)(ntiles < want ? ntiles : want);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ public launchers
+cudaError_t launch_unpack(const void *in, size_t nbytes, void *out_i32, void *out_f32, unsigned fmt, const Tuning &t,
+                          int sm_count, cudaStream_t stream, int *launches)
+{
+	*launches = 0;
+	const uint64_t nsamples = nbytes / 6;
+	if (nsamples == 0) return cudaSuccess;
+	if (!(fmt & FMT_I32)) out_i32 = nullptr;
+	if (!(fmt & (FMT_F32 | FMT_POW2))) out_f32 = nullptr;
+	const bool out16 = aligned_to(out_i32, 16) && aligned_to(out_f32, 16);
+	const bool can_stream = aligned_to(in, 16) && out16;
+	const bool use_stream = t.variant == 2 ? false : can_stream;   // variant 1 (STREAM) degrades to direct when unaligned
+
+	if (use_stream) {
+		StreamParams p{};
+		p.in = static_cast<const uint8_t *>(in);
+		p.out_i32 = static_cast<uint8_t *>(out_i32);
+		p.out_f32 = static_cast<uint8_t *>(out_f32);
+		p.in_bytes = nsamples * 6;
+		p.ntiles = (p.in_bytes + (uint64_t)t.tile_bytes - 1) / (uint64_t)t.tile_bytes;
+		p.stages = t.stages;
+		const int grid = persistent_grid(p.ntiles, sm_count, t.ctas_per_sm);
+		cudaError_t e = launch_stream_fmt<false>(p, fmt, t.tile_bytes, t.store_mode, grid, stream);
+		if (e == cudaSuccess) *launches = 1;
+		return e;
+	}
+	DirectParams p{};
+	p.in = static_cast<const uint8_t *>(in);
+	p.out_i32 = static_cast<uint8_t *>(out_i32);
+	p.out_f32 = static_cast<uint8_t *>(out_f32);
+	p.nsamples = nsamples;
+	const bool aligned = aligned_to(in, 4) && out16;
+	const uint64_t nunits = nsamples / 2;
+	const uint64_t per_block = aligned ? 256 * 4 : 256;
+	uint64_t blocks = (nunits + per_block - 1) / per_block;
+	const uint64_t cap = (uint64_t)sm_count * 8 * (aligned ? 4 : 16);
+	if (blocks > cap) blocks = cap;
+	if (blocks == 0) blocks = 1;
+	cudaError_t e = launch_direct_fmt(p, fmt, aligned, t.store_mode, (int)blocks, stream);
+	if (e == cudaSuccess) *launches = 1;
+	return e;
+}
+
+cudaError_t launch_unpack_batch(const SegDesc *d_segs, const TileRef *d_tiles, uint64_t ntiles, unsigned fmt, bool all_aligned,
+                                const Tuning &t, int sm_count, cudaStream_t stream, int *launches)
+{
+	*launches = 0;
+	if (ntiles == 0) return cudaSuccess;
+	cudaError_t e;
+	if (all_aligned && t.variant != 2) {
+		StreamParams p{};
+		p.segs = d_segs;
+		p.tiles = d_tiles;
+		p.ntiles = ntiles;
+		p.stages = t.stages;
+		e = launch_stream_fmt<true>(p, fmt, t.tile_bytes, t.store_mode, persistent_grid(ntiles, sm_count, t.ctas_per_sm), stream);
+	} else {
+		DirectParams p{};
+		p.segs = d_segs;
+		p.tiles = d_tiles;
+		p.ntiles = ntiles;
+		p.tile_bytes = t.tile_bytes;
+		e = launch_direct_batch_fmt(p, fmt, persistent_grid(ntiles, sm_count, 16), stream);
+	}
+	if (e == cudaSuccess) *launches = 1;
+	return e;
+}
+
+cudaError_t launch_generate(void *dst, size_t nbytes, int pattern, uint64_t seed, uint64_t byte_offset, cudaStream_t stream)
+{
+	if (nbytes == 0) return cudaSuccess;
+	if (pattern == 0) {
+		const uint64_t nwords = (nbytes + 15) / 8;
+		uint64_t blocks = (nwords + 255) / 256;
+		if (blocks > 148 * 32) blocks = 148 * 32;
+		generate_random_kernel<<<(int)blocks, 256, 0, stream>>>(static_cast<uint8_t *>(dst), nbytes, seed, byte_offset);
+	} else if (pattern == 1) {
+		if (byte_offset % 6) return cudaErrorInvalidValue;
+		const uint64_t ns = nbytes / 6;
+		if (ns) {
+			uint64_t blocks = (ns + 255) / 256;
+			if (blocks > 148 * 32) blocks = 148 * 32;
+			generate_ramp_kernel<<<(int)blocks, 256, 0, stream>>>(static_cast<uint8_t *>(dst), ns, byte_offset / 6);
+		}
+		if (nbytes % 6) {
+			cudaError_t e = cudaMemsetAsync(static_cast<uint8_t *>(dst) + ns * 6, 0, nbytes % 6, stream);
+			if (e != cudaSuccess) return e;
+		}
+	} else {
+		return cudaErrorInvalidValue;
+	}
+	return cudaGetLastError();
+}
+
+cudaError_t launch_checksum(const void *words, size_t nwords, uint64_t first_index, unsigned long long *d_sum, cudaStream_t stream)
+{
+	cudaError_t e = cudaMemsetAsync(d_sum, 0, sizeof(unsigned long long), stream);
+	if (e != cudaSuccess || nwords == 0) return e;
+	uint64_t blocks = (nwords + 256 * 8 - 1) / (256 * 8);
+	if (blocks > 148 * 16) blocks = 148 * 16;
+	checksum32_kernel<<<(int)blocks, 256, 0, stream>>>(static_cast<const uint32_t *>(words), nwords, first_index, d_sum);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_verify(const void *in, size_t nbytes, const void *out_i32, const void *out_f32, unsigned fmt,
+                          unsigned long long *d_result, cudaStream_t stream)
+{
+	const unsigned long long init[2] = {0ull, ~0ull};
+	cudaError_t e = cudaMemcpyAsync(d_result, init, sizeof(init), cudaMemcpyHostToDevice, stream);
+	const uint64_t ns = nbytes / 6;
+	if (e != cudaSuccess || ns == 0) return e;
+	uint64_t blocks = (ns + 255) / 256;
+	if (blocks > 148 * 32) blocks = 148 * 32;
+	verify_kernel<<<(int)blocks, 256, 0, stream>>>(static_cast<const uint8_t *>(in), ns, static_cast<const uint32_t *>(out_i32),
+	                                               static_cast<const uint32_t *>(out_f32), fmt, d_result);
+	return cudaGetLastError();
+}
+
+void host_generate(uint8_t *dst, size_t nbytes, int pattern, uint64_t seed, uint64_t byte_offset)
+{
+	if (pattern == 1) {
+		const size_t ns = nbytes / 6;
+		for (size_t k = 0; k < ns; ++k) ramp_sample(byte_offset / 6 + k, dst + 6 * k);
+		memset(dst + ns * 6, 0, nbytes - ns * 6);
+		return;
+	}
+	size_t i = 0;
+	// head: up to the next 8-byte stream-word boundary
+	while (i < nbytes && ((byte_offset + i) & 7)) {
+		const uint64_t pos = byte_offset + i;
+		dst[i++] = (uint8_t)(splitmix64(seed + (pos >> 3)) >> (8 * (pos & 7)));
+	}
+	for (; i + 8 <= nbytes; i += 8) {
+		const uint64_t word = splitmix64(seed + ((byte_offset + i) >> 3));   // little-endian host
+		memcpy(dst + i, &word, 8);
+	}
+	for (; i < nbytes; ++i) {
+		const uint64_t pos = byte_offset + i;
+		dst[i] = (uint8_t)(splitmix64(seed + (pos >> 3)) >> (8 * (pos & 7)));
+	}
+}
+
+}  // namespace pg

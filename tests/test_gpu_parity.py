@@ -1,0 +1,482 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI
+(include/perseus-gpu.h), against the CPU oracle / the committed golden vectors.
+Bar: bit-exact for int32 AND float (the float path is one exact int->float conversion and one
+correctly-rounded multiply, proven equal to the reference's division for all 2^24 codes)."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+FMT_CASES = None  # filled lazily (needs the package constants)
+
+
+def fmt_cases(pg):
+    return [("i32", pg.OUT_INT32, [O.MODE_I32, None]), ("f32", pg.OUT_FLOAT, [None, O.MODE_F32]),
+            ("pow2", pg.OUT_FLOAT_POW2, [None, O.MODE_F32_POW2]), ("i32+f32", pg.OUT_INT32 | pg.OUT_FLOAT, [O.MODE_I32, O.MODE_F32]),
+            ("i32+pow2", pg.OUT_INT32 | pg.OUT_FLOAT_POW2, [O.MODE_I32, O.MODE_F32_POW2])]
+
+
+class DevBuf:
+    """device allocation through the C ABI, freed on exit"""
+
+    def __init__(self, h, nbytes):
+        self.h, self.n = h, nbytes
+        self.p = h.dev_alloc(nbytes)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.h.dev_free(self.p)
+
+
+def run_unpack(pg, h, wire, flags, in_off=0, out_off=0, fill=0xA5):
+    """Unpacks `wire` (numpy u8) placed at device offset in_off; returns (i32 words | None, f32 words | None).
+    The output buffers are pre-filled and carry guard bytes so out-of-range writes are caught."""
+    ns = wire.size // 6
+    guard = 256
+    with DevBuf(h, in_off + wire.size + 64) as din, DevBuf(h, out_off + ns * 8 + guard) as di, DevBuf(h, out_off + ns * 8 + guard) as df:
+        if wire.size:
+            h.memcpy(din.p + in_off, wire.ctypes.data, wire.size)
+        h.memset(di.p, fill, di.n)
+        h.memset(df.p, fill, df.n)
+        want_i = bool(flags & pg.OUT_INT32)
+        want_f = bool(flags & (pg.OUT_FLOAT | pg.OUT_FLOAT_POW2))
+        got = h.unpack(din.p + in_off, wire.size, di.p + out_off if want_i else None, df.p + out_off if want_f else None, flags)
+        assert got == ns
+        res = []
+        for want, d in ((want_i, di), (want_f, df)):
+            raw = h.to_host(d.p, d.n, np.uint8)
+            if want:
+                assert (raw[:out_off] == fill).all() and (raw[out_off + ns * 8:] == fill).all(), "wrote outside the output range"
+                res.append(raw[out_off:out_off + ns * 8].copy().view(np.uint32))
+            else:
+                assert (raw == fill).all(), "wrote to an output that was not requested"
+                res.append(None)
+        return res
+
+
+def check_against_oracle(pg, h, coracle, wire, in_off=0, out_off=0, cases=None):
+    for name, flags, modes in (cases or fmt_cases(pg)):
+        got = run_unpack(pg, h, wire, flags, in_off, out_off)
+        for g, m in zip(got, modes):
+            if m is None:
+                assert g is None
+            else:
+                want = coracle.unpack(wire, m).view(np.uint32).reshape(-1)
+                assert np.array_equal(g, want), (name, wire.size, in_off, out_off, h.get_tuning())
+
+
+@pytest.fixture(params=["stream", "direct"])
+def variant(request, pg, gpu):
+    gpu.set_tuning(variant=pg.VARIANT_STREAM if request.param == "stream" else pg.VARIANT_DIRECT)
+    yield request.param
+    gpu.set_tuning()
+
+
+def test_device_is_b200_class(pg, gpu):
+    L = pg.lib()
+    name = C.create_string_buffer(128)
+    sm, maj, mnr, mem = C.c_int(), C.c_int(), C.c_int(), C.c_uint64()
+    assert L.perseus_gpu_device_info(0, name, 128, C.byref(sm), C.byref(maj), C.byref(mnr), C.byref(mem)) == 0
+    assert maj.value == 10 and sm.value >= 100, (name.value, maj.value, sm.value)
+
+
+def test_golden_known_answers(pg, gpu, variant):
+    kat = json.loads((GOLDEN / "kat.json").read_text())["vectors"]
+    wire = np.frombuffer(b"".join(bytes.fromhex(v["wire_hex"]) + bytes.fromhex(v["q_code24"])[::-1] for v in kat), np.uint8)
+    i32, f32 = run_unpack(pg, gpu, wire, pg.OUT_INT32 | pg.OUT_FLOAT)
+    for k, v in enumerate(kat):
+        assert f"{int(i32[2 * k]):08x}" == v["int32_hex"] and f"{int(i32[2 * k + 1]):08x}" == v["q_int32_hex"], v
+        assert f"{int(f32[2 * k]):08x}" == v["float_bits_hex"] and f"{int(f32[2 * k + 1]):08x}" == v["q_float_bits_hex"], v
+
+
+@pytest.mark.parametrize("name", ["xfer6144", "xfer510", "ragged1000"])
+def test_golden_fixtures(pg, gpu, variant, name):
+    wire = np.fromfile(GOLDEN / f"{name}.in.bin", np.uint8)
+    i32, f32 = run_unpack(pg, gpu, wire, pg.OUT_INT32 | pg.OUT_FLOAT)
+    assert np.array_equal(i32, np.fromfile(GOLDEN / f"{name}.i32.bin", np.uint32))
+    assert np.array_equal(f32, np.fromfile(GOLDEN / f"{name}.f32.bin", np.uint32))
+
+
+def test_exhaustive_2p24_all_formats(pg, gpu, coracle, variant):
+    """Every 24-bit code in I, a permutation of them in Q: device ramp generator == oracle ramp, every
+    format bit-exact vs the oracle, int32/float hashes == tests/golden/exhaustive.json (from oracle/_ref)."""
+    g = json.loads((GOLDEN / "exhaustive.json").read_text())
+    n = (1 << 24) * 6
+    ramp = coracle.synth_ramp(1 << 24)
+    with DevBuf(gpu, n) as din:
+        gpu.generate(din.p, n, pg.SYNTH_RAMP, 0, 0)
+        assert np.array_equal(gpu.to_host(din.p, n, np.uint8), ramp)
+    assert f"{coracle.fnv1a64(ramp):016x}" == g["input_fnv1a64"]
+    for name, flags, modes in fmt_cases(pg):
+        got = run_unpack(pg, gpu, ramp, flags)
+        for out, m in zip(got, modes):
+            if m is None:
+                continue
+            assert np.array_equal(out, coracle.unpack(ramp, m, nthreads=O.host_threads()).view(np.uint32).reshape(-1)), name
+            if m == O.MODE_I32:
+                assert f"{coracle.fnv1a64(out):016x}" == g["int32_fnv1a64"]
+            if m == O.MODE_F32:
+                assert f"{coracle.fnv1a64(out):016x}" == g["float_fnv1a64"]
+
+
+def test_multiply_equals_ieee_division_on_device(pg, gpu):
+    """SURVEY.md F2 re-proved on the B200: the product's I2F + FMUL(0x30000001) vs the verify kernel's
+    I2F + correctly rounded division by 2147483392.0f, for all 2^24 codes in both fields."""
+    n = (1 << 24) * 6
+    with DevBuf(gpu, n) as din, DevBuf(gpu, (1 << 24) * 8) as di, DevBuf(gpu, (1 << 24) * 8) as df:
+        gpu.generate(din.p, n, pg.SYNTH_RAMP, 0, 0)
+        gpu.unpack(din.p, n, di.p, df.p, pg.OUT_INT32 | pg.OUT_FLOAT)
+        assert gpu.verify(din.p, n, di.p, df.p, pg.OUT_INT32 | pg.OUT_FLOAT) == (0, 2 ** 64 - 1)
+        gpu.unpack(din.p, n, None, df.p, pg.OUT_FLOAT_POW2)
+        assert gpu.verify(din.p, n, None, df.p, pg.OUT_FLOAT_POW2)[0] == 0
+        bad, first = gpu.verify(din.p, n, None, df.p, pg.OUT_FLOAT)   # POW2 output is NOT the reference scale
+        assert bad == 2 * (1 << 24) - 2 and first == 2               # all but the two zero fields (I and Q of sample 0)
+
+
+def test_verify_detects_single_corruption(pg, gpu, coracle):
+    wire = coracle.synth_random(6144 * 7, seed=21)
+    ns = wire.size // 6
+    with DevBuf(gpu, wire.size) as din, DevBuf(gpu, ns * 8) as di:
+        gpu.memcpy(din.p, wire.ctypes.data, wire.size)
+        gpu.unpack(din.p, wire.size, di.p, None, pg.OUT_INT32)
+        assert gpu.verify(din.p, wire.size, di.p, None, pg.OUT_INT32)[0] == 0
+        word = np.array([0xDEADBE00], np.uint32)
+        gpu.memcpy(di.p + 4 * 4321, word.ctypes.data, 4)
+        assert gpu.verify(din.p, wire.size, di.p, None, pg.OUT_INT32) == (1, 4321)
+
+
+SIZES = sorted(set(list(range(0, 100)) + [510, 1020, 16320, 6143, 6144, 6145, 6150, 12287, 12288, 12289, 12294, 12300, 12288 + 48,
+                                          24575, 24576, 24582, 3 * 12288 - 6, 3 * 12288 + 18, 510 * 7, 49152, 100_003]))
+
+
+def test_every_small_and_ragged_size(pg, gpu, coracle, variant):
+    """Empty, sub-sample, odd sample counts, sizes straddling every tile size; n%6 trailing bytes ignored."""
+    big = coracle.synth_random(max(SIZES) + 16, seed=5)
+    cases = [c for c in fmt_cases(pg) if c[0] in ("i32", "i32+f32")]
+    for n in SIZES:
+        check_against_oracle(pg, gpu, coracle, big[:n], cases=cases)
+
+
+def test_unaligned_pointers_take_the_direct_path_and_stay_exact(pg, gpu, coracle):
+    """Legacy 510-byte transfers and ring seams give pointers with any alignment."""
+    wire = coracle.synth_random(510 * 9 + 4, seed=6)
+    for in_off in (0, 1, 2, 3, 4, 6, 8, 12, 15):
+        for out_off in (0, 4, 8, 12):
+            check_against_oracle(pg, gpu, coracle, wire, in_off=in_off, out_off=out_off,
+                                 cases=[c for c in fmt_cases(pg) if c[0] in ("i32+f32", "pow2")])
+
+
+@pytest.mark.parametrize("tile", [6144, 12288, 24576])
+@pytest.mark.parametrize("stages", [2, 3, 8])
+def test_every_pipeline_geometry(pg, gpu, coracle, tile, stages):
+    wire = coracle.synth_random(24576 * 3 * 148 + 6144 * 5 + 30, seed=tile + stages)   # > one wave, ragged end
+    for ctas in (1, 2, 4):
+        for store in (1, 2):
+            try:
+                gpu.set_tuning(variant=pg.VARIANT_STREAM, tile_bytes=tile, stages=stages, ctas_per_sm=ctas, store_mode=store)
+            except pg.PerseusGpuError as e:
+                assert e.code == pg.ERR["ERRPARAM"] and stages * tile * ctas > 150 * 1024
+                continue
+            check_against_oracle(pg, gpu, coracle, wire, cases=[c for c in fmt_cases(pg) if c[0] == "i32+f32"])
+    gpu.set_tuning()
+
+
+def test_device_generator_matches_oracle_definition(pg, gpu, coracle):
+    for off, n in ((0, 6144 * 3), (8, 100_000), (3, 1000), (12345, 7777), ((1 << 36) + 11, 4099)):
+        for misalign in (0, 1, 4):
+            with DevBuf(gpu, n + 16) as d:
+                gpu.memset(d.p, 0xEE, n + 16)
+                gpu.generate(d.p + misalign, n, pg.SYNTH_RANDOM, O.SYNTH_SEED, off)
+                raw = gpu.to_host(d.p, n + 16, np.uint8)
+                assert np.array_equal(raw[misalign:misalign + n], coracle.synth_random(n, O.SYNTH_SEED, off))
+                assert (raw[:misalign] == 0xEE).all() and (raw[misalign + n:] == 0xEE).all()
+
+
+def test_checksum_kernel_matches_oracle_and_is_shard_additive(pg, gpu, coracle):
+    w = coracle.unpack(coracle.synth_random(6 * 300_001, seed=8), O.MODE_I32).reshape(-1)
+    d = gpu.to_device(w)
+    total = gpu.checksum(d, w.size)
+    assert total == coracle.checksum32(w)
+    cut = 123_457
+    assert (gpu.checksum(d, cut) + gpu.checksum(d + 4 * cut, w.size - cut, first_index=cut)) % (1 << 64) == total
+    gpu.dev_free(d)
+
+
+def test_host_pointers_pageable_and_pinned(pg, coracle):
+    """perseus_gpu_unpack with HOST buffers: staged H2D -> kernel -> D2H in chunks (chunk smaller than the input)."""
+    wire = coracle.synth_random(6144 * 37 + 13, seed=9)
+    ns = wire.size // 6
+    want_i = coracle.unpack(wire, O.MODE_I32).view(np.uint32).reshape(-1)
+    want_f = coracle.unpack(wire, O.MODE_F32).view(np.uint32).reshape(-1)
+    with pg.PerseusGpu(device=0, chunk_bytes=6144 * 5, nstreams=3) as h:
+        oi, of = np.zeros(ns * 2, np.uint32), np.zeros(ns * 2, np.uint32)
+        assert h.unpack(wire.ctypes.data, wire.size, oi.ctypes.data, of.ctypes.data, 0) == ns      # pageable in and out
+        assert np.array_equal(oi, want_i) and np.array_equal(of, want_f)
+        pin = h.host_alloc(wire.size)
+        pout = h.host_alloc(ns * 8)
+        C.memmove(pin, wire.ctypes.data, wire.size)
+        assert h.unpack(pin, wire.size, pout, None, pg.OUT_INT32) == ns                             # pinned in and out
+        assert np.array_equal(np.ctypeslib.as_array((C.c_uint32 * (ns * 2)).from_address(pout)), want_i)
+        with DevBuf(h, ns * 8) as df:                                                              # pinned in, device out (cfg5 shape)
+            assert h.unpack(pin, wire.size, None, df.p, pg.OUT_FLOAT | pg.ASYNC) == ns
+            h.sync()
+            assert np.array_equal(h.to_host(df.p, ns * 8, np.uint32), want_f)
+        st = h.stats()
+        assert st["h2d_bytes"] == 3 * ns * 6 and st["d2h_bytes"] == 3 * ns * 8 and st["kernel_launches"] >= 3 * 8
+        h.host_free(pin)
+        h.host_free(pout)
+
+
+def test_argument_errors(pg, gpu):
+    with DevBuf(gpu, 6144) as d, DevBuf(gpu, 8192) as o:
+        for args, code in (((d.p, 6144, o.p, o.p, pg.OUT_FLOAT | pg.OUT_FLOAT_POW2), "ERRPARAM"),
+                           ((d.p, 6144, None, None, 0), "ERRPARAM"),
+                           ((d.p, 6144, None, o.p, pg.OUT_INT32), "ERRPARAM"),
+                           ((d.p, 6144, o.p, None, 0x8000), "ERRPARAM"),
+                           ((None, 6144, o.p, None, 0), "ERRPARAM"),
+                           ((d.p, 6144, o.p + 2, None, 0), "ERRPARAM")):
+            with pytest.raises(pg.PerseusGpuError) as e:
+                gpu.unpack(*args)
+            assert e.value.code == pg.ERR[code], args
+        assert gpu.unpack(d.p, 5, o.p, None, 0) == 0 and gpu.unpack(d.p, 0, o.p, None, 0) == 0
+    for bad in (dict(tile_bytes=1000), dict(stages=1), dict(stages=9), dict(ctas_per_sm=9), dict(tile_bytes=24576, stages=8, ctas_per_sm=2),
+                dict(variant=7), dict(store_mode=5)):
+        with pytest.raises(pg.PerseusGpuError) as e:
+            gpu.set_tuning(**bad)
+        assert e.value.code == pg.ERR["ERRPARAM"], bad
+    gpu.set_tuning()
+
+
+# ------------------------------------------------------------------ BASELINE configs
+
+def test_cfg2_one_gib_2ms_layout_bit_exact_over_entire_output(pg, gpu, coracle):
+    """BASELINE config 2: 174 762 transfers x 6144 B generated on the device, unpacked to int32 and float,
+    compared word for word with the CPU oracle over the ENTIRE output, plus size-independent properties."""
+    nbuf = 174_762
+    n = nbuf * 6144
+    ns = n // 6
+    threads = O.host_threads()
+    with DevBuf(gpu, n) as din, DevBuf(gpu, ns * 8) as di, DevBuf(gpu, ns * 8) as df:
+        gpu.generate(din.p, n, pg.SYNTH_RANDOM, O.SYNTH_SEED, 0)
+        assert gpu.unpack(din.p, n, di.p, df.p, pg.OUT_INT32 | pg.OUT_FLOAT) == ns
+        wire = gpu.to_host(din.p, n, np.uint8)
+        # the device generator wrote the stream the oracle defines (spot ranges, incl. the end)
+        for off in (0, 6144 * 1000 + 5, n - 4099):
+            assert np.array_equal(wire[off:off + 4099], coracle.synth_random(4099, O.SYNTH_SEED, off))
+        want = np.empty((ns, 2), np.int32)
+        coracle.unpack(wire, O.MODE_I32, nthreads=threads, out=want)
+        got = gpu.to_host(di.p, ns * 8, np.uint32)
+        assert np.array_equal(got, want.view(np.uint32).reshape(-1))
+        cs_i = gpu.checksum(di.p, ns * 2)
+        assert cs_i == coracle.checksum32(got)
+        wantf = want.view(np.float32)
+        coracle.unpack(wire, O.MODE_F32, nthreads=threads, out=wantf)
+        got = gpu.to_host(df.p, ns * 8, np.uint32)
+        assert np.array_equal(got, wantf.view(np.uint32).reshape(-1))
+        del want, wantf, got
+        # properties that do not need the oracle: independent per-sample kernel agrees everywhere,
+        assert gpu.verify(din.p, n, di.p, df.p, pg.OUT_INT32 | pg.OUT_FLOAT)[0] == 0
+        # the fused pass equals the single-format passes, and every shard split reproduces the whole
+        gpu.memset(di.p, 0, ns * 8)
+        for shards in (2, 8):
+            for s in range(shards):
+                first, count = pg.shard_range(nbuf, shards, s)
+                gpu.unpack(din.p + first * 6144, count * 6144, di.p + first * 8192, None, pg.OUT_INT32 | pg.ASYNC)
+            gpu.sync()
+            assert gpu.checksum(di.p, ns * 2) == cs_i
+            parts = [gpu.checksum(di.p + 8192 * pg.shard_range(nbuf, shards, s)[0], 2048 * pg.shard_range(nbuf, shards, s)[1],
+                                  first_index=2048 * pg.shard_range(nbuf, shards, s)[0]) for s in range(shards)]
+            assert sum(parts) % (1 << 64) == cs_i                         # checksum of checksums
+
+
+def mixed_rate_segments(nrx, window_s):
+    """cfg3 layout: receiver r runs at {48k,96k,192k,500k,1M,2M}[r%6]; window_s seconds of 6144-byte transfers."""
+    rates = [48000, 96000, 192000, 500000, 1000000, 2000000]
+    return [max(1, round(rates[r % 6] * window_s / 1024)) for r in range(nrx)]
+
+
+def test_cfg3_mixed_rate_batch_small_against_oracle(pg, gpu, coracle):
+    """Same structure as BASELINE config 3 at a size the oracle checks completely; ragged and unaligned segments included."""
+    nbufs = mixed_rate_segments(96, 0.064)          # 3..125 transfers per receiver
+    sizes = [b * 6144 for b in nbufs]
+    sizes[5] += 510                                  # ragged: not a multiple of the tile, not of 16
+    sizes[11] = 6 * 333                              # smaller than one tile
+    sizes[17] = 0                                    # an idle receiver
+    sizes[23] += 4                                   # trailing bytes that are not a sample
+    for flags, modes in ((pg.OUT_INT32 | pg.OUT_FLOAT, (O.MODE_I32, O.MODE_F32)), (pg.OUT_FLOAT_POW2, (None, O.MODE_F32_POW2))):
+        for misalign in (0, 2):                      # misalign != 0 forces the byte-load batched kernel
+            wires = [coracle.synth_random(s, seed=O.SYNTH_SEED + r) for r, s in enumerate(sizes)]
+            bufs = []
+            segs = []
+            for w in wires:
+                din = DevBuf(gpu, w.size + 64); di = DevBuf(gpu, w.size // 6 * 8 + 64); df = DevBuf(gpu, w.size // 6 * 8 + 64)
+                if w.size:
+                    gpu.memcpy(din.p + misalign, w.ctypes.data, w.size)
+                gpu.memset(di.p, 0x5A, di.n); gpu.memset(df.p, 0x5A, df.n)
+                bufs.append((din, di, df))
+                segs.append((din.p + misalign, w.size, di.p if modes[0] is not None else None, df.p))
+            launches0 = gpu.stats()["kernel_launches"]
+            total = gpu.unpack_batch(segs, flags)
+            assert total == sum(s // 6 for s in sizes)
+            assert gpu.stats()["kernel_launches"] == launches0 + 1           # ONE launch for all receivers
+            for w, (din, di, df) in zip(wires, bufs):
+                ns = w.size // 6
+                for d, m in ((di, modes[0]), (df, modes[1])):
+                    raw = gpu.to_host(d.p, d.n, np.uint8)
+                    if m is None:
+                        assert (raw == 0x5A).all()
+                        continue
+                    assert np.array_equal(raw[:ns * 8].view(np.uint32), coracle.unpack(w, m).view(np.uint32).reshape(-1))
+                    assert (raw[ns * 8:] == 0x5A).all()
+            for t in bufs:
+                for b in t:
+                    gpu.dev_free(b.p)
+
+
+def test_cfg3_full_size_1024_receivers_one_launch(pg, gpu, coracle):
+    """BASELINE config 3 at full size: 1024 receivers, 652 956 transfers = 4 011 761 664 B in one launch.
+    Checked on the device by the independent per-sample kernel over everything, and against the CPU oracle
+    on a sample of receivers (first, last, one per rate)."""
+    nbufs = mixed_rate_segments(1024, 1.024)
+    assert sorted(set(nbufs)) == [48, 96, 192, 500, 1000, 2000] and sum(nbufs) == 652_956
+    total_in = sum(nbufs) * 6144
+    with DevBuf(gpu, total_in) as din, DevBuf(gpu, total_in // 6 * 8) as di, DevBuf(gpu, total_in // 6 * 8) as df:
+        segs, off = [], 0
+        for r, b in enumerate(nbufs):
+            gpu.generate(din.p + off, b * 6144, pg.SYNTH_RANDOM, O.SYNTH_SEED + r, 0)     # own seed per receiver
+            segs.append((din.p + off, b * 6144, di.p + off // 6 * 8, df.p + off // 6 * 8))
+            off += b * 6144
+        plan = gpu.plan_create(segs, pg.OUT_INT32 | pg.OUT_FLOAT)
+        l0 = gpu.stats()["kernel_launches"]
+        assert gpu.plan_run(plan) == total_in // 6
+        assert gpu.stats()["kernel_launches"] == l0 + 1
+        gpu.plan_destroy(plan)
+        assert gpu.verify(din.p, total_in, di.p, df.p, pg.OUT_INT32 | pg.OUT_FLOAT)[0] == 0
+        offs = np.concatenate([[0], np.cumsum(nbufs)]) * 6144
+        for r in (0, 1, 2, 3, 4, 5, 511, 1023):
+            n = nbufs[r] * 6144
+            wire = coracle.synth_random(n, seed=O.SYNTH_SEED + r)
+            o = int(offs[r]) // 6 * 8
+            assert np.array_equal(gpu.to_host(di.p + o, n // 6 * 8, np.uint32), coracle.unpack(wire, O.MODE_I32).view(np.uint32).reshape(-1))
+            assert np.array_equal(gpu.to_host(df.p + o, n // 6 * 8, np.uint32), coracle.unpack(wire, O.MODE_F32).view(np.uint32).reshape(-1))
+
+
+# ------------------------------------------------------------------ the drop-in boundary: callback trampoline
+
+def collect_stream(pg, h, run):
+    """Installs a sink that records block descriptors, runs `run()`, returns the concatenated device outputs."""
+    blocks = []
+    h.set_sink(lambda blk, extra: blocks.append((blk.contents.first_sample, blk.contents.nsamples, blk.contents.dev_i32,
+                                                 blk.contents.dev_f32, blk.contents.stream)))
+    run()
+    return blocks
+
+
+@pytest.mark.parametrize("buffersize,ep", [(6144, 512), (12288, 512), (510, 510), (510 * 32, 510)])
+def test_callback_trampoline_driven_by_virtual_receiver(pg, coracle, buffersize, ep):
+    """perseus_vrx_* plays perseus_start_async_input + the libusb queue (8-slot pageable ring, in-order
+    callbacks, buffer reused right after return); the registered callback IS perseus_gpu_input_callback,
+    passed as a C function pointer exactly as a libperseus-sdr user would."""
+    ntransfers = 203
+    slab = 48 * 1000                                   # not a multiple of the transfer: slabs split transfers
+    with pg.PerseusGpu(device=0, stream_flags=pg.OUT_INT32 | pg.OUT_FLOAT, slab_bytes=slab, nslabs=3, nstreams=2) as h:
+        outs_i, outs_f = [], []
+
+        def sink(blk, extra):
+            b = blk.contents
+            h.sync()                                   # test-only: a real sink would enqueue work on b.stream instead
+            outs_i.append((b.first_sample, h.to_host(b.dev_i32, b.nsamples * 8, np.uint32)))
+            outs_f.append((b.first_sample, h.to_host(b.dev_f32, b.nsamples * 8, np.uint32)))
+
+        h.set_sink(sink)
+        v = pg.VirtualReceiver(sample_rate=2_000_000, ep_max_packet=ep, seed=77)
+        cb, extra = h.callback
+        st = v.run(buffersize, cb, extra, ntransfers)
+        h.flush()
+        v.close()
+        assert st["delivered"] == ntransfers
+        wire = coracle.synth_random(ntransfers * buffersize, seed=77)
+        ns = wire.size // 6
+        pos = 0
+        for first, arr in outs_i:
+            assert first == pos
+            pos += arr.size // 2
+        assert pos == ns
+        assert np.array_equal(np.concatenate([a for _, a in outs_i]), coracle.unpack(wire, O.MODE_I32).view(np.uint32).reshape(-1))
+        assert np.array_equal(np.concatenate([a for _, a in outs_f]), coracle.unpack(wire, O.MODE_F32).view(np.uint32).reshape(-1))
+        s = h.stats()
+        assert s["callbacks"] == ntransfers and s["samples"] == ns and s["h2d_bytes"] == wire.size
+        assert s["slabs"] == -(-wire.size // slab)
+
+
+def test_callback_with_dropped_transfers_leaves_a_gap_like_the_reference(pg, coracle):
+    """Dropped transfers never reach the callback (perseus-in.c:209-216): the consumer sees the stream minus them."""
+    with pg.PerseusGpu(device=0, stream_flags=pg.OUT_INT32, slab_bytes=6144 * 4, nslabs=2) as h:
+        got = []
+
+        def sink(blk, extra):
+            h.sync()
+            got.append(h.to_host(blk.contents.dev_i32, blk.contents.nsamples * 8, np.uint32))
+
+        h.set_sink(sink)
+        v = pg.VirtualReceiver(drop_every=4, seed=3)
+        st = v.run(6144, *h.callback, 16)
+        h.flush()
+        v.close()
+        assert st["delivered"] == 12 and st["dropped_short"] == 4
+        wire = coracle.synth_random(16 * 6144, seed=3).reshape(16, 6144)
+        kept = wire[[k for k in range(16) if (k + 1) % 4]].reshape(-1)
+        assert np.array_equal(np.concatenate(got), coracle.unpack(kept, O.MODE_I32).view(np.uint32).reshape(-1))
+
+
+@pytest.mark.parametrize("fmt,mode,refmode", [("OUT_INT32", O.MODE_I32, O.MODE_I32), ("OUT_FLOAT", O.MODE_F32, O.MODE_F32)])
+def test_stream_file_is_byte_identical_to_perseustest_output(pg, coracle, tmp_path, fmt, mode, refmode):
+    """`perseustest -o file [-p]` writes a raw headerless stream of 8-byte samples (perseustest.c:337-343,457,499).
+    The GPU path's file sink must produce the same bytes; compared with what the reference's own callbacks
+    fwrite (oracle/_ref) when that library travelled here, else with the restated oracle."""
+    path = tmp_path / "perseusdata"
+    ntransfers = 97
+    with pg.PerseusGpu(device=0, stream_flags=getattr(pg, fmt), slab_bytes=6144 * 10, nslabs=3) as h:
+        h.stream_to_file(str(path))
+        v = pg.VirtualReceiver(sample_rate=250000, seed=11)
+        v.run(6144, *h.callback, ntransfers)
+        h.flush()
+        h.stream_to_file(None)
+        v.close()
+        assert h.stats()["d2h_bytes"] == ntransfers * 8192
+    wire = coracle.synth_random(ntransfers * 6144, seed=11)
+    want = O.Ref().unpack(wire, refmode, chunk=6144) if O.Ref.available() else coracle.unpack(wire, mode)
+    assert path.read_bytes() == want.tobytes()
+
+
+def test_stream_to_file_rejects_two_formats(pg):
+    with pg.PerseusGpu(device=0, stream_flags=pg.OUT_INT32 | pg.OUT_FLOAT) as h:
+        with pytest.raises(pg.PerseusGpuError) as e:
+            h.stream_to_file("/tmp/never")
+        assert e.value.code == pg.ERR["ERRPARAM"]
+
+
+def test_sharded_recording_reassembles(pg, coracle):
+    """cfg4 structure on one GPU: each shard generates ITS byte range of the recording on the device
+    (random access generator) and unpacks it; shard checksums add up to the oracle's whole-recording checksum."""
+    nbuf = 4099
+    wire = coracle.synth_random(nbuf * 6144, seed=O.SYNTH_SEED)
+    want = coracle.checksum32(coracle.unpack(wire, O.MODE_F32))
+    for shards in (2, 4, 8):
+        acc = 0
+        for s in range(shards):
+            first, count = pg.shard_range(nbuf, shards, s)
+            with pg.PerseusGpu(device=0) as h, DevBuf(h, count * 6144) as din, DevBuf(h, count * 8192) as df:
+                h.generate(din.p, count * 6144, pg.SYNTH_RANDOM, O.SYNTH_SEED, first * 6144)
+                h.unpack(din.p, count * 6144, None, df.p, pg.OUT_FLOAT)
+                acc += h.checksum(df.p, count * 2048, first_index=first * 2048)
+        assert acc % (1 << 64) == want
