@@ -258,28 +258,19 @@ def ours(args):
         if world > 1:
             dist.barrier()
 
-    def allmax(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def allsum(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
     pg = G.load_package()
+    import importlib
+    sharding = importlib.import_module("libperseus_sdr_b200.sharding")
+    allmax = sharding.allreduce_max
+
     h = pg.PerseusGpu(device=local, chunk_bytes=args.chunk_mib << 20, nstreams=args.streams)
     if args.tile or args.stages or args.ctas or args.variant or args.store:
         h.set_tuning(variant=args.variant, tile_bytes=args.tile, stages=args.stages, ctas_per_sm=args.ctas, store_mode=args.store)
     tuning = h.get_tuning()
+    tuning["auto_rule"] = "0 = per format: tile 12288 B, ring of 3 stages when int32+float are fused, 4 stages for one format, 1 CTA/SM"
 
     nbuf = args.buffers
-    first, count = pg.shard_range(nbuf * world, world, rank)          # this rank's transfers of the N x cfg2 recording
+    first, count = sharding.rank_shard(pg, nbuf * world, world, rank)   # this rank's transfers of the N x cfg2 recording
     assert count == nbuf
     nbytes = nbuf * BUF
     ns = nbytes // 6
@@ -303,6 +294,8 @@ def ours(args):
         assert np.array_equal(wire, co.synth_random(probe, O.SYNTH_SEED, first * BUF + nbytes - probe))
         assert np.array_equal(h.to_host(d_i32 + o, probe // 6 * 8, np.uint32), co.unpack(wire, O.MODE_I32).view(np.uint32).reshape(-1))
         assert np.array_equal(h.to_host(d_f32 + o, probe // 6 * 8, np.uint32), co.unpack(wire, O.MODE_F32).view(np.uint32).reshape(-1))
+
+    recording_checksum = sharding.allreduce_sum_u64(h.checksum(d_f32, ns * 2, first_index=first * 2048))   # shard checksums add up
 
     def timed(fn, steps, warmup, sampler=None):
         for _ in range(warmup):
@@ -417,6 +410,7 @@ def ours(args):
                      "algorithmic_bytes_per_launch": BYTES_PER_SAMPLE_FUSED * ns, "bytes_per_sample": BYTES_PER_SAMPLE_FUSED,
                      "launch_ms": round(ms_step, 4), "frac_of_nominal_8TBs": round(achieved / 8000.0, 4)},
         "single_format": extra,
+        "recording_float_checksum": f"{recording_checksum:016x}",
         "e2e": e2e,
         "gpu_launches": int(launches),
         "clocks": clocks,

@@ -81,9 +81,10 @@ typedef struct perseus_vrx perseus_vrx;               /* synthetic receiver (sta
 
 typedef struct perseus_gpu_tuning {
 	int variant;       /* PERSEUS_GPU_VARIANT_*                                      (0 = auto)   */
-	int tile_bytes;    /* input bytes per pipeline stage: 6144, 12288 or 24576       (0 = default) */
-	int stages;        /* shared-memory ring depth, 2..8                             (0 = default) */
-	int ctas_per_sm;   /* persistent CTAs per SM, 1..8                               (0 = default) */
+	int tile_bytes;    /* input bytes per pipeline stage: 6144, 9216, 12288, 18432 or 24576         */
+	int stages;        /* shared-memory ring depth, 2..8                                            */
+	int ctas_per_sm;   /* persistent CTAs per SM, 1..8                                              */
+	                   /* 0 in the three fields above = chosen per output format at launch time     */
 	int store_mode;    /* 0 = default, 1 = st.global.cs (streaming), 2 = plain st.global           */
 	int reserved[3];
 } perseus_gpu_tuning;

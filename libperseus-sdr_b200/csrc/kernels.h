@@ -13,13 +13,26 @@ enum : unsigned { FMT_I32 = 1u, FMT_F32 = 2u, FMT_POW2 = 4u };
 constexpr int kConsumerThreads = 256;                  // threads that convert + store, per CTA
 constexpr int kProducerThreads = 32;                   // one warp; lane 0 issues the bulk copies
 constexpr int kMaxStages       = 8;
-constexpr int kDefaultTile     = 12288;                // two 6144-byte transfers per stage
-constexpr int kDefaultStages   = 4;
-constexpr int kDefaultCtasPerSm = 3;
 
-struct Tuning {            // resolved (no zeros) copy of perseus_gpu_tuning
+struct Tuning {            // copy of perseus_gpu_tuning; 0 in tile_bytes/stages/ctas_per_sm = pick by output format
 	int variant, tile_bytes, stages, ctas_per_sm, store_mode;
 };
+
+// Pipeline geometry actually used for a launch.  The defaults come from the sweep committed in
+// profiles/ (round 1): what matters is the wire bytes in flight per SM -- about 48 KiB when one
+// 8-byte output is written per sample, about 36 KiB when both are (fewer read bytes per byte of
+// traffic); more read-ahead than that starves the write stream and costs 5-10 % of HBM bandwidth.
+struct Geometry { int tile_bytes, stages, ctas_per_sm; };
+inline Geometry resolve_geometry(const Tuning &t, unsigned fmt)
+{
+	const bool fused = (fmt & FMT_I32) && (fmt & (FMT_F32 | FMT_POW2));
+	Geometry g;
+	g.tile_bytes = t.tile_bytes ? t.tile_bytes : 12288;     // two 6144-byte transfers per stage
+	g.stages = t.stages ? t.stages : (fused ? 3 : 4);
+	g.ctas_per_sm = t.ctas_per_sm ? t.ctas_per_sm : 1;
+	return g;
+}
+inline bool valid_tile(int tile) { return tile == 6144 || tile == 9216 || tile == 12288 || tile == 18432 || tile == 24576; }
 
 // One tile of a batched launch: which segment, which tile of it.
 struct TileRef { uint32_t seg, tile; };
@@ -32,8 +45,8 @@ cudaError_t launch_unpack(const void *in, size_t nbytes, void *out_i32, void *ou
                           const Tuning &t, int sm_count, cudaStream_t stream, int *launches);
 
 // Batched unpack over nseg segments described on the device; tile map built by the caller
-// with tile size `t.tile_bytes`.  `all_aligned` = every in/out pointer is 16-byte aligned.
-cudaError_t launch_unpack_batch(const SegDesc *d_segs, const TileRef *d_tiles, uint64_t ntiles, unsigned fmt,
+// with tile size `tile_bytes`.  `all_aligned` = every in/out pointer is 16-byte aligned.
+cudaError_t launch_unpack_batch(const SegDesc *d_segs, const TileRef *d_tiles, uint64_t ntiles, int tile_bytes, unsigned fmt,
                                 bool all_aligned, const Tuning &t, int sm_count, cudaStream_t stream, int *launches);
 
 cudaError_t launch_generate(void *dst, size_t nbytes, int pattern, uint64_t seed, uint64_t byte_offset,

@@ -119,29 +119,35 @@ int surface_latched(perseus_gpu *h)
 pg::Tuning resolve_tuning(const perseus_gpu_tuning *t)
 {
 	pg::Tuning r{};
-	r.variant = t ? t->variant : 0;
-	r.tile_bytes = t && t->tile_bytes ? t->tile_bytes : pg::kDefaultTile;
-	r.stages = t && t->stages ? t->stages : pg::kDefaultStages;
-	r.ctas_per_sm = t && t->ctas_per_sm ? t->ctas_per_sm : pg::kDefaultCtasPerSm;
-	r.store_mode = t && t->store_mode ? t->store_mode : 1;
+	if (t) {
+		r.variant = t->variant;
+		r.tile_bytes = t->tile_bytes;      // 0 = chosen per output format at launch (kernels.h resolve_geometry)
+		r.stages = t->stages;
+		r.ctas_per_sm = t->ctas_per_sm;
+		r.store_mode = t->store_mode;
+	}
+	if (r.store_mode == 0) r.store_mode = 1;
 	return r;
 }
 
 int check_tuning(const pg::Tuning &t)
 {
 	if (t.variant < 0 || t.variant > 2) return fail(PERSEUS_GPU_ERRPARAM, "tuning.variant %d not in 0..2", t.variant);
-	if (t.tile_bytes != 6144 && t.tile_bytes != 12288 && t.tile_bytes != 24576)
-		return fail(PERSEUS_GPU_ERRPARAM, "tuning.tile_bytes %d must be 6144, 12288 or 24576", t.tile_bytes);
-	if (t.stages < 2 || t.stages > pg::kMaxStages) return fail(PERSEUS_GPU_ERRPARAM, "tuning.stages %d not in 2..%d", t.stages, pg::kMaxStages);
-	if ((size_t)t.stages * t.tile_bytes > 200 * 1024)
-		return fail(PERSEUS_GPU_ERRPARAM, "tuning: stages*tile_bytes = %zu exceeds 200 KiB of shared memory", (size_t)t.stages * t.tile_bytes);
-	if (t.ctas_per_sm < 1 || t.ctas_per_sm > 8) return fail(PERSEUS_GPU_ERRPARAM, "tuning.ctas_per_sm %d not in 1..8", t.ctas_per_sm);
-	// what actually fits: 227 KiB of shared memory and 2048 threads per SM
-	const int by_smem = (int)((227 * 1024) / ((size_t)t.stages * t.tile_bytes + 1024));
-	const int by_threads = 2048 / (pg::kConsumerThreads + pg::kProducerThreads);
-	if (t.ctas_per_sm > by_smem || t.ctas_per_sm > by_threads)
-		return fail(PERSEUS_GPU_ERRPARAM, "tuning: %d CTAs/SM do not fit (shared memory allows %d, threads allow %d)", t.ctas_per_sm, by_smem, by_threads);
+	if (t.tile_bytes && !pg::valid_tile(t.tile_bytes))
+		return fail(PERSEUS_GPU_ERRPARAM, "tuning.tile_bytes %d must be 6144, 9216, 12288, 18432 or 24576", t.tile_bytes);
+	if (t.stages && (t.stages < 2 || t.stages > pg::kMaxStages)) return fail(PERSEUS_GPU_ERRPARAM, "tuning.stages %d not in 2..%d", t.stages, pg::kMaxStages);
+	if (t.ctas_per_sm < 0 || t.ctas_per_sm > 8) return fail(PERSEUS_GPU_ERRPARAM, "tuning.ctas_per_sm %d not in 1..8", t.ctas_per_sm);
 	if (t.store_mode < 1 || t.store_mode > 2) return fail(PERSEUS_GPU_ERRPARAM, "tuning.store_mode %d not in 0..2", t.store_mode);
+	// what actually fits, for either default the unset fields could resolve to: 227 KiB of shared memory, 2048 threads per SM
+	for (unsigned fmt : {1u, 3u}) {
+		const pg::Geometry g = pg::resolve_geometry(t, fmt);
+		if ((size_t)g.stages * g.tile_bytes > 200 * 1024)
+			return fail(PERSEUS_GPU_ERRPARAM, "tuning: stages*tile_bytes = %zu exceeds 200 KiB of shared memory", (size_t)g.stages * g.tile_bytes);
+		const int by_smem = (int)((227 * 1024) / ((size_t)g.stages * g.tile_bytes + 1024));
+		const int by_threads = 2048 / (pg::kConsumerThreads + pg::kProducerThreads);
+		if (g.ctas_per_sm > by_smem || g.ctas_per_sm > by_threads)
+			return fail(PERSEUS_GPU_ERRPARAM, "tuning: %d CTAs/SM do not fit (shared memory allows %d, threads allow %d)", g.ctas_per_sm, by_smem, by_threads);
+	}
 	return 0;
 }
 
@@ -547,7 +553,7 @@ int perseus_gpu_plan_create(perseus_gpu *h, const perseus_gpu_seg *segs, int nse
 		return fail(PERSEUS_GPU_ERRPARAM, "OUT_FLOAT and OUT_FLOAT_POW2 are mutually exclusive");
 	if (fmt == 0 && nseg > 0) return fail(PERSEUS_GPU_ERRPARAM, "no output requested");
 
-	const int tile = h->tune.tile_bytes;
+	const int tile = pg::resolve_geometry(h->tune, fmt).tile_bytes;
 	std::vector<pg::SegDesc> hs((size_t)nseg);
 	std::vector<pg::TileRef> ht;
 	bool aligned = true;
@@ -599,10 +605,9 @@ int64_t perseus_gpu_plan_run(perseus_gpu *h, perseus_gpu_plan *p, unsigned flags
 	int rc = bind(h);
 	if (rc) return rc;
 	if (!p) return fail(PERSEUS_GPU_ERRPARAM, "null plan");
-	if (p->tile_bytes != h->tune.tile_bytes)
-		return fail(PERSEUS_GPU_ERRPARAM, "plan was built for tile_bytes=%d, handle now uses %d", p->tile_bytes, h->tune.tile_bytes);
-	int n = 0;
-	cudaError_t e = pg::launch_unpack_batch(p->d_segs, p->d_tiles, p->ntiles, p->fmt, p->all_aligned, h->tune, h->sm_count, h->streams[0], &n);
+	int n = 0;   // the plan keeps the tile size it was built with; stages / CTAs per SM follow the handle's current tuning
+	cudaError_t e = pg::launch_unpack_batch(p->d_segs, p->d_tiles, p->ntiles, p->tile_bytes, p->fmt, p->all_aligned, h->tune, h->sm_count,
+	                                        h->streams[0], &n);
 	if (e != cudaSuccess) return fail(PERSEUS_GPU_CUDAERR, "batched unpack launch failed: %s", cudaGetErrorString(e));
 	h->stats.kernel_launches += (uint64_t)n;
 	h->stats.samples += p->nsamples;

@@ -448,6 +448,8 @@ cudaError_t launch_stream_tile(const StreamParams &p, int tile, int st, int grid
 {
 	switch (tile) {
 	case 6144: return launch_stream_st<FMT, 6144, BATCHED>(p, st, grid, stream);
+	case 9216: return launch_stream_st<FMT, 9216, BATCHED>(p, st, grid, stream);
+	case 18432: return launch_stream_st<FMT, 18432, BATCHED>(p, st, grid, stream);
 	case 12288: return launch_stream_st<FMT, 12288, BATCHED>(p, st, grid, stream);
 	case 24576: return launch_stream_st<FMT, 24576, BATCHED>(p, st, grid, stream);
 	default: return cudaErrorInvalidValue;
@@ -527,16 +529,17 @@ cudaError_t launch_unpack(const void *in, size_t nbytes, void *out_i32, void *ou
 	const bool can_stream = aligned_to(in, 16) && out16;
 	const bool use_stream = t.variant == 2 ? false : can_stream;   // variant 1 (STREAM) degrades to direct when unaligned
 
+	const Geometry g = resolve_geometry(t, fmt);
 	if (use_stream) {
 		StreamParams p{};
 		p.in = static_cast<const uint8_t *>(in);
 		p.out_i32 = static_cast<uint8_t *>(out_i32);
 		p.out_f32 = static_cast<uint8_t *>(out_f32);
 		p.in_bytes = nsamples * 6;
-		p.ntiles = (p.in_bytes + (uint64_t)t.tile_bytes - 1) / (uint64_t)t.tile_bytes;
-		p.stages = t.stages;
-		const int grid = persistent_grid(p.ntiles, sm_count, t.ctas_per_sm);
-		cudaError_t e = launch_stream_fmt<false>(p, fmt, t.tile_bytes, t.store_mode, grid, stream);
+		p.ntiles = (p.in_bytes + (uint64_t)g.tile_bytes - 1) / (uint64_t)g.tile_bytes;
+		p.stages = g.stages;
+		const int grid = persistent_grid(p.ntiles, sm_count, g.ctas_per_sm);
+		cudaError_t e = launch_stream_fmt<false>(p, fmt, g.tile_bytes, t.store_mode, grid, stream);
 		if (e == cudaSuccess) *launches = 1;
 		return e;
 	}
@@ -557,25 +560,27 @@ cudaError_t launch_unpack(const void *in, size_t nbytes, void *out_i32, void *ou
 	return e;
 }
 
-cudaError_t launch_unpack_batch(const SegDesc *d_segs, const TileRef *d_tiles, uint64_t ntiles, unsigned fmt, bool all_aligned,
-                                const Tuning &t, int sm_count, cudaStream_t stream, int *launches)
+cudaError_t launch_unpack_batch(const SegDesc *d_segs, const TileRef *d_tiles, uint64_t ntiles, int tile_bytes, unsigned fmt,
+                                bool all_aligned, const Tuning &t, int sm_count, cudaStream_t stream, int *launches)
 {
 	*launches = 0;
 	if (ntiles == 0) return cudaSuccess;
 	cudaError_t e;
+	const Geometry g = resolve_geometry(t, fmt);
 	if (all_aligned && t.variant != 2) {
 		StreamParams p{};
 		p.segs = d_segs;
 		p.tiles = d_tiles;
 		p.ntiles = ntiles;
-		p.stages = t.stages;
-		e = launch_stream_fmt<true>(p, fmt, t.tile_bytes, t.store_mode, persistent_grid(ntiles, sm_count, t.ctas_per_sm), stream);
+		p.stages = g.stages;
+		if ((size_t)g.stages * tile_bytes > 200 * 1024) p.stages = (int)(200 * 1024 / tile_bytes);
+		e = launch_stream_fmt<true>(p, fmt, tile_bytes, t.store_mode, persistent_grid(ntiles, sm_count, g.ctas_per_sm), stream);
 	} else {
 		DirectParams p{};
 		p.segs = d_segs;
 		p.tiles = d_tiles;
 		p.ntiles = ntiles;
-		p.tile_bytes = t.tile_bytes;
+		p.tile_bytes = tile_bytes;
 		e = launch_direct_batch_fmt(p, fmt, persistent_grid(ntiles, sm_count, 16), stream);
 	}
 	if (e == cudaSuccess) *launches = 1;

@@ -175,7 +175,7 @@ def test_unaligned_pointers_take_the_direct_path_and_stay_exact(pg, gpu, coracle
                                  cases=[c for c in fmt_cases(pg) if c[0] in ("i32+f32", "pow2")])
 
 
-@pytest.mark.parametrize("tile", [6144, 12288, 24576])
+@pytest.mark.parametrize("tile", [6144, 9216, 12288, 18432, 24576])
 @pytest.mark.parametrize("stages", [2, 3, 8])
 def test_every_pipeline_geometry(pg, gpu, coracle, tile, stages):
     wire = coracle.synth_random(24576 * 3 * 148 + 6144 * 5 + 30, seed=tile + stages)   # > one wave, ragged end
