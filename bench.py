@@ -383,6 +383,26 @@ def ours(args):
         h.host_free(po_i); h.host_free(po_f)
     h.host_free(pin)
 
+    # -- the literal drop-in: 6144-byte transfers through perseus_gpu_input_callback (one host thread, like the
+    #    reference's poll thread), delivered by the virtual receiver from its 8-slot pageable ring
+    e2e_cb = None
+    if not args.no_callback:
+        hs = pg.PerseusGpu(device=local, stream_flags=FUSED, slab_bytes=16 << 20, nslabs=4, nstreams=2)
+        v = pg.VirtualReceiver(sample_rate=2_000_000, replay=True)
+        cbp, cbx = hs.callback
+        v.run(BUF, cbp, cbx, 4096); hs.flush()                            # warm: slabs allocated, pages touched
+        barrier()
+        t0 = time.perf_counter()
+        st = v.run(BUF, cbp, cbx, nbuf)
+        hs.flush()
+        dt = allmax(time.perf_counter() - t0)
+        hst = hs.stats()
+        e2e_cb = {"value": round(ns * world / dt / 1e6, 1), "unit": UNIT, "wire_gbs_per_gpu": round(nbytes / dt / 1e9, 2),
+                  "transfers": nbuf, "callbacks": int(st["delivered"]), "slab_stalls": hst["stalls"], "slabs": hst["slabs"],
+                  "what": "perseus_vrx_run -> perseus_gpu_input_callback per 6144-byte transfer (memcpy into a pinned 16 MiB slab, "
+                          "H2D + fused unpack per slab on 2 streams), one host thread; bounded by that thread's memcpy"}
+        v.close(); hs.close()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline_leg(args.cpu_budget_s)
@@ -417,9 +437,118 @@ def ours(args):
     }
     if e2e_rt:
         line["e2e_roundtrip"] = e2e_rt
+    if e2e_cb:
+        line["e2e_callback"] = e2e_cb
     if cpu:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
+    return 0
+
+
+def dist_setup():
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local
+
+
+def timed_region(h, fn, steps, warmup, world, sampler=None):
+    """W untimed steps, then exactly K steps between barrier+sync, CUDA events on the launching stream, max over ranks."""
+    import importlib
+    import torch
+    import torch.distributed as dist
+    sharding = importlib.import_module("libperseus_sdr_b200.sharding")
+    for _ in range(warmup):
+        fn()
+    h.sync(); torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    with (sampler if sampler is not None else _Null()):
+        h.event_record(0)
+        for _ in range(steps):
+            fn()
+        h.event_record(1)
+        h.sync(); torch.cuda.synchronize()
+        ms = h.event_elapsed_ms(0, 1)
+    if world > 1:
+        dist.barrier()
+    return sharding.allreduce_max(ms) / steps
+
+
+def mixed_rate_buffers(nrx=1024, window_s=1.024):
+    rates = [48000, 96000, 192000, 500000, 1000000, 2000000]          # SURVEY.md §8d cfg3
+    return [max(1, round(rates[r % 6] * window_s / 1024)) for r in range(nrx)]
+
+
+def other_workload(args):
+    """cfg3 / cfg4 of BASELINE.json: kernel-only lines with the same schema (no e2e legs)."""
+    import torch.distributed as dist
+    import __graft_entry__ as G
+    rank, world, local = dist_setup()
+    pg = G.load_package()
+    h = pg.PerseusGpu(device=local)
+    peak, peak_src = measured_peak()
+    sampler = ClockSampler(local)
+    if args.workload == "cfg3":
+        nbufs = mixed_rate_buffers()
+        total_in = sum(nbufs) * BUF
+        ns = total_in // 6
+        d_in, d_i, d_f = h.dev_alloc(total_in), h.dev_alloc(ns * 8), h.dev_alloc(ns * 8)
+        segs, off = [], 0
+        for r, b in enumerate(nbufs):
+            h.generate(d_in + off, b * BUF, pg.SYNTH_RANDOM, pg.SYNTH_SEED + r, 0)
+            segs.append((d_in + off, b * BUF, d_i + off // 6 * 8, d_f + off // 6 * 8))
+            off += b * BUF
+        flags = pg.OUT_INT32 | pg.OUT_FLOAT
+        plan = h.plan_create(segs, flags)
+        h.plan_run(plan)
+        bad, _ = h.verify(d_in, total_in, d_i, d_f, flags)
+        assert bad == 0, bad
+        l0 = h.stats()["kernel_launches"]
+        ms = timed_region(h, lambda: h.plan_run(plan, pg.ASYNC), args.steps, args.warmup, world, sampler)
+        launches = h.stats()["kernel_launches"] - l0 - args.warmup
+        h.plan_destroy(plan)
+        bps, scaling = BYTES_PER_SAMPLE_FUSED, "weak"
+        samples_all = ns * world
+        workload = (f"cfg3: 1024 virtual receivers at 48k/96k/192k/500k/1M/2M S/s, 1.024 s window = {sum(nbufs)} transfers x {BUF} B "
+                    f"({total_in} wire bytes) per GPU, own seed per receiver, unpacked to int32 AND float in ONE launch")
+        kernel = "unpack24_stream_kernel<I32|F32, batched>"
+    else:
+        total_buffers = 11_184_810                                    # 64 GiB of 6144-byte transfers, SURVEY.md §8d cfg4
+        first, count = pg.shard_range(total_buffers, world, rank)
+        nbytes = count * BUF
+        ns = nbytes // 6
+        d_in, d_i, d_f = h.dev_alloc(nbytes), None, h.dev_alloc(ns * 8)
+        h.generate(d_in, nbytes, pg.SYNTH_RANDOM, pg.SYNTH_SEED, first * BUF)
+        flags = pg.OUT_FLOAT
+        h.unpack(d_in, nbytes, None, d_f, flags)
+        bad, _ = h.verify(d_in, nbytes, None, d_f, flags)
+        assert bad == 0, bad
+        l0 = h.stats()["kernel_launches"]
+        ms = timed_region(h, lambda: h.unpack(d_in, nbytes, None, d_f, flags | pg.ASYNC), args.steps, args.warmup, world, sampler)
+        launches = h.stats()["kernel_launches"] - l0 - args.warmup
+        bps, scaling = BYTES_PER_SAMPLE_SINGLE, "strong"
+        samples_all = total_buffers * 1024
+        workload = (f"cfg4: 64 GiB recording ({total_buffers} transfers x {BUF} B) sharded by contiguous transfer range over {world} GPU(s), "
+                    f"this rank {count} transfers; generated on the device; float output; kernel-only")
+        kernel = "unpack24_stream_kernel<F32>"
+    achieved = bps * ns / (ms * 1e-3) / 1e9
+    if world > 1:
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": round(samples_all / (ms * 1e-3) / 1e6, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+            "dtype": "int32+f32" if bps == BYTES_PER_SAMPLE_FUSED else "f32", "data": "synthetic",
+            "config": {"workload": workload, "l2": "no flush needed: working set per step is far larger than the 126 MB L2"},
+            "roofline": {"bound": "hbm", "kernel": kernel, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src, "bytes_per_sample": bps},
+            "e2e": None, "gpu_launches": int(launches), "clocks": sampler.summary()}), flush=True)
     return 0
 
 
@@ -443,6 +572,10 @@ def main():
     ap.add_argument("--streams", type=int, default=3)
     ap.add_argument("--no-roundtrip", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-callback", action="store_true")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4"],
+                    help="cfg2 (default, the headline): 1 GiB per GPU, fused; cfg3: 1024 mixed-rate receivers in one launch; "
+                         "cfg4: 64 GiB recording sharded over the GPUs, float only")
     ap.add_argument("--cpu-budget-s", type=float, default=12.0)
     for k in ("variant", "tile", "stages", "ctas", "store"):
         ap.add_argument(f"--{k}", type=int, default=0)
@@ -455,7 +588,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", str(29500 + os.getpid() % 2000), __file__] + sys.argv[1:]
         return subprocess.call(cmd)
-    return ours(args)
+    return ours(args) if args.workload == "cfg2" else other_workload(args)
 
 
 if __name__ == "__main__":

@@ -263,7 +263,9 @@ typedef struct perseus_vrx_config {
 	/* fault injection (perseus-in.c:204-216 log-and-drop cases); 0 = never */
 	uint32_t drop_every;       /* every Nth transfer completes short -> not delivered           */
 	uint32_t swap_every;       /* every Nth transfer completes out of sequence -> not delivered */
-	uint32_t reserved[5];
+	uint32_t replay;           /* non-zero: generate only the first 8 transfers and re-deliver the ring's contents
+	                              (stream repeats every 8 transfers): isolates the hand-off cost in benchmarks */
+	uint32_t reserved[4];
 } perseus_vrx_config;
 
 typedef struct perseus_vrx_stats {        /* cf. perseus-sdr.c:719-722 */

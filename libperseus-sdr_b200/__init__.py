@@ -71,7 +71,7 @@ class Stats(C.Structure):
 class VrxConfig(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("sample_rate", C.c_int32), ("ep_max_packet", C.c_int32), ("pattern", C.c_int32),
                 ("seed", C.c_uint64), ("realtime", C.c_int32), ("drop_every", C.c_uint32), ("swap_every", C.c_uint32),
-                ("reserved", C.c_uint32 * 5)]
+                ("replay", C.c_uint32), ("reserved", C.c_uint32 * 4)]
 
 
 class VrxStats(C.Structure):
@@ -345,11 +345,11 @@ class VirtualReceiver:
     """perseus_vrx handle: the reference's transfer delivery (8-slot ring, in-order callbacks) over synthetic data."""
 
     def __init__(self, sample_rate: int = 95000, ep_max_packet: int = 0, pattern: int = SYNTH_RANDOM, seed: int = 0,
-                 realtime: bool = False, drop_every: int = 0, swap_every: int = 0):
+                 realtime: bool = False, drop_every: int = 0, swap_every: int = 0, replay: bool = False):
         cfg = VrxConfig()
         cfg.struct_size = C.sizeof(VrxConfig)
         cfg.sample_rate, cfg.ep_max_packet, cfg.pattern, cfg.seed = sample_rate, ep_max_packet, pattern, seed
-        cfg.realtime, cfg.drop_every, cfg.swap_every = int(realtime), drop_every, swap_every
+        cfg.realtime, cfg.drop_every, cfg.swap_every, cfg.replay = int(realtime), drop_every, swap_every, int(replay)
         self.v = C.c_void_p()
         self.L = lib()
         check(self.L.perseus_vrx_open(C.byref(self.v), C.byref(cfg)))

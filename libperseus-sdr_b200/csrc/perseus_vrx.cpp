@@ -41,6 +41,8 @@ struct perseus_vrx {
 	perseus_input_callback cb = nullptr;
 	void *cb_extra = nullptr;
 	int idx_expected = 0;
+	int fifo[PERSEUS_VRX_QUEUE_SIZE] = {0, 1, 2, 3, 4, 5, 6, 7};   // slots in the order they were (re)submitted to the device
+	int fifo_head = 0;
 	uint64_t submitted = 0;               // transfers handed to the "device" so far == stream position
 	std::atomic<bool> cancelling{false};
 	bool started = false;
@@ -100,6 +102,10 @@ void complete_transfer(perseus_vrx *v, int idx, uint32_t actual)
 void arm_transfer(perseus_vrx *v, int idx)
 {
 	const uint64_t seed = v->cfg.seed ? v->cfg.seed : PERSEUS_SYNTH_SEED;
+	if (v->cfg.replay && v->submitted >= PERSEUS_VRX_QUEUE_SIZE) {   // ring already holds transfers 0..7: replay them
+		v->submitted++;
+		return;
+	}
 	pg::host_generate(v->ring + (size_t)idx * v->size, v->size, v->cfg.pattern, seed, v->submitted * (uint64_t)v->size);
 	v->submitted++;
 }
@@ -111,32 +117,50 @@ void pace(perseus_vrx *v, uint64_t transfers_done)
 	std::this_thread::sleep_until(v->t_start + std::chrono::duration_cast<Clock::duration>(std::chrono::duration<double>(due)));
 }
 
+// The device completes transfers in the order they were submitted; a completed transfer is resubmitted at once
+// (perseus-in.c:263), so it re-enters the FIFO at the tail.  With no faults that is the cyclic order 0..7,0..;
+// after an out-of-order completion the submission order stays permuted, exactly as it would with libusb.
+int fifo_pop(perseus_vrx *v)
+{
+	const int idx = v->fifo[v->fifo_head];
+	v->fifo_head = (v->fifo_head + 1) % PERSEUS_VRX_QUEUE_SIZE;
+	return idx;
+}
+void fifo_push(perseus_vrx *v, int idx, int free_slots_before)
+{
+	// the FIFO always holds QUEUE_SIZE - free_slots_before entries starting at fifo_head
+	v->fifo[(v->fifo_head + PERSEUS_VRX_QUEUE_SIZE - free_slots_before) % PERSEUS_VRX_QUEUE_SIZE] = idx;
+}
+
 // Delivers `limit` completions (UINT64_MAX: until cancelled).
 void deliver(perseus_vrx *v, uint64_t limit)
 {
 	uint64_t n = 0;            // completions so far in this run
-	int idx = v->idx_expected; // device fills slots cyclically
 	while (n < limit && !v->cancelling.load(std::memory_order_acquire)) {
 		const uint64_t seq = v->submitted + 1;   // 1-based number of the transfer about to complete
 		const bool swap = v->cfg.swap_every && seq % v->cfg.swap_every == 0 && n + 1 < limit;
+		const int a = fifo_pop(v);
 		if (swap) {
-			// slots idx and idx+1 complete in the wrong order
-			const int nxt = (idx + 1) % PERSEUS_VRX_QUEUE_SIZE;
-			arm_transfer(v, idx);
-			arm_transfer(v, nxt);
+			// the two oldest submissions complete in the wrong order; each carries the data of its own stream position
+			const int b = fifo_pop(v);
+			arm_transfer(v, a);
+			arm_transfer(v, b);
 			pace(v, n + 2);
-			complete_transfer(v, nxt, v->size);
-			complete_transfer(v, idx, v->size);
+			const bool a_short = v->cfg.drop_every && seq % v->cfg.drop_every == 0;
+			const bool b_short = v->cfg.drop_every && (seq + 1) % v->cfg.drop_every == 0;
+			complete_transfer(v, b, b_short ? v->size - 6 : v->size);
+			fifo_push(v, b, 2);
+			complete_transfer(v, a, a_short ? v->size - 6 : v->size);
+			fifo_push(v, a, 1);
 			n += 2;
-			idx = (nxt + 1) % PERSEUS_VRX_QUEUE_SIZE;
 			continue;
 		}
-		arm_transfer(v, idx);
+		arm_transfer(v, a);
 		pace(v, n + 1);
 		const bool is_short = v->cfg.drop_every && seq % v->cfg.drop_every == 0;
-		complete_transfer(v, idx, is_short ? v->size - 6 : v->size);
+		complete_transfer(v, a, is_short ? v->size - 6 : v->size);
+		fifo_push(v, a, 1);
 		++n;
-		idx = (idx + 1) % PERSEUS_VRX_QUEUE_SIZE;
 	}
 }
 
@@ -159,6 +183,9 @@ int setup(perseus_vrx *v, uint32_t buffersize, perseus_input_callback cb, void *
 	v->cb = cb;
 	v->cb_extra = extra;
 	v->idx_expected = 0;
+	v->submitted = 0;                                                  // every start is a new stream
+	for (int k = 0; k < PERSEUS_VRX_QUEUE_SIZE; ++k) v->fifo[k] = k;   // perseus-in.c:95-96 submits slots 0..7 in order
+	v->fifo_head = 0;
 	v->cancelling.store(false);
 	v->stats = perseus_vrx_stats{};
 	v->t_start = Clock::now();

@@ -22,6 +22,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import subprocess
+import sys
 from pathlib import Path
 
 import numpy as np
@@ -29,6 +30,7 @@ import numpy as np
 HERE = Path(__file__).resolve().parent
 LIB_ORACLE = HERE / "liboracle.so"
 LIB_REF = HERE / "_ref" / "libperseus_ref.so"
+LIB_REFQUEUE = HERE / "_ref" / "libperseus_refqueue.so"
 
 MODE_I32, MODE_F32, MODE_F32_POW2 = 0, 1, 2
 #: (float)(INT_MAX - 256), perseustest.c:496 — exactly representable in binary32.
@@ -38,7 +40,8 @@ SYNTH_SEED = 0x5045525345555300  # "PERSEUS\0", SURVEY.md §8(d)
 
 def build(force: bool = False) -> None:
     """Compile liboracle.so (and _ref/ when /root/reference is mounted); make decides staleness."""
-    subprocess.run(["make", "-s", "-C", str(HERE)] + (["-B"] if force else []), check=True)
+    # stdout -> stderr: bench.py must print exactly one JSON line on stdout
+    subprocess.run(["make", "-s", "-C", str(HERE)] + (["-B"] if force else []), check=True, stdout=sys.stderr)
 
 
 def _u8(a) -> np.ndarray:
@@ -148,6 +151,66 @@ class Ref:
 
     def build_info(self) -> str:
         return self.L.perseus_ref_build_info().decode()
+
+
+class RefQueue:
+    """The reference's own transfer queue (/root/reference/perseus-in.c, unmodified) over the fake libusb device
+    of oracle/fakeusb.c.  start() == what perseus_start_async_input does at perseus-sdr.c:683; pump(n) completes
+    n transfers (each runs the reference's input_queue_callback); stop() == perseus-sdr.c:708-726."""
+
+    @staticmethod
+    def available() -> bool:
+        return LIB_REFQUEUE.exists()
+
+    def __init__(self, seed: int = SYNTH_SEED, drop_every: int = 0, swap_every: int = 0) -> None:
+        if not self.available():
+            raise FileNotFoundError(f"{LIB_REFQUEUE} not built (needs /root/reference at build time)")
+        L = C.CDLL(str(LIB_REFQUEUE))
+        vp, u64, u32 = C.c_void_p, C.c_uint64, C.c_uint32
+        L.fakeusb_open.restype, L.fakeusb_open.argtypes = vp, [u64, u32, u32]
+        L.fakeusb_close.restype, L.fakeusb_close.argtypes = None, [vp]
+        L.fakeusb_pump.restype, L.fakeusb_pump.argtypes = u64, [vp, u64]
+        L.refq_start.restype, L.refq_start.argtypes = vp, [vp, C.c_int, vp, vp]
+        L.refq_stop.restype, L.refq_stop.argtypes = u64, [vp, vp]
+        L.refq_bytes_received.restype, L.refq_bytes_received.argtypes = u64, [vp]
+        L.refq_ring.restype, L.refq_ring.argtypes = vp, [vp]
+        L.refq_idx_expected.restype, L.refq_idx_expected.argtypes = C.c_int, [vp]
+        self.L = L
+        self.dev = L.fakeusb_open(seed, drop_every, swap_every)
+        self.q = None
+        self._keep = None
+
+    def start(self, buffersize: int, callback, extra=None) -> None:
+        """callback: a C function pointer (int/c_void_p) or a Python callable (buf, size, extra) -> int."""
+        if callable(callback) and not isinstance(callback, (int, C.c_void_p)):
+            self._keep = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p)(callback)
+            callback = C.cast(self._keep, C.c_void_p)
+        self.q = self.L.refq_start(self.dev, buffersize, callback, extra)
+        if not self.q:
+            raise RuntimeError("perseus_input_queue_create failed")
+
+    def pump(self, n: int) -> int:
+        return int(self.L.fakeusb_pump(self.dev, n))
+
+    @property
+    def bytes_received(self) -> int:
+        return int(self.L.refq_bytes_received(self.q))
+
+    @property
+    def ring(self) -> int:
+        return int(self.L.refq_ring(self.q))
+
+    def stop(self) -> int:
+        n = int(self.L.refq_stop(self.dev, self.q))
+        self.q = None
+        return n
+
+    def close(self) -> None:
+        if self.q:
+            self.stop()
+        if self.dev:
+            self.L.fakeusb_close(self.dev)
+            self.dev = None
 
 
 # --------------------------------------------------------------------------- numpy

@@ -184,25 +184,82 @@ def test_vrx_cfg1_replay_through_reference_style_callback(pg, coracle):
     v.close()
 
 
-def test_vrx_fault_injection_follows_reference_drop_rules(pg):
-    """perseus-in.c:204-216: short or out-of-sequence transfers are counted in bytes_received but never delivered;
-    one swapped pair costs three transfers because idx_expected follows the last completed slot (:260)."""
+def model_reference_queue(n, drop_every=0, swap_every=0):
+    """The reference's completion handler as a model (perseus-in.c:199-216,260-263): FIFO of resubmitted slots,
+    deliver only the expected slot at full length, idx_expected follows the last completed slot."""
+    fifo, expected, done, pos = list(range(8)), 0, 0, 0
+    delivered = short = seq = 0
     order = []
 
+    def complete(idx, is_short):
+        nonlocal expected, delivered, short, seq
+        if idx == expected:
+            if is_short:
+                short += 1
+            else:
+                delivered += 1
+                order.append(idx)
+        else:
+            seq += 1
+        expected = (idx + 1) % 8
+        fifo.append(idx)
+
+    while done < n:
+        a = fifo.pop(0)
+        if swap_every and (pos + 1) % swap_every == 0 and done + 1 < n:
+            b = fifo.pop(0)
+            pos += 2
+            complete(b, False)
+            complete(a, False)
+            done += 2
+            continue
+        is_short = bool(drop_every) and (pos + 1) % drop_every == 0
+        pos += 1
+        complete(a, is_short)
+        done += 1
+    return delivered, short, seq, order
+
+
+def test_vrx_fault_injection_follows_reference_drop_rules(pg):
+    """perseus-in.c:204-216: short or out-of-sequence transfers are counted in bytes_received but never delivered.
+    After one out-of-order completion the resubmission order stays permuted (perseus-in.c:263 resubmits in completion
+    order), so sequence errors keep recurring: the model above and tests/test_refqueue_cpu.py (the reference's real
+    code) pin that behaviour."""
+    slots = []
+
     def cb(b, n, e):
-        order.append(b)
+        slots.append(b)
         return 0
 
     v = pg.VirtualReceiver(drop_every=5)
     st = v.run(6144, cb, None, 20)
-    assert st["dropped_short"] == 4 and st["delivered"] == 16 and st["bytes_received"] == 20 * 6144 - 4 * 6
+    assert (st["delivered"], st["dropped_short"], st["dropped_sequence"]) == model_reference_queue(20, drop_every=5)[:3] == (16, 4, 0)
+    assert st["bytes_received"] == 20 * 6144 - 4 * 6
     v.close()
-    order.clear()
-    v = pg.VirtualReceiver(swap_every=10)
-    st = v.run(6144, cb, None, 30)
-    # swaps at transfers 10 and 20 (30 is the last one: no partner); each loses 3 transfers
-    assert st["dropped_sequence"] == 6 and st["delivered"] == 24 and st["bytes_received"] == 30 * 6144
+    for swap_every, n in ((10, 30), (7, 61), (3, 40)):
+        slots.clear()
+        v = pg.VirtualReceiver(swap_every=swap_every)
+        st = v.run(6144, cb, None, n)
+        d, sh, sq, order = model_reference_queue(n, swap_every=swap_every)
+        assert (st["delivered"], st["dropped_short"], st["dropped_sequence"]) == (d, sh, sq) and sq >= 3
+        assert st["bytes_received"] == n * 6144
+        base = min(slots)
+        assert [(a - base) // 6144 for a in slots] == order or len(set(slots)) < 8
+        v.close()
+
+
+def test_vrx_replay_mode_repeats_the_first_ring(pg, coracle):
+    got = []
+
+    def cb(b, n, e):
+        got.append(bytes((C.c_ubyte * n).from_address(b)))
+        return 0
+
+    v = pg.VirtualReceiver(seed=5, replay=True)
+    v.run(6144, cb, None, 20)
     v.close()
+    first = coracle.synth_random(8 * 6144, 5).reshape(8, 6144)
+    assert got == [first[k % 8].tobytes() for k in range(20)]
 
 
 def test_vrx_async_thread_start_stop_and_stats(pg):

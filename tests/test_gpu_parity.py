@@ -458,6 +458,47 @@ def test_stream_file_is_byte_identical_to_perseustest_output(pg, coracle, tmp_pa
     assert path.read_bytes() == want.tobytes()
 
 
+@pytest.mark.skipif(not O.RefQueue.available(), reason="oracle/_ref/libperseus_refqueue.so not built")
+@pytest.mark.parametrize("faults", [{}, {"drop_every": 9}, {"swap_every": 13}])
+def test_reference_own_queue_code_drives_the_gpu_callback(pg, coracle, faults):
+    """/root/reference/perseus-in.c, compiled UNMODIFIED over a fake libusb device, registers
+    perseus_gpu_input_callback (a C function pointer, extra = perseus_gpu*) exactly as perseus_start_async_input does
+    (perseus-sdr.c:683).  The GPU output must equal the oracle's unpack of exactly the transfers the reference's queue
+    chose to deliver (same code applied with a recording Python callback)."""
+    n, seed = 120, 4242
+    delivered = []
+    rq = O.RefQueue(seed=seed, **faults)
+    rq.start(6144, lambda b, s, e: delivered.append(bytes((C.c_ubyte * s).from_address(b))) or 0)
+    rq.pump(n)
+    rq.close()
+    with pg.PerseusGpu(device=0, stream_flags=pg.OUT_INT32 | pg.OUT_FLOAT, slab_bytes=6144 * 7, nslabs=3) as h:
+        oi, of = [], []
+
+        def sink(blk, extra):
+            h.sync()
+            oi.append(h.to_host(blk.contents.dev_i32, blk.contents.nsamples * 8, np.uint32))
+            of.append(h.to_host(blk.contents.dev_f32, blk.contents.nsamples * 8, np.uint32))
+
+        h.set_sink(sink)
+        rq = O.RefQueue(seed=seed, **faults)
+        rq.start(6144, *h.callback)
+        assert rq.pump(n) == n
+        assert rq.stop() == rq_bytes(n, faults)
+        rq.close()
+        h.flush()
+        assert h.stats()["callbacks"] == len(delivered)
+    wire = np.frombuffer(b"".join(delivered), np.uint8)
+    assert len(delivered) < n or not faults
+    assert np.array_equal(np.concatenate(oi), coracle.unpack(wire, O.MODE_I32).view(np.uint32).reshape(-1))
+    assert np.array_equal(np.concatenate(of), coracle.unpack(wire, O.MODE_F32).view(np.uint32).reshape(-1))
+
+
+def rq_bytes(n, faults):
+    """bytes_received as perseus-in.c:202 counts it: every completed transfer, short ones with their short length."""
+    d = faults.get("drop_every", 0)
+    return n * 6144 - (6 * (n // d) if d else 0)
+
+
 def test_stream_to_file_rejects_two_formats(pg):
     with pg.PerseusGpu(device=0, stream_flags=pg.OUT_INT32 | pg.OUT_FLOAT) as h:
         with pytest.raises(pg.PerseusGpuError) as e:

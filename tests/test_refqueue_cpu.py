@@ -1,0 +1,73 @@
+"""SURVEY.md §8(f) row n1 on the CPU: the reference's OWN transfer queue (perseus-in.c, compiled unmodified into
+oracle/_ref/libperseus_refqueue.so over a fake libusb device) against the product's virtual receiver
+(perseus_vrx_*, libperseus_gpu.so).  Same synthetic stream, same fault schedule -> the two must make the same
+callbacks: same ring-slot addresses in the same order, same bytes, same drop accounting."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.skipif(not O.RefQueue.available(), reason="oracle/_ref/libperseus_refqueue.so not built")
+
+
+def record_reference(buffersize, n, **faults):
+    calls = []
+    rq = O.RefQueue(seed=0xABCD, **faults)
+    rq.start(buffersize, lambda buf, size, extra: calls.append((buf, size, bytes((C.c_ubyte * size).from_address(buf)))) or 0)
+    base = rq.ring
+    assert rq.pump(n) == n
+    received = rq.bytes_received
+    stopped = rq.stop()
+    rq.close()
+    return [(a - base, s, b) for a, s, b in calls], received, stopped
+
+
+def record_vrx(pg, buffersize, n, ep=0, **faults):
+    calls = []
+    v = pg.VirtualReceiver(sample_rate=2_000_000, ep_max_packet=ep, seed=0xABCD, **faults)
+    st = v.run(buffersize, lambda buf, size, extra: calls.append((buf, size, bytes((C.c_ubyte * size).from_address(buf)))) or 0, None, n)
+    v.close()
+    base = calls[0][0] - 0 if calls else 0
+    return calls, st
+
+
+@pytest.mark.parametrize("buffersize,ep", [(6144, 512), (12288, 512), (510 * 3, 510)])
+@pytest.mark.parametrize("faults", [{}, {"drop_every": 5}, {"swap_every": 7}, {"drop_every": 4, "swap_every": 9}])
+def test_virtual_receiver_equals_reference_queue(pg, buffersize, ep, faults):
+    n = 61
+    ref_calls, ref_received, ref_stopped = record_reference(buffersize, n, **faults)
+    calls, st = record_vrx(pg, buffersize, n, ep=ep, **faults)
+    # slot 0 of each ring is where the first delivered transfer (stream position 0, never faulted here) landed
+    vbase = calls[0][0]
+    assert [(a - vbase, s, b) for a, s, b in calls] == ref_calls
+    assert st["delivered"] == len(ref_calls)
+    assert st["bytes_received"] == ref_received == ref_stopped       # cancelled transfers add nothing (perseus-in.c:191-196)
+    assert st["dropped_short"] + st["dropped_sequence"] == n - len(ref_calls)
+
+
+def test_reference_queue_cancel_handshake():
+    """perseus_stop_async_input's loop (perseus-sdr.c:714-716) terminates: all 8 transfers report cancelled."""
+    rq = O.RefQueue()
+    got = []
+    rq.start(6144, lambda b, s, e: got.append(s) or 0)
+    rq.pump(11)
+    assert rq.stop() == 11 * 6144 and len(got) == 11
+    rq.close()
+
+
+def test_reference_queue_feeds_oracle_unpack(coracle):
+    """End-to-end on the CPU: reference queue -> reference-style callback (the restated oracle) == unpack of the stream."""
+    chunks = []
+
+    def cb(buf, size, extra):
+        chunks.append(coracle.unpack(np.ctypeslib.as_array((C.c_ubyte * size).from_address(buf)).copy(), O.MODE_I32))
+        return 0
+
+    rq = O.RefQueue(seed=99)
+    rq.start(6144, cb)
+    rq.pump(24)
+    rq.close()
+    want = coracle.unpack(coracle.synth_random(24 * 6144, 99), O.MODE_I32)
+    assert np.array_equal(np.concatenate(chunks), want)
