@@ -45,6 +45,28 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# stdout carries exactly ONE JSON line.  Libraries (NCCL prints its version banner on stdout, make, ...) write to
+# file descriptor 1 behind Python's back, so fd 1 is pointed at stderr for the whole run and the JSON line goes to
+# a private duplicate of the original stdout.
+_JSON_FD = None
+
+
+def claim_stdout():
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def measured_peak():
     p = ROOT / "MEASURED_PEAKS.json"
     try:
@@ -110,11 +132,26 @@ class ClockSampler:
 
 
 def bind_to_gpu_numa_node(index: int):
-    """Best effort: run (and first-touch pinned memory) on the CPUs next to this GPU."""
+    """Best effort: run (and therefore first-touch pinned memory) on the CPUs next to this GPU.  Tries NVML's ideal
+    CPU set first, then sysfs.  Returns a short description for the JSON line, or None when the host hides its topology."""
     try:
         import pynvml as N
         N.nvmlInit()
-        bus = N.nvmlDeviceGetPciInfo(N.nvmlDeviceGetHandleByIndex(index)).busId
+        dev = N.nvmlDeviceGetHandleByIndex(index)
+    except Exception:
+        return None
+    allowed = os.sched_getaffinity(0)
+    try:
+        words = (max(allowed) // 64) + 1
+        mask = N.nvmlDeviceGetCpuAffinity(dev, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1} & allowed
+        if cpus and cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+            return f"nvml cpu affinity: {len(cpus)} of {len(allowed)} cpus"
+    except Exception:
+        pass
+    try:
+        bus = N.nvmlDeviceGetPciInfo(dev).busId
         bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
         if len(bus.split(":")[0]) == 8:
             bus = bus[4:]
@@ -125,10 +162,10 @@ def bind_to_gpu_numa_node(index: int):
         for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
             a, _, b = part.partition("-")
             cpus.update(range(int(a), int(b or a) + 1))
-        cpus &= os.sched_getaffinity(0)
+        cpus &= allowed
         if cpus:
             os.sched_setaffinity(0, cpus)
-            return node
+            return f"sysfs numa node {node}: {len(cpus)} cpus"
     except Exception:
         return None
     return None
@@ -232,7 +269,7 @@ def reference_arm(args):
             "cpu_baseline": {"value": round(val, 2), "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": round(val, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -441,7 +478,7 @@ def ours(args):
         line["e2e_callback"] = e2e_cb
     if cpu:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -541,14 +578,14 @@ def other_workload(args):
     if world > 1:
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps({
+        emit({
             "metric": METRIC, "value": round(samples_all / (ms * 1e-3) / 1e6, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "int32+f32" if bps == BYTES_PER_SAMPLE_FUSED else "f32", "data": "synthetic",
             "config": {"workload": workload, "l2": "no flush needed: working set per step is far larger than the 126 MB L2"},
             "roofline": {"bound": "hbm", "kernel": kernel, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src, "bytes_per_sample": bps},
-            "e2e": None, "gpu_launches": int(launches), "clocks": sampler.summary()}), flush=True)
+            "e2e": None, "gpu_launches": int(launches), "clocks": sampler.summary()})
     return 0
 
 
@@ -582,12 +619,13 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3                                   # timing rule: at least 3 warm-up steps
-    if args.impl == "reference":
-        return reference_arm(args)
-    if args.gpus > 1 and "RANK" not in os.environ:        # convenience: relaunch ourselves under torchrun
+    if args.gpus > 1 and "RANK" not in os.environ and args.impl == "ours":        # convenience: relaunch ourselves under torchrun
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", str(29500 + os.getpid() % 2000), __file__] + sys.argv[1:]
         return subprocess.call(cmd)
+    claim_stdout()
+    if args.impl == "reference":
+        return reference_arm(args)
     return ours(args) if args.workload == "cfg2" else other_workload(args)
 
 
