@@ -365,6 +365,16 @@ def ours(args):
     except Exception:
         pass
 
+    # -- context for the roofline: what this very device sustains on one-directional streams, same run
+    probe = None
+    if not args.no_probe:
+        rd, wr, cp = (h.probe_hbm(k, 1 << 30, 10) for k in (0, 1, 2))
+        t_bound = 6 * ns / (rd * 1e9) + 16 * ns / (wr * 1e9)             # reads at the pure-read rate, then writes at the pure-write rate
+        probe = {"read_gbs": round(rd, 1), "write_gbs": round(wr, 1), "copy_gbs": round(cp, 1),
+                 "fused_mix_bound_gbs": round(BYTES_PER_SAMPLE_FUSED * ns / t_bound / 1e9, 1),
+                 "what": "plain 16-byte streaming kernels on 1 GiB (perseus_gpu_probe_hbm), best of 4 grid sizes; mix bound = "
+                         "6 B/sample at the read rate + 16 B/sample at the write rate, no overlap credit"}
+
     # -- supporting numbers: single-format kernels (14 B/sample)
     extra = {}
     short = max(3, min(args.steps, 50))
@@ -383,26 +393,39 @@ def ours(args):
         h.event_record(2); h.memcpy(d_in, pin, nbytes); h.event_record(3)
         h2d_ms.append(h.event_elapsed_ms(2, 3))
     pcie_gbs = nbytes / (min(h2d_ms) * 1e-3) / 1e9
+    pcie_concurrent = None
+    if world > 1:                                                         # all ranks copying at once: what the host can feed
+        conc = []
+        for _ in range(2):
+            barrier()
+            h.event_record(2); h.memcpy(d_in, pin, nbytes); h.event_record(3)
+            conc.append(allmax(h.event_elapsed_ms(2, 3)))
+        pcie_concurrent = nbytes / (min(conc) * 1e-3) / 1e9
     sums = []
 
     def e2e_step():
-        h.unpack(pin, nbytes, d_i32, d_f32, FUSED | pg.ASYNC)             # chunked H2D + kernels overlapped on the handle's streams
-        h.sync()
-        sums.append((h.checksum(d_i32, ns * 2), h.checksum(d_f32, ns * 2)))   # device reduce + 8-byte D2H each
+        # chunked H2D + unpack kernels + per-chunk checksum kernels, overlapped on the handle's streams ...
+        h.unpack(pin, nbytes, d_i32, d_f32, FUSED | pg.ASYNC | pg.CHECKSUM)
+        sums.append(h.get_checksums())                                   # ... then wait and read the 16-byte result
 
     s0 = h.stats()
     ms_e2e = timed(e2e_step, e2e_steps, 2)
     s1 = h.stats()
     assert len(set(sums)) == 1, "end-to-end results changed between steps"
+    assert sums[0] == (h.checksum(d_i32, ns * 2), h.checksum(d_f32, ns * 2)), "overlapped checksum differs from the whole-output checksum"
     h2d_per_step = (s1["h2d_bytes"] - s0["h2d_bytes"]) // (e2e_steps + 2)
     e2e_val = total_samples / (ms_e2e * 1e-3) / 1e6
     e2e = {"value": round(e2e_val, 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d_per_step), "d2h_bytes_per_step": 16,
            "ms_per_step": round(ms_e2e, 3), "steps": e2e_steps,
-           "what": "perseus_gpu_unpack(pinned host wire -> device int32+float), H2D in chunks overlapped with the kernels, then "
-                   "on-device checksum of both outputs read back (outputs stay in HBM, as north_star's end-to-end mode specifies)",
+           "what": "perseus_gpu_unpack(pinned host wire -> device int32+float, PERSEUS_GPU_CHECKSUM): H2D in chunks overlapped with the "
+                   "unpack and checksum kernels, then the checksums of both outputs read back (outputs stay in HBM, as north_star's "
+                   "end-to-end mode specifies)",
            "h2d_gbs_per_gpu": round(6 * ns / (ms_e2e * 1e-3) / 1e9, 2), "pcie_h2d_gbs_measured": round(pcie_gbs, 2),
            "frac_of_measured_pcie": round(6 * ns / (ms_e2e * 1e-3) / 1e9 / pcie_gbs, 4),
            "frac_of_gen5_x16_theory": round(6 * ns / (ms_e2e * 1e-3) / 1e9 / PCIE_GEN5_X16_GBS, 4)}
+    if pcie_concurrent:
+        e2e["pcie_h2d_gbs_all_ranks_at_once"] = round(pcie_concurrent, 2)
+        e2e["frac_of_concurrent_pcie"] = round(6 * ns / (ms_e2e * 1e-3) / 1e9 / pcie_concurrent, 4)
 
     e2e_rt = None
     if not args.no_roundtrip:
@@ -465,7 +488,7 @@ def ours(args):
         "roofline": {"bound": "hbm", "kernel": "unpack24_stream_kernel<I32|F32>", "achieved": round(achieved, 1), "peak": peak,
                      "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": BYTES_PER_SAMPLE_FUSED * ns, "bytes_per_sample": BYTES_PER_SAMPLE_FUSED,
-                     "launch_ms": round(ms_step, 4), "frac_of_nominal_8TBs": round(achieved / 8000.0, 4)},
+                     "launch_ms": round(ms_step, 4), "frac_of_nominal_8TBs": round(achieved / 8000.0, 4), "in_run_probe": probe},
         "single_format": extra,
         "recording_float_checksum": f"{recording_checksum:016x}",
         "e2e": e2e,
@@ -610,6 +633,7 @@ def main():
     ap.add_argument("--no-roundtrip", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-callback", action="store_true")
+    ap.add_argument("--no-probe", action="store_true")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4"],
                     help="cfg2 (default, the headline): 1 GiB per GPU, fused; cfg3: 1024 mixed-rate receivers in one launch; "
                          "cfg4: 64 GiB recording sharded over the GPUs, float only")

@@ -72,6 +72,9 @@ typedef struct perseus_vrx perseus_vrx;               /* synthetic receiver (sta
 #define PERSEUS_GPU_OUT_FLOAT       0x0002u  /* write out_f32, reference scale (user_data_callback_c_f) */
 #define PERSEUS_GPU_OUT_FLOAT_POW2  0x0004u  /* write out_f32, 2^-31 scale (mutually exclusive with OUT_FLOAT) */
 #define PERSEUS_GPU_ASYNC           0x0100u  /* enqueue only; complete with perseus_gpu_sync() */
+#define PERSEUS_GPU_CHECKSUM        0x0200u  /* perseus_gpu_unpack: also accumulate the checksum (see perseus_gpu_checksum) of
+                                                every output it produces, piece by piece on the streams that produce them, so
+                                                it overlaps the copies; read the totals with perseus_gpu_get_checksums() */
 /* flags == 0 means: produce whatever non-NULL output pointers were passed (float = reference scale). */
 
 /* kernel selection (perseus_gpu_tuning.variant) */
@@ -127,6 +130,10 @@ int64_t perseus_gpu_unpack(perseus_gpu *h, const void *buf, size_t nbytes,
 
 /* Waits for everything queued on the handle; returns the first latched error. */
 int perseus_gpu_sync(perseus_gpu *h);
+
+/* Checksums of the int32 and float outputs of the most recent perseus_gpu_unpack(..., PERSEUS_GPU_CHECKSUM) call
+ * (word index 0 = first output word of that call; a format that was not produced reports 0).  Waits for the call. */
+int perseus_gpu_get_checksums(perseus_gpu *h, uint64_t *sum_i32, uint64_t *sum_f32);
 
 /* ---- batched launch: many independent receivers in ONE kernel launch --------------------- */
 typedef struct perseus_gpu_seg {
@@ -239,6 +246,14 @@ int perseus_gpu_checksum(perseus_gpu *h, const void *dev_words, size_t nwords, u
  *         *first_bad_word (index into the interleaved output) are filled when non-NULL. */
 int perseus_gpu_verify(perseus_gpu *h, const void *dev_in, size_t nbytes, const void *dev_i32, const void *dev_f32,
                        unsigned flags, uint64_t *nmismatch, uint64_t *first_bad_word);
+
+/* ---- in-run roofline context: what THIS device sustains on one-directional HBM streams -----------------
+ * kind 0 = read nbytes, 1 = write nbytes, 2 = copy nbytes (traffic counted = 2*nbytes).  Runs `reps` launches of a plain
+ * streaming kernel (best grid of a small built-in set) on scratch memory and returns the best GB/s in *gbs. */
+#define PERSEUS_GPU_PROBE_READ  0
+#define PERSEUS_GPU_PROBE_WRITE 1
+#define PERSEUS_GPU_PROBE_COPY  2
+int perseus_gpu_probe_hbm(perseus_gpu *h, int kind, size_t nbytes, int reps, double *gbs);
 
 /* ---- multi-GPU sharding: contiguous ranges of whole transfers, no exchange --- */
 /* Shard `shard` of `nshards` of a recording of `total_buffers` transfers gets

@@ -19,7 +19,7 @@ LIB_PATH = PKG_DIR / "lib" / "libperseus_gpu.so"
 HEADER = REPO / "include" / "perseus-gpu.h"
 
 # include/perseus-gpu.h
-OUT_INT32, OUT_FLOAT, OUT_FLOAT_POW2, ASYNC = 0x1, 0x2, 0x4, 0x100
+OUT_INT32, OUT_FLOAT, OUT_FLOAT_POW2, ASYNC, CHECKSUM = 0x1, 0x2, 0x4, 0x100, 0x200
 VARIANT_AUTO, VARIANT_STREAM, VARIANT_DIRECT = 0, 1, 2
 SYNTH_RANDOM, SYNTH_RAMP = 0, 1
 SYNTH_SEED = 0x5045525345555300
@@ -107,6 +107,7 @@ def lib() -> C.CDLL:
         "perseus_gpu_close": (ci, [vp]),
         "perseus_gpu_unpack": (i64, [vp, vp, sz, vp, vp, C.c_uint]),
         "perseus_gpu_sync": (ci, [vp]),
+        "perseus_gpu_get_checksums": (ci, [vp, P(u64), P(u64)]),
         "perseus_gpu_unpack_batch": (i64, [vp, P(Seg), ci, C.c_uint]),
         "perseus_gpu_plan_create": (ci, [vp, P(Seg), ci, C.c_uint, P(vp)]),
         "perseus_gpu_plan_run": (i64, [vp, vp, C.c_uint]),
@@ -136,6 +137,7 @@ def lib() -> C.CDLL:
         "perseus_gpu_checksum": (ci, [vp, vp, sz, u64, P(u64)]),
         "perseus_gpu_verify": (ci, [vp, vp, sz, vp, vp, C.c_uint, P(u64), P(u64)]),
         "perseus_gpu_shard_range": (ci, [u64, ci, ci, P(u64), P(u64)]),
+        "perseus_gpu_probe_hbm": (ci, [vp, ci, sz, ci, P(C.c_double)]),
         "perseus_vrx_open": (ci, [P(vp), P(VrxConfig)]),
         "perseus_vrx_close": (ci, [vp]),
         "perseus_vrx_get_sampling_rates": (ci, [P(ci), C.c_uint]),
@@ -222,6 +224,12 @@ class PerseusGpu:
 
     def sync(self) -> None:
         check(self.L.perseus_gpu_sync(self.h))
+
+    def get_checksums(self) -> tuple[int, int]:
+        """(int32 checksum, float checksum) accumulated by the last unpack(..., CHECKSUM); waits for it."""
+        a, b = C.c_uint64(), C.c_uint64()
+        check(self.L.perseus_gpu_get_checksums(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def unpack_batch(self, segs: list[tuple[int, int, int | None, int | None]], flags: int = 0) -> int:
         arr = (Seg * max(1, len(segs)))(*[Seg(a, n, oi, of) for a, n, oi, of in segs])
@@ -317,6 +325,12 @@ class PerseusGpu:
         s = C.c_uint64()
         check(self.L.perseus_gpu_checksum(self.h, dev_words, nwords, first_index, C.byref(s)))
         return s.value
+
+    def probe_hbm(self, kind: int, nbytes: int = 1 << 30, reps: int = 10) -> float:
+        """GB/s this device sustains on a pure read (0), pure write (1) or copy (2) stream."""
+        g = C.c_double()
+        check(self.L.perseus_gpu_probe_hbm(self.h, kind, nbytes, reps, C.byref(g)))
+        return g.value
 
     def verify(self, dev_in: int, nbytes: int, dev_i32: int | None, dev_f32: int | None, flags: int = 0) -> tuple[int, int]:
         """Returns (mismatching words, first bad word); raises only on errors other than MISMATCH."""

@@ -51,12 +51,15 @@ cudaError_t launch_unpack_batch(const SegDesc *d_segs, const TileRef *d_tiles, u
 
 cudaError_t launch_generate(void *dst, size_t nbytes, int pattern, uint64_t seed, uint64_t byte_offset,
                             cudaStream_t stream);
-// *d_sum (device, zeroed by the callee) += checksum of nwords 32-bit words
+// *d_sum (device; zeroed first unless `accumulate`) += checksum of nwords 32-bit words
 cudaError_t launch_checksum(const void *words, size_t nwords, uint64_t first_index, unsigned long long *d_sum,
-                            cudaStream_t stream);
+                            cudaStream_t stream, bool accumulate = false);
 // d_result[0] = mismatching words, d_result[1] = lowest mismatching word index (callee initialises)
 cudaError_t launch_verify(const void *in, size_t nbytes, const void *out_i32, const void *out_f32, unsigned fmt,
                           unsigned long long *d_result, cudaStream_t stream);
+
+// One-directional HBM streams for in-run roofline context: kind 0 = read src, 1 = write dst, 2 = copy src -> dst.
+cudaError_t launch_probe(int kind, const void *src, void *dst, size_t nbytes, int sm_count, int ctas_per_sm, cudaStream_t stream);
 
 // Host mirror of the device generator (bit-identical), for perseus_synth_fill and the virtual receiver.
 void host_generate(uint8_t *dst, size_t nbytes, int pattern, uint64_t seed, uint64_t byte_offset);

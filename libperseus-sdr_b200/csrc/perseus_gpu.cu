@@ -61,6 +61,7 @@ struct perseus_gpu {
 	cudaEvent_t events[kEventSlots]{};
 	unsigned long long *d_scratch = nullptr;   // 2 x u64: checksum / verify results
 	unsigned long long *h_scratch = nullptr;   // pinned mirror
+	unsigned long long *d_sums = nullptr;      // 2 x u64: running checksums of PERSEUS_GPU_CHECKSUM calls (int32, float)
 	// staging for perseus_gpu_unpack with host pointers (one slot per stream)
 	size_t chunk_bytes = 0;
 	uint8_t *stage_in[kMaxStreams]{};
@@ -211,6 +212,19 @@ int do_launch(perseus_gpu *h, const void *in, size_t nbytes, void *o_i32, void *
 	h->stats.kernel_launches += (uint64_t)n;
 	h->stats.samples += nbytes / 6;
 	h->stats.bytes_in += nbytes / 6 * 6;
+	return 0;
+}
+
+// Queues the checksum of the piece just unpacked behind its kernel, on the same stream (PERSEUS_GPU_CHECKSUM).
+int queue_checksums(perseus_gpu *h, const void *o_i32, const void *o_f32, uint64_t nsamples, uint64_t first_sample, cudaStream_t st)
+{
+	const void *outs[2] = {o_i32, o_f32};
+	for (int k = 0; k < 2; ++k) {
+		if (!outs[k] || nsamples == 0) continue;
+		cudaError_t e = pg::launch_checksum(outs[k], nsamples * 2, first_sample * 2, h->d_sums + k, st, /*accumulate=*/true);
+		if (e != cudaSuccess) return fail(PERSEUS_GPU_CUDAERR, "checksum launch failed: %s", cudaGetErrorString(e));
+		h->stats.kernel_launches++;
+	}
 	return 0;
 }
 
@@ -445,6 +459,8 @@ int perseus_gpu_open(perseus_gpu **out, const perseus_gpu_config *ucfg)
 		if (e != cudaSuccess) return bail(fail(PERSEUS_GPU_CUDAERR, "cudaEventCreate: %s", cudaGetErrorString(e)));
 	}
 	e = cudaMalloc(&h->d_scratch, 2 * sizeof(unsigned long long));
+	if (e == cudaSuccess) e = cudaMalloc(&h->d_sums, 2 * sizeof(unsigned long long));
+	if (e == cudaSuccess) e = cudaMemset(h->d_sums, 0, 2 * sizeof(unsigned long long));
 	if (e == cudaSuccess) e = cudaHostAlloc(&h->h_scratch, 2 * sizeof(unsigned long long), cudaHostAllocDefault);
 	if (e != cudaSuccess) return bail(fail(PERSEUS_GPU_CUDAERR, "scratch allocation: %s", cudaGetErrorString(e)));
 	*out = h;
@@ -475,6 +491,7 @@ int perseus_gpu_close(perseus_gpu *h)
 			if (h->stage_out[s][1]) cudaFree(h->stage_out[s][1]);
 		}
 		if (h->d_scratch) cudaFree(h->d_scratch);
+		if (h->d_sums) cudaFree(h->d_sums);
 		if (h->h_scratch) cudaFreeHost(h->h_scratch);
 		for (int k = 0; k < kEventSlots; ++k)
 			if (h->events[k]) cudaEventDestroy(h->events[k]);
@@ -507,8 +524,9 @@ int64_t perseus_gpu_unpack(perseus_gpu *h, const void *buf, size_t nbytes, void 
 {
 	int rc = bind(h);
 	if (rc) return rc;
-	if (flags & ~(PERSEUS_GPU_OUT_INT32 | PERSEUS_GPU_OUT_FLOAT | PERSEUS_GPU_OUT_FLOAT_POW2 | PERSEUS_GPU_ASYNC))
+	if (flags & ~(PERSEUS_GPU_OUT_INT32 | PERSEUS_GPU_OUT_FLOAT | PERSEUS_GPU_OUT_FLOAT_POW2 | PERSEUS_GPU_ASYNC | PERSEUS_GPU_CHECKSUM))
 		return fail(PERSEUS_GPU_ERRPARAM, "unknown flag bits 0x%x", flags);
+	const bool want_sums = flags & PERSEUS_GPU_CHECKSUM;
 	unsigned fmt = 0;
 	rc = resolve_fmt(flags, out_i32, out_f32, &fmt);
 	if (rc) return rc;
@@ -520,6 +538,12 @@ int64_t perseus_gpu_unpack(perseus_gpu *h, const void *buf, size_t nbytes, void 
 	if ((out_i32 && ((uintptr_t)out_i32 & 3)) || (out_f32 && ((uintptr_t)out_f32 & 3)))
 		return fail(PERSEUS_GPU_ERRPARAM, "output pointers must be 4-byte aligned");
 
+	if (want_sums) {   // totals restart with this call; everything queued earlier has to be done with them first
+		rc = perseus_gpu_sync(h);
+		if (rc) return rc;
+		CU(h, cudaMemsetAsync(h->d_sums, 0, 2 * sizeof(unsigned long long), h->streams[0]));
+		CU(h, cudaStreamSynchronize(h->streams[0]));
+	}
 	const Mem min_ = classify(buf);
 	const Mem mi = out_i32 ? classify(out_i32) : Mem::Device;
 	const Mem mf = out_f32 ? classify(out_f32) : Mem::Device;
@@ -528,6 +552,7 @@ int64_t perseus_gpu_unpack(perseus_gpu *h, const void *buf, size_t nbytes, void 
 	if (in_dev && oi_dev && of_dev) {
 		rc = do_launch(h, buf, ns * 6, out_i32, out_f32, fmt, h->streams[0]);
 		if (rc) return rc;
+		if (want_sums && (rc = queue_checksums(h, out_i32, out_f32, ns, 0, h->streams[0]))) return rc;
 	} else {
 		// staged pipeline: chunk c uses stream/slot c % nstreams; H2D, kernel and D2H of
 		// neighbouring chunks overlap, stream order protects slot reuse.
@@ -551,6 +576,7 @@ int64_t perseus_gpu_unpack(perseus_gpu *h, const void *buf, size_t nbytes, void 
 			uint8_t *kf = out_f32 ? (of_dev ? static_cast<uint8_t *>(out_f32) + o : h->stage_out[s][1]) : nullptr;
 			rc = do_launch(h, kin, n, ki, kf, fmt, st);
 			if (rc) return rc;
+			if (want_sums && (rc = queue_checksums(h, ki, kf, n / 6, off / 6, st))) return rc;
 			if (out_i32 && !oi_dev) {
 				CU(h, cudaMemcpyAsync(static_cast<uint8_t *>(out_i32) + o, ki, on, cudaMemcpyDeviceToHost, st));
 				h->stats.d2h_bytes += on;
@@ -567,6 +593,18 @@ int64_t perseus_gpu_unpack(perseus_gpu *h, const void *buf, size_t nbytes, void 
 		if (rc) return rc;
 	}
 	return (int64_t)ns;
+}
+
+int perseus_gpu_get_checksums(perseus_gpu *h, uint64_t *sum_i32, uint64_t *sum_f32)
+{
+	int rc = perseus_gpu_sync(h);
+	if (rc) return rc;
+	CU(h, cudaMemcpyAsync(h->h_scratch, h->d_sums, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->streams[0]));
+	CU(h, cudaStreamSynchronize(h->streams[0]));
+	h->stats.d2h_bytes += 2 * sizeof(unsigned long long);
+	if (sum_i32) *sum_i32 = h->h_scratch[0];
+	if (sum_f32) *sum_f32 = h->h_scratch[1];
+	return 0;
 }
 
 // ---- batched ------------------------------------------------------------------------------------
@@ -917,6 +955,44 @@ int perseus_gpu_verify(perseus_gpu *h, const void *dev_in, size_t nbytes, const 
 	if (first_bad_word) *first_bad_word = h->h_scratch[1];
 	if (h->h_scratch[0])
 		return fail(PERSEUS_GPU_MISMATCH, "%llu output words differ from the per-sample recomputation (first at word %llu)", h->h_scratch[0], h->h_scratch[1]);
+	return 0;
+}
+
+int perseus_gpu_probe_hbm(perseus_gpu *h, int kind, size_t nbytes, int reps, double *gbs)
+{
+	int rc = bind(h);
+	if (rc) return rc;
+	if (kind < 0 || kind > 2 || !gbs || reps < 1 || nbytes < (1u << 20)) return fail(PERSEUS_GPU_ERRPARAM, "bad probe arguments");
+	nbytes -= nbytes % 16;
+	void *a = nullptr, *b = nullptr;
+	cudaError_t e = cudaMalloc(&a, nbytes);
+	if (e == cudaSuccess && kind == 2) e = cudaMalloc(&b, nbytes);
+	if (e != cudaSuccess) {
+		if (a) cudaFree(a);
+		cudaGetLastError();
+		return fail(PERSEUS_GPU_NOMEM, "probe scratch: %s", cudaGetErrorString(e));
+	}
+	cudaStream_t st = h->streams[0];
+	cudaMemsetAsync(a, 0x5A, nbytes, st);
+	double best = 0.0;
+	cudaEvent_t e0 = h->events[kEventSlots - 2], e1 = h->events[kEventSlots - 1];
+	for (int ctas : {2, 4, 8, 16}) {
+		float ms = 0.f;
+		e = pg::launch_probe(kind, a, kind == 2 ? b : a, nbytes, h->sm_count, ctas, st);   // warm
+		if (e == cudaSuccess) e = cudaEventRecord(e0, st);
+		for (int r = 0; r < reps && e == cudaSuccess; ++r) e = pg::launch_probe(kind, a, kind == 2 ? b : a, nbytes, h->sm_count, ctas, st);
+		if (e == cudaSuccess) e = cudaEventRecord(e1, st);
+		if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+		if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+		if (e != cudaSuccess) break;
+		h->stats.kernel_launches += (uint64_t)reps + 1;
+		const double g = (kind == 2 ? 2.0 : 1.0) * (double)nbytes * reps / (ms * 1e-3) / 1e9;
+		if (g > best) best = g;
+	}
+	cudaFree(a);
+	if (b) cudaFree(b);
+	if (e != cudaSuccess) return fail(PERSEUS_GPU_CUDAERR, "probe failed: %s", cudaGetErrorString(e));
+	*gbs = best;
 	return 0;
 }
 

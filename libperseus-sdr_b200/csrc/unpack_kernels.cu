@@ -417,6 +417,46 @@ __global__ void __launch_bounds__(256) verify_kernel(const uint8_t *in, uint64_t
 	if (bad) { atomicAdd(&result[0], bad); atomicMin(&result[1], first); }
 }
 
+// ------------------------------------------------------------------ in-run HBM probes (roofline context)
+// Pure-read, pure-write and copy streams with the same access style as the product kernels (16-byte vectors,
+// evict-first, 4 independent requests per thread), so bench.py can put the unpack's read/write mix next to what
+// the same device does on one-directional traffic in the same run.
+__global__ void __launch_bounds__(256) probe_read_kernel(const uint4 *__restrict__ p, uint64_t n, uint4 *sink)
+{
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	uint4 acc = make_uint4(0, 0, 0, 0);
+	for (; i + 3 * stride < n; i += 4 * stride) {
+		uint4 v[4];
+#pragma unroll
+		for (int k = 0; k < 4; ++k) v[k] = __ldcs(p + i + k * stride);
+#pragma unroll
+		for (int k = 0; k < 4; ++k) { acc.x ^= v[k].x; acc.y ^= v[k].y; acc.z ^= v[k].z; acc.w ^= v[k].w; }
+	}
+	for (; i < n; i += stride) { const uint4 v = __ldcs(p + i); acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w; }
+	if ((acc.x & acc.y & acc.z & acc.w) == 0x9E3779B9u) *sink = acc;   // practically never: keeps the loads alive
+}
+
+__global__ void __launch_bounds__(256) probe_write_kernel(uint4 *__restrict__ p, uint64_t n, uint4 v)
+{
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) __stcs(p + i, v);
+}
+
+__global__ void __launch_bounds__(256) probe_copy_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, uint64_t n)
+{
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	for (; i + 3 * stride < n; i += 4 * stride) {
+		uint4 v[4];
+#pragma unroll
+		for (int k = 0; k < 4; ++k) v[k] = __ldcs(src + i + k * stride);
+#pragma unroll
+		for (int k = 0; k < 4; ++k) __stcs(dst + i + k * stride, v[k]);
+	}
+	for (; i < n; i += stride) __stcs(dst + i, __ldcs(src + i));
+}
+
 // ------------------------------------------------------------------ dispatch tables
 template <unsigned FMT, int TILE, int ST, bool BATCHED>
 cudaError_t launch_stream_inst(const StreamParams &p, int grid, cudaStream_t stream)
@@ -613,9 +653,10 @@ cudaError_t launch_generate(void *dst, size_t nbytes, int pattern, uint64_t seed
 	return cudaGetLastError();
 }
 
-cudaError_t launch_checksum(const void *words, size_t nwords, uint64_t first_index, unsigned long long *d_sum, cudaStream_t stream)
+cudaError_t launch_checksum(const void *words, size_t nwords, uint64_t first_index, unsigned long long *d_sum, cudaStream_t stream,
+                            bool accumulate)
 {
-	cudaError_t e = cudaMemsetAsync(d_sum, 0, sizeof(unsigned long long), stream);
+	cudaError_t e = accumulate ? cudaSuccess : cudaMemsetAsync(d_sum, 0, sizeof(unsigned long long), stream);
 	if (e != cudaSuccess || nwords == 0) return e;
 	uint64_t blocks = (nwords + 256 * 8 - 1) / (256 * 8);
 	if (blocks > 148 * 16) blocks = 148 * 16;
@@ -634,6 +675,19 @@ cudaError_t launch_verify(const void *in, size_t nbytes, const void *out_i32, co
 	if (blocks > 148 * 32) blocks = 148 * 32;
 	verify_kernel<<<(int)blocks, 256, 0, stream>>>(static_cast<const uint8_t *>(in), ns, static_cast<const uint32_t *>(out_i32),
 	                                               static_cast<const uint32_t *>(out_f32), fmt, d_result);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_probe(int kind, const void *src, void *dst, size_t nbytes, int sm_count, int ctas_per_sm, cudaStream_t stream)
+{
+	const uint64_t n = nbytes / 16;
+	const int grid = sm_count * ctas_per_sm;
+	switch (kind) {
+	case 0: probe_read_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint4 *>(src), n, static_cast<uint4 *>(dst)); break;
+	case 1: probe_write_kernel<<<grid, 256, 0, stream>>>(static_cast<uint4 *>(dst), n, make_uint4(1, 2, 3, 4)); break;
+	case 2: probe_copy_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint4 *>(src), static_cast<uint4 *>(dst), n); break;
+	default: return cudaErrorInvalidValue;
+	}
 	return cudaGetLastError();
 }
 

@@ -190,6 +190,44 @@ def test_every_pipeline_geometry(pg, gpu, coracle, tile, stages):
     gpu.set_tuning()
 
 
+def test_randomised_sizes_alignments_formats_geometries(pg, gpu, coracle):
+    """Seeded fuzz: 300 random (size, input misalignment, output misalignment, format, kernel variant, geometry) cases."""
+    rng = np.random.default_rng(20261017)
+    big = coracle.synth_random(400_000, seed=77)
+    cases = fmt_cases(pg)
+    tiles = [0, 6144, 9216, 12288, 18432, 24576]
+    for it in range(300):
+        n = int(rng.integers(0, 400_000 - 64)) if it % 3 else int(rng.integers(0, 700))
+        in_off = int(rng.integers(0, 32)) if it % 2 else 0
+        out_off = 4 * int(rng.integers(0, 8)) if it % 4 == 1 else 0
+        tile, stages, ctas = int(rng.choice(tiles)), int(rng.choice([0, 2, 3, 5, 8])), int(rng.choice([0, 1, 2, 4]))
+        try:
+            gpu.set_tuning(variant=int(rng.integers(0, 3)), tile_bytes=tile, stages=stages, ctas_per_sm=ctas, store_mode=int(rng.integers(0, 3)))
+        except pg.PerseusGpuError:
+            gpu.set_tuning()
+        start = int(rng.integers(0, 64))
+        check_against_oracle(pg, gpu, coracle, big[start:start + n], in_off=in_off, out_off=out_off, cases=[cases[it % len(cases)]])
+    gpu.set_tuning()
+
+
+def test_offsets_beyond_4_gib(pg, gpu, coracle):
+    """Byte offsets exceed 2^32 in cfg4-sized recordings: unpack 4.5 GiB in one call and compare windows around the
+    4 GiB input boundary, the 4 GiB output boundary and the end against the oracle; everything else by the verify kernel."""
+    nbuf = 750_000                                    # 4 608 000 000 bytes in, 6 144 000 000 bytes out
+    n = nbuf * 6144
+    with DevBuf(gpu, n) as din, DevBuf(gpu, n // 6 * 8) as df:
+        gpu.generate(din.p, n, pg.SYNTH_RANDOM, O.SYNTH_SEED, 0)
+        assert gpu.unpack(din.p, n, None, df.p, pg.OUT_FLOAT) == n // 6
+        assert gpu.verify(din.p, n, None, df.p, pg.OUT_FLOAT)[0] == 0
+        win = 6144 * 4
+        for centre in ((1 << 32), (1 << 32) * 6 // 8, n - win // 2):      # input boundary, output boundary (in input bytes), end
+            off = (centre - win // 2) // 6144 * 6144
+            wire = gpu.to_host(din.p + off, win, np.uint8)
+            assert np.array_equal(wire, coracle.synth_random(win, O.SYNTH_SEED, off))
+            got = gpu.to_host(df.p + off // 6 * 8, win // 6 * 8, np.uint32)
+            assert np.array_equal(got, coracle.unpack(wire, O.MODE_F32).view(np.uint32).reshape(-1))
+
+
 def test_device_generator_matches_oracle_definition(pg, gpu, coracle):
     for off, n in ((0, 6144 * 3), (8, 100_000), (3, 1000), (12345, 7777), ((1 << 36) + 11, 4099)):
         for misalign in (0, 1, 4):
@@ -234,6 +272,25 @@ def test_host_pointers_pageable_and_pinned(pg, coracle):
         assert st["h2d_bytes"] == 3 * ns * 6 and st["d2h_bytes"] == 3 * ns * 8 and st["kernel_launches"] >= 3 * 8
         h.host_free(pin)
         h.host_free(pout)
+
+
+def test_overlapped_checksum_flag(pg, coracle):
+    """PERSEUS_GPU_CHECKSUM: per-piece checksums queued behind each piece's kernel add up to the oracle's checksum of the
+    whole output, for the one-launch device path and the chunked host path, and restart with every call."""
+    wire = coracle.synth_random(6144 * 41 + 30, seed=13)
+    ns = wire.size // 6
+    want_i = coracle.checksum32(coracle.unpack(wire, O.MODE_I32))
+    want_f = coracle.checksum32(coracle.unpack(wire, O.MODE_F32))
+    with pg.PerseusGpu(device=0, chunk_bytes=6144 * 6, nstreams=3) as h, DevBuf(h, ns * 8) as di, DevBuf(h, ns * 8) as df:
+        d_in = h.to_device(wire)
+        h.unpack(d_in, wire.size, di.p, df.p, pg.OUT_INT32 | pg.OUT_FLOAT | pg.CHECKSUM)
+        assert h.get_checksums() == (want_i, want_f)
+        h.unpack(wire.ctypes.data, wire.size, None, df.p, pg.OUT_FLOAT | pg.CHECKSUM | pg.ASYNC)      # host input, 7 chunks
+        assert h.get_checksums() == (0, want_f)
+        host_out = np.zeros(ns * 2, np.uint32)
+        h.unpack(wire.ctypes.data, wire.size, host_out.ctypes.data, None, pg.OUT_INT32 | pg.CHECKSUM)  # host in and out
+        assert h.get_checksums() == (want_i, 0) and coracle.checksum32(host_out) == want_i
+        h.dev_free(d_in)
 
 
 def test_argument_errors(pg, gpu):
