@@ -99,8 +99,10 @@ namespace {
 #define CU(h, call)                                                                                               \
 	do {                                                                                                          \
 		cudaError_t e__ = (call);                                                                                 \
-		if (e__ != cudaSuccess)                                                                                   \
+		if (e__ != cudaSuccess) {                                                                                 \
+			cudaGetLastError(); /* non-sticky errors must not show up at the next kernel launch check */          \
 			return fail(PERSEUS_GPU_CUDAERR, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+		}                                                                                                         \
 	} while (0)
 
 void latch(perseus_gpu *h, int code)

@@ -166,7 +166,7 @@ unpack24_stream_kernel(const __grid_constant__ StreamParams p)
 	if (tid == 0) {
 		for (int s = 0; s < nstages; ++s) {
 			mbar_init(smem_u32(&full_bar[s]), 1);
-			mbar_init(smem_u32(&empty_bar[s]), kConsumerThreads / 32);
+			mbar_init(smem_u32(&empty_bar[s]), kConsumerThreads);
 		}
 		fence_mbar_init();
 	}
@@ -246,8 +246,9 @@ unpack24_stream_kernel(const __grid_constant__ StreamParams p)
 			for (uint32_t k = 2 * nunits + tid; k < ns; k += kConsumerThreads)
 				emit_sample_bytes<FMT>(h.src, h.o_i32, h.o_f32, k);
 		}
-		__syncwarp();
-		if ((tid & 31) == 0) mbar_arrive(smem_u32(&empty_bar[s]));
+		// every consumer thread releases the stage itself: its own shared-memory reads are ordered before its own
+		// arrive (release), and the producer's wait (acquire) orders them before the next bulk copy into this stage
+		mbar_arrive(smem_u32(&empty_bar[s]));
 		if (++s == nstages) { s = 0; phase ^= 1; }
 	}
 }

@@ -1,0 +1,65 @@
+"""examples/perseus_gpu_replay.c — the reference's perseustest flow (perseustest.c:93-409) on the virtual receiver and the
+GPU callback, in plain C against include/perseus-gpu.h.  Built here with gcc exactly as a libperseus-sdr user would."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle import oracle as O
+
+LIBDIR = ROOT / "libperseus-sdr_b200" / "lib"
+
+
+@pytest.fixture(scope="module")
+def replay_bin(tmp_path_factory):
+    out = tmp_path_factory.mktemp("bin") / "perseus_gpu_replay"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", str(ROOT / "include"),
+                    str(ROOT / "examples" / "perseus_gpu_replay.c"), "-L", str(LIBDIR), "-lperseus_gpu", "-o", str(out)], check=True)
+    return out
+
+
+def run(binary, *args):
+    env = dict(os.environ, LD_LIBRARY_PATH=f"{LIBDIR}:{os.environ.get('LD_LIBRARY_PATH', '')}")
+    return subprocess.run([str(binary), *args], capture_output=True, text=True, env=env, timeout=120)
+
+
+def test_example_builds_as_c99_and_fails_loudly_without_a_gpu(replay_bin, tmp_path):
+    import torch
+    r = run(replay_bin, "-h")
+    assert r.returncode == 0 and "48000 95000 96000" in r.stderr
+    if not torch.cuda.is_available():
+        r = run(replay_bin, "-N", "4", "-o", str(tmp_path / "x"))
+        assert r.returncode == 1 and "perseus_gpu_open" in r.stderr          # no CPU fallback
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flag,mode", [((), O.MODE_I32), (("-p",), O.MODE_F32)])
+def test_example_output_file_equals_reference_callbacks(replay_bin, tmp_path, coracle, flag, mode):
+    out = tmp_path / "perseusdata"
+    r = run(replay_bin, "-s", "96000", "-n", "6", "-b", "1024", "-N", "211", "-o", str(out), *flag)
+    assert r.returncode == 0, r.stderr
+    assert "Sample rate 96000 S/s, buffers of 6144 bytes" in r.stderr and "kSamples read: 216" in r.stderr   # 211*6144/6000
+    wire = coracle.synth_random(211 * 6144)
+    want = O.Ref().unpack(wire, mode, chunk=6144) if O.Ref.available() else coracle.unpack(wire, mode)
+    assert out.read_bytes() == want.tobytes()
+
+
+@pytest.mark.gpu
+def test_example_rejects_illegal_buffer_sizes_like_the_reference(replay_bin, tmp_path):
+    r = run(replay_bin, "-n", "5", "-b", "1024", "-N", "3", "-o", str(tmp_path / "x"))    # 5120 is not a multiple of 6144
+    assert r.returncode == 1 and "integer multiple of 6144" in r.stderr                   # perseus-sdr.c:672
+    r = run(replay_bin, "-n", "18", "-b", "1024", "-N", "3", "-o", str(tmp_path / "x"))   # 18432 > 16320
+    assert r.returncode == 1 and "16320" in r.stderr                                       # perseus-sdr.c:663
+
+
+@pytest.mark.gpu
+def test_example_paced_run_streams_at_the_sample_rate(replay_bin, tmp_path):
+    out = tmp_path / "paced"
+    r = run(replay_bin, "-s", "2000000", "-t", "1", "-o", str(out), "-p")
+    assert r.returncode == 0, r.stderr
+    nsamples = out.stat().st_size // 8
+    assert 1.5e6 < nsamples < 2.6e6 and out.stat().st_size % 8192 == 0
+    wire = O.COracle().synth_random(6144 * 8)
+    assert out.read_bytes()[: 8 * 8192] == O.COracle().unpack(wire, O.MODE_F32).tobytes()

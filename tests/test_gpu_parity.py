@@ -556,6 +556,24 @@ def rq_bytes(n, faults):
     return n * 6144 - (6 * (n // d) if d else 0)
 
 
+def test_callback_errors_are_latched_and_surface_at_flush(pg, coracle):
+    """The reference ignores callback return values (perseus-in.c:207), so the trampoline returns 0 even when it fails;
+    the failure is reported by the next perseus_gpu_flush / close, once, and the handle stays usable."""
+    h = pg.PerseusGpu(device=0, slab_bytes=1 << 44, nslabs=2)            # 16 TiB pinned slabs cannot be allocated
+    buf = coracle.synth_random(6144, seed=1)
+    assert h.input_callback(buf.ctypes.data, 6144) == 0
+    assert h.input_callback(buf.ctypes.data, 6144) == 0                  # further transfers are dropped quietly
+    with pytest.raises(pg.PerseusGpuError) as e:
+        h.flush()
+    assert e.value.code == pg.ERR["CUDAERR"] and "cudaHostAlloc" in e.value.msg
+    h.flush()                                                            # reported once
+    with DevBuf(h, 6144) as d, DevBuf(h, 8192) as o:                     # bulk path still works on the same handle
+        h.memcpy(d.p, buf.ctypes.data, 6144)
+        assert h.unpack(d.p, 6144, o.p, None, pg.OUT_INT32) == 1024
+        assert np.array_equal(h.to_host(o.p, 8192, np.uint32), coracle.unpack(buf, O.MODE_I32).view(np.uint32).reshape(-1))
+    h.close()
+
+
 def test_stream_to_file_rejects_two_formats(pg):
     with pg.PerseusGpu(device=0, stream_flags=pg.OUT_INT32 | pg.OUT_FLOAT) as h:
         with pytest.raises(pg.PerseusGpuError) as e:
