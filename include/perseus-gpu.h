@@ -89,10 +89,7 @@ typedef struct perseus_gpu_tuning {
 	int ctas_per_sm;   /* persistent CTAs per SM, 1..8                                              */
 	                   /* 0 in the three fields above = chosen per output format at launch time     */
 	int store_mode;    /* 0 = default, 1 = st.global.cs (streaming), 2 = plain st.global           */
-	/* experiment knobs kept for the tuning sweeps in profiles/ (0 = shipped behaviour): */
-	int consumer_threads; /* 128, 256 or 512 converting threads per CTA                                */
-	int read_policy;      /* 1 = no L2 evict-first hint on the wire reads                              */
-	int l2_prefetch;      /* prefetch the tile this many iterations ahead into L2                      */
+	int reserved[3];
 } perseus_gpu_tuning;
 
 typedef struct perseus_gpu_config {

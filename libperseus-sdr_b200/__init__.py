@@ -39,7 +39,7 @@ class PerseusGpuError(RuntimeError):
 
 class Tuning(C.Structure):
     _fields_ = [("variant", C.c_int), ("tile_bytes", C.c_int), ("stages", C.c_int), ("ctas_per_sm", C.c_int),
-                ("store_mode", C.c_int), ("consumer_threads", C.c_int), ("read_policy", C.c_int), ("l2_prefetch", C.c_int)]
+                ("store_mode", C.c_int), ("reserved", C.c_int * 3)]
 
 
 class Config(C.Structure):
@@ -280,8 +280,7 @@ class PerseusGpu:
     def get_tuning(self) -> dict:
         t = Tuning()
         check(self.L.perseus_gpu_get_tuning(self.h, C.byref(t)))
-        return {k: getattr(t, k) for k in ("variant", "tile_bytes", "stages", "ctas_per_sm", "store_mode", "consumer_threads",
-                                           "read_policy", "l2_prefetch")}
+        return {k: getattr(t, k) for k in ("variant", "tile_bytes", "stages", "ctas_per_sm", "store_mode")}
 
     # -- plumbing
     def dev_alloc(self, nbytes: int) -> int:

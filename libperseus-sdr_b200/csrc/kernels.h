@@ -16,9 +16,6 @@ constexpr int kMaxStages       = 8;
 
 struct Tuning {            // copy of perseus_gpu_tuning; 0 in tile_bytes/stages/ctas_per_sm = pick by output format
 	int variant, tile_bytes, stages, ctas_per_sm, store_mode;
-	int consumer_threads;   // experimental: 0/256 (default), 128 or 512 consumer threads per CTA
-	int read_policy;        // experimental: 0 = evict-first hint on the wire reads, 1 = no hint
-	int l2_prefetch;        // experimental: prefetch this many iterations ahead into L2 (0 = off)
 };
 
 // Pipeline geometry actually used for a launch.  The defaults come from the sweep committed in

@@ -131,9 +131,6 @@ pg::Tuning resolve_tuning(const perseus_gpu_tuning *t)
 		r.stages = t->stages;
 		r.ctas_per_sm = t->ctas_per_sm;
 		r.store_mode = t->store_mode;
-		r.consumer_threads = t->consumer_threads;
-		r.read_policy = t->read_policy;
-		r.l2_prefetch = t->l2_prefetch;
 	}
 	if (r.store_mode == 0) r.store_mode = 1;
 	return r;
@@ -147,20 +144,13 @@ int check_tuning(const pg::Tuning &t)
 	if (t.stages && (t.stages < 2 || t.stages > pg::kMaxStages)) return fail(PERSEUS_GPU_ERRPARAM, "tuning.stages %d not in 2..%d", t.stages, pg::kMaxStages);
 	if (t.ctas_per_sm < 0 || t.ctas_per_sm > 8) return fail(PERSEUS_GPU_ERRPARAM, "tuning.ctas_per_sm %d not in 1..8", t.ctas_per_sm);
 	if (t.store_mode < 1 || t.store_mode > 2) return fail(PERSEUS_GPU_ERRPARAM, "tuning.store_mode %d not in 0..2", t.store_mode);
-	if (t.consumer_threads != 0 && t.consumer_threads != 128 && t.consumer_threads != 256 && t.consumer_threads != 512)
-		return fail(PERSEUS_GPU_ERRPARAM, "tuning.consumer_threads %d must be 128, 256 or 512", t.consumer_threads);
-	if ((t.consumer_threads == 128 || t.consumer_threads == 512) &&
-	    (t.store_mode != 1 || (t.tile_bytes != 0 && t.tile_bytes != 6144 && t.tile_bytes != 12288 && t.tile_bytes != 24576)))
-		return fail(PERSEUS_GPU_ERRPARAM, "tuning.consumer_threads %d needs store_mode 1 and tile_bytes 6144, 12288 or 24576", t.consumer_threads);
-	if (t.read_policy < 0 || t.read_policy > 1) return fail(PERSEUS_GPU_ERRPARAM, "tuning.read_policy %d not in 0..1", t.read_policy);
-	if (t.l2_prefetch < 0 || t.l2_prefetch > 64) return fail(PERSEUS_GPU_ERRPARAM, "tuning.l2_prefetch %d not in 0..64", t.l2_prefetch);
 	// what actually fits, for either default the unset fields could resolve to: 227 KiB of shared memory, 2048 threads per SM
 	for (unsigned fmt : {1u, 3u}) {
 		const pg::Geometry g = pg::resolve_geometry(t, fmt);
 		if ((size_t)g.stages * g.tile_bytes > 200 * 1024)
 			return fail(PERSEUS_GPU_ERRPARAM, "tuning: stages*tile_bytes = %zu exceeds 200 KiB of shared memory", (size_t)g.stages * g.tile_bytes);
 		const int by_smem = (int)((227 * 1024) / ((size_t)g.stages * g.tile_bytes + 1024));
-		const int by_threads = 2048 / ((t.consumer_threads ? t.consumer_threads : pg::kConsumerThreads) + pg::kProducerThreads);
+		const int by_threads = 2048 / (pg::kConsumerThreads + pg::kProducerThreads);
 		if (g.ctas_per_sm > by_smem || g.ctas_per_sm > by_threads)
 			return fail(PERSEUS_GPU_ERRPARAM, "tuning: %d CTAs/SM do not fit (shared memory allows %d, threads allow %d)", g.ctas_per_sm, by_smem, by_threads);
 	}
@@ -815,9 +805,6 @@ int perseus_gpu_get_tuning(perseus_gpu *h, perseus_gpu_tuning *t)
 	t->stages = h->tune.stages;
 	t->ctas_per_sm = h->tune.ctas_per_sm;
 	t->store_mode = h->tune.store_mode;
-	t->consumer_threads = h->tune.consumer_threads;
-	t->read_policy = h->tune.read_policy;
-	t->l2_prefetch = h->tune.l2_prefetch;
 	return 0;
 }
 

@@ -61,16 +61,6 @@ __device__ __forceinline__ uint64_t l2_evict_first_policy()
 	return pol;
 }
 // TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP).
-__device__ __forceinline__ void bulk_g2s_nohint(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
-{
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-	             "r"(bytes), "r"(bar)
-	             : "memory");
-}
-__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes)
-{
-	asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t pol)
 {
 	asm volatile(
@@ -149,8 +139,6 @@ struct StreamParams {
 	const SegDesc *segs;      // batched
 	const TileRef *tiles;
 	int stages;
-	int read_policy;          // 0 = L2 evict-first hint on the bulk copies, 1 = no hint
-	int l2_prefetch;          // > 0: also prefetch the tile this many iterations ahead into L2 (flat launches only)
 };
 
 struct TileHdr {              // written by the producer lane, read by the consumers of that stage
@@ -160,12 +148,12 @@ struct TileHdr {              // written by the producer lane, read by the consu
 	uint32_t pad;
 };
 
-template <unsigned FMT, int TILE, int ST, bool BATCHED, int NCONS>
-__global__ void __launch_bounds__(NCONS + kProducerThreads)
+template <unsigned FMT, int TILE, int ST, bool BATCHED>
+__global__ void __launch_bounds__(kConsumerThreads + kProducerThreads)
 unpack24_stream_kernel(const __grid_constant__ StreamParams p)
 {
-	static_assert(TILE % 48 == 0 && (TILE / 12) % NCONS == 0, "tile must keep 16-byte phase and split evenly");
-	constexpr int kPasses = TILE / 12 / NCONS;
+	static_assert(TILE % 48 == 0 && (TILE / 12) % kConsumerThreads == 0, "tile must keep 16-byte phase and split evenly");
+	constexpr int kPasses = TILE / 12 / kConsumerThreads;
 
 	extern __shared__ __align__(128) uint8_t ring[];
 	__shared__ __align__(8) uint64_t full_bar[kMaxStages];
@@ -178,15 +166,15 @@ unpack24_stream_kernel(const __grid_constant__ StreamParams p)
 	if (tid == 0) {
 		for (int s = 0; s < nstages; ++s) {
 			mbar_init(smem_u32(&full_bar[s]), 1);
-			mbar_init(smem_u32(&empty_bar[s]), NCONS);
+			mbar_init(smem_u32(&empty_bar[s]), kConsumerThreads);
 		}
 		fence_mbar_init();
 	}
 	__syncthreads();
 
-	if (tid >= NCONS) {
+	if (tid >= kConsumerThreads) {
 		// ---------------- producer warp: one lane drives the TMA
-		if (tid == NCONS) {
+		if (tid == kConsumerThreads) {
 			const uint64_t pol = l2_evict_first_policy();   // wire bytes are read exactly once
 			int s = 0;
 			uint32_t phase = 0;
@@ -219,12 +207,7 @@ unpack24_stream_kernel(const __grid_constant__ StreamParams p)
 				const uint32_t bulk = h.valid & ~15u;             // bulk copies move multiples of 16 bytes
 				if (bulk) {
 					mbar_arrive_expect_tx(smem_u32(&full_bar[s]), bulk);
-					if (p.read_policy == 0) bulk_g2s(smem_u32(ring + (size_t)s * TILE), h.src, bulk, smem_u32(&full_bar[s]), pol);
-					else bulk_g2s_nohint(smem_u32(ring + (size_t)s * TILE), h.src, bulk, smem_u32(&full_bar[s]));
-					if (!BATCHED && p.l2_prefetch > 0) {
-						const uint64_t ahead = (tile + (uint64_t)p.l2_prefetch * gridDim.x) * TILE;
-						if (ahead + TILE <= p.in_bytes) bulk_prefetch_l2(p.in + ahead, TILE);
-					}
+					bulk_g2s(smem_u32(ring + (size_t)s * TILE), h.src, bulk, smem_u32(&full_bar[s]), pol);
 				} else {
 					mbar_arrive(smem_u32(&full_bar[s]));
 				}
@@ -245,22 +228,22 @@ unpack24_stream_kernel(const __grid_constant__ StreamParams p)
 			uint32_t r[kPasses][3];
 #pragma unroll
 			for (int k = 0; k < kPasses; ++k) {
-				const int u = k * NCONS + tid;
+				const int u = k * kConsumerThreads + tid;
 				r[k][0] = w[3 * u];
 				r[k][1] = w[3 * u + 1];
 				r[k][2] = w[3 * u + 2];
 			}
 #pragma unroll
 			for (int k = 0; k < kPasses; ++k)
-				emit_unit<FMT, ST>(r[k][0], r[k][1], r[k][2], h.o_i32, h.o_f32, (size_t)(k * NCONS + tid));
+				emit_unit<FMT, ST>(r[k][0], r[k][1], r[k][2], h.o_i32, h.o_f32, (size_t)(k * kConsumerThreads + tid));
 		} else {
 			// ragged last tile of a buffer/segment: units that lie inside the bulk-copied part
 			// come from smem, the (at most 5) samples after it straight from global memory.
 			const uint32_t nunits = (h.valid & ~15u) / 12;
-			for (uint32_t u = tid; u < nunits; u += NCONS)
+			for (uint32_t u = tid; u < nunits; u += kConsumerThreads)
 				emit_unit<FMT, ST>(w[3 * u], w[3 * u + 1], w[3 * u + 2], h.o_i32, h.o_f32, u);
 			const uint32_t ns = h.valid / 6;
-			for (uint32_t k = 2 * nunits + tid; k < ns; k += NCONS)
+			for (uint32_t k = 2 * nunits + tid; k < ns; k += kConsumerThreads)
 				emit_sample_bytes<FMT>(h.src, h.o_i32, h.o_f32, k);
 		}
 		// every consumer thread releases the stage itself: its own shared-memory reads are ordered before its own
@@ -476,10 +459,10 @@ __global__ void __launch_bounds__(256) probe_copy_kernel(const uint4 *__restrict
 }
 
 // ------------------------------------------------------------------ dispatch tables
-template <unsigned FMT, int TILE, int ST, bool BATCHED, int NCONS = kConsumerThreads>
+template <unsigned FMT, int TILE, int ST, bool BATCHED>
 cudaError_t launch_stream_inst(const StreamParams &p, int grid, cudaStream_t stream)
 {
-	auto kern = unpack24_stream_kernel<FMT, TILE, ST, BATCHED, NCONS>;
+	auto kern = unpack24_stream_kernel<FMT, TILE, ST, BATCHED>;
 	const size_t smem = (size_t)p.stages * TILE;
 	static bool configured[64] = {};                      // per instantiation: devices whose smem limit is raised
 	int dev = 0;
@@ -491,7 +474,7 @@ cudaError_t launch_stream_inst(const StreamParams &p, int grid, cudaStream_t str
 		if (dev >= 0 && dev < 64) configured[dev] = true;
 	}
 	if (smem > 200 * 1024) return cudaErrorInvalidValue;
-	kern<<<grid, NCONS + kProducerThreads, smem, stream>>>(p);
+	kern<<<grid, kConsumerThreads + kProducerThreads, smem, stream>>>(p);
 	return cudaGetLastError();
 }
 
@@ -502,21 +485,8 @@ cudaError_t launch_stream_st(const StreamParams &p, int st, int grid, cudaStream
 }
 
 template <unsigned FMT, bool BATCHED>
-cudaError_t launch_stream_tile(const StreamParams &p, int tile, int st, int ncons, int grid, cudaStream_t stream)
+cudaError_t launch_stream_tile(const StreamParams &p, int tile, int st, int grid, cudaStream_t stream)
 {
-	if (ncons != kConsumerThreads) {   // experimental consumer counts: flat launches, streaming stores, power-of-two tiles only
-		if (BATCHED || st != 1) return cudaErrorInvalidValue;
-		if (ncons == 128) {
-			if (tile == 6144) return launch_stream_inst<FMT, 6144, 1, false, 128>(p, grid, stream);
-			if (tile == 12288) return launch_stream_inst<FMT, 12288, 1, false, 128>(p, grid, stream);
-			if (tile == 24576) return launch_stream_inst<FMT, 24576, 1, false, 128>(p, grid, stream);
-		} else if (ncons == 512) {
-			if (tile == 6144) return launch_stream_inst<FMT, 6144, 1, false, 512>(p, grid, stream);
-			if (tile == 12288) return launch_stream_inst<FMT, 12288, 1, false, 512>(p, grid, stream);
-			if (tile == 24576) return launch_stream_inst<FMT, 24576, 1, false, 512>(p, grid, stream);
-		}
-		return cudaErrorInvalidValue;
-	}
 	switch (tile) {
 	case 6144: return launch_stream_st<FMT, 6144, BATCHED>(p, st, grid, stream);
 	case 9216: return launch_stream_st<FMT, 9216, BATCHED>(p, st, grid, stream);
@@ -528,14 +498,14 @@ cudaError_t launch_stream_tile(const StreamParams &p, int tile, int st, int ncon
 }
 
 template <bool BATCHED>
-cudaError_t launch_stream_fmt(const StreamParams &p, unsigned fmt, int tile, int st, int ncons, int grid, cudaStream_t stream)
+cudaError_t launch_stream_fmt(const StreamParams &p, unsigned fmt, int tile, int st, int grid, cudaStream_t stream)
 {
 	switch (fmt) {
-	case FMT_I32: return launch_stream_tile<FMT_I32, BATCHED>(p, tile, st, ncons, grid, stream);
-	case FMT_F32: return launch_stream_tile<FMT_F32, BATCHED>(p, tile, st, ncons, grid, stream);
-	case FMT_POW2: return launch_stream_tile<FMT_POW2, BATCHED>(p, tile, st, ncons, grid, stream);
-	case FMT_I32 | FMT_F32: return launch_stream_tile<FMT_I32 | FMT_F32, BATCHED>(p, tile, st, ncons, grid, stream);
-	case FMT_I32 | FMT_POW2: return launch_stream_tile<FMT_I32 | FMT_POW2, BATCHED>(p, tile, st, ncons, grid, stream);
+	case FMT_I32: return launch_stream_tile<FMT_I32, BATCHED>(p, tile, st, grid, stream);
+	case FMT_F32: return launch_stream_tile<FMT_F32, BATCHED>(p, tile, st, grid, stream);
+	case FMT_POW2: return launch_stream_tile<FMT_POW2, BATCHED>(p, tile, st, grid, stream);
+	case FMT_I32 | FMT_F32: return launch_stream_tile<FMT_I32 | FMT_F32, BATCHED>(p, tile, st, grid, stream);
+	case FMT_I32 | FMT_POW2: return launch_stream_tile<FMT_I32 | FMT_POW2, BATCHED>(p, tile, st, grid, stream);
 	default: return cudaErrorInvalidValue;
 	}
 }
@@ -609,11 +579,8 @@ cudaError_t launch_unpack(const void *in, size_t nbytes, void *out_i32, void *ou
 		p.in_bytes = nsamples * 6;
 		p.ntiles = (p.in_bytes + (uint64_t)g.tile_bytes - 1) / (uint64_t)g.tile_bytes;
 		p.stages = g.stages;
-		p.read_policy = t.read_policy;
-		p.l2_prefetch = t.l2_prefetch;
 		const int grid = persistent_grid(p.ntiles, sm_count, g.ctas_per_sm);
-		cudaError_t e = launch_stream_fmt<false>(p, fmt, g.tile_bytes, t.store_mode, t.consumer_threads ? t.consumer_threads : kConsumerThreads,
-		                                         grid, stream);
+		cudaError_t e = launch_stream_fmt<false>(p, fmt, g.tile_bytes, t.store_mode, grid, stream);
 		if (e == cudaSuccess) *launches = 1;
 		return e;
 	}
@@ -648,8 +615,7 @@ cudaError_t launch_unpack_batch(const SegDesc *d_segs, const TileRef *d_tiles, u
 		p.ntiles = ntiles;
 		p.stages = g.stages;
 		if ((size_t)g.stages * tile_bytes > 200 * 1024) p.stages = (int)(200 * 1024 / tile_bytes);
-		p.read_policy = t.read_policy;
-		e = launch_stream_fmt<true>(p, fmt, tile_bytes, t.store_mode, kConsumerThreads, persistent_grid(ntiles, sm_count, g.ctas_per_sm), stream);
+		e = launch_stream_fmt<true>(p, fmt, tile_bytes, t.store_mode, persistent_grid(ntiles, sm_count, g.ctas_per_sm), stream);
 	} else {
 		DirectParams p{};
 		p.segs = d_segs;

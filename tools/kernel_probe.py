@@ -25,7 +25,6 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--buffers", type=int, default=NBUF)
     ap.add_argument("--sweep", action="store_true")
-    ap.add_argument("--explore", action="store_true", help="experiment knobs: consumer threads, read policy, L2 prefetch distance")
     ap.add_argument("--fine", action="store_true", help="few CTAs/SM, all tile sizes, every ring depth, 3 repeats each")
     for k in ("variant", "tile", "stages", "ctas", "store"):
         ap.add_argument(f"--{k}", type=int, default=0)
@@ -63,30 +62,10 @@ def main():
             h.sync()
             ms = h.event_elapsed_ms(0, 1) / a.reps
             gbs = bps * ns / (ms * 1e-3) / 1e9
-            return {"fmt": fmt, **{k: v for k, v in h.get_tuning().items() if v or k in ("tile_bytes", "stages", "ctas_per_sm")}, "ms": round(ms, 4), "gbs": round(gbs, 1), "frac": round(gbs / peak, 4),
+            return {"fmt": fmt, **h.get_tuning(), "ms": round(ms, 4), "gbs": round(gbs, 1), "frac": round(gbs / peak, 4),
                     "gsamples_s": round(ns / ms / 1e6, 1)}
 
-        if a.explore:
-            def best_of(fmt, n=2, **tune):
-                rs = [run(fmt, variant=pg.VARIANT_STREAM, store_mode=1, **tune) for _ in range(n)]
-                if rs[0]:
-                    b = max(rs, key=lambda r: r["gbs"])
-                    b["gbs_all"] = sorted(r["gbs"] for r in rs)
-                    print(json.dumps(b), flush=True)
-            for fmt in ("both", "f32"):
-                best_of(fmt, 3)
-                for pol in (0, 1):
-                    for st in (2, 3, 4, 5):
-                        best_of(fmt, read_policy=pol, tile_bytes=12288, stages=st, ctas_per_sm=1)
-                for pf in (1, 2, 4, 8, 16, 32):
-                    for st in (2, 3, 4):
-                        best_of(fmt, l2_prefetch=pf, tile_bytes=12288, stages=st, ctas_per_sm=1)
-                    best_of(fmt, l2_prefetch=pf, tile_bytes=6144, stages=3, ctas_per_sm=1)
-                    best_of(fmt, l2_prefetch=pf, tile_bytes=6144, stages=2, ctas_per_sm=2)
-                for nc in (128, 512):
-                    for tile, st, ctas in itertools.product((6144, 12288, 24576), (2, 3, 4, 5, 6, 8), (1, 2, 3)):
-                        best_of(fmt, consumer_threads=nc, tile_bytes=tile, stages=st, ctas_per_sm=ctas)
-        elif a.fine:
+        if a.fine:
             for fmt in ("both", "f32", "i32"):
                 for ctas, tile, stages in itertools.product((1, 2), (6144, 9216, 12288, 18432, 24576), range(2, 9)):
                     rs = [run(fmt, variant=pg.VARIANT_STREAM, tile_bytes=tile, stages=stages, ctas_per_sm=ctas, store_mode=1) for _ in range(3)]
