@@ -34,6 +34,7 @@ def ref():
 def pg():
     """The product, through its C ABI (ctypes).  Fails loudly if the CUDA library is missing."""
     import __graft_entry__ as G
+    G.ensure_built()
     return G.load_package()
 
 
