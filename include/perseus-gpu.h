@@ -99,7 +99,10 @@ typedef struct perseus_gpu_config {
 	uint32_t nslabs;          /* pinned slabs in the hand-off ring, >= 2          (0 = 4)       */
 	uint64_t slab_bytes;      /* bytes per slab, rounded down to a multiple of 48 (0 = 8 MiB)   */
 	uint32_t nstreams;        /* CUDA streams used for copy/compute overlap, 1..8 (0 = 2)       */
-	uint32_t reserved0;
+	uint32_t max_latency_us;  /* streaming path: a partly filled slab is submitted once its oldest transfer has
+	                             waited this long, checked at every callback (0 = 50 000 us; 0xFFFFFFFF = only
+	                             when full).  At 95 kS/s a transfer arrives every 10.8 ms, so slabs are
+	                             time-bounded, not size-bounded, on a real receiver.                */
 	uint64_t chunk_bytes;     /* host<->device staging chunk for perseus_gpu_unpack with host
 	                             pointers, rounded down to a multiple of 48       (0 = 32 MiB)  */
 	perseus_gpu_tuning tuning;

@@ -44,7 +44,7 @@ class Tuning(C.Structure):
 
 class Config(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("stream_flags", C.c_uint32), ("nslabs", C.c_uint32),
-                ("slab_bytes", C.c_uint64), ("nstreams", C.c_uint32), ("reserved0", C.c_uint32), ("chunk_bytes", C.c_uint64),
+                ("slab_bytes", C.c_uint64), ("nstreams", C.c_uint32), ("max_latency_us", C.c_uint32), ("chunk_bytes", C.c_uint64),
                 ("tuning", Tuning)]
 
 
@@ -193,12 +193,12 @@ class PerseusGpu:
     """perseus_gpu handle.  Pointers are plain integers (device or host addresses)."""
 
     def __init__(self, device: int = 0, stream_flags: int = 0, nslabs: int = 0, slab_bytes: int = 0, nstreams: int = 0,
-                 chunk_bytes: int = 0, **tuning):
+                 chunk_bytes: int = 0, max_latency_us: int = 0, **tuning):
         L = lib()
         cfg = Config()
         cfg.struct_size = C.sizeof(Config)
         cfg.device, cfg.stream_flags, cfg.nslabs, cfg.slab_bytes = device, stream_flags, nslabs, slab_bytes
-        cfg.nstreams, cfg.chunk_bytes = nstreams, chunk_bytes
+        cfg.nstreams, cfg.chunk_bytes, cfg.max_latency_us = nstreams, chunk_bytes, max_latency_us
         for k, v in tuning.items():
             setattr(cfg.tuning, k, v)
         self.h = C.c_void_p()

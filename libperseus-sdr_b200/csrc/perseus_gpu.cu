@@ -15,6 +15,7 @@
 #include <cstring>
 #include <new>
 #include <vector>
+#include <time.h>
 #if defined(__SSE2__)
 #include <emmintrin.h>
 #endif
@@ -73,6 +74,8 @@ struct perseus_gpu {
 	Slab slabs[kMaxSlabs];
 	int cur = 0;               // slab being filled
 	size_t fill = 0;           // bytes in it
+	uint64_t fill_started_ns = 0;   // monotonic time the first transfer of the current slab arrived
+	uint64_t max_latency_ns = 0;    // 0 = submit only full slabs
 	int next_to_write = 0;     // oldest slab whose output has not reached the file sink
 	bool streaming_ready = false;
 	uint64_t samples_submitted = 0;
@@ -339,10 +342,19 @@ inline void copy_to_slab(uint8_t *dst, const uint8_t *src, size_t n)
 	memcpy(dst, src, n);
 }
 
+inline uint64_t monotonic_ns()
+{
+	timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec;
+}
+
 int stream_push(perseus_gpu *h, const uint8_t *buf, size_t nbytes)
 {
 	int rc = ensure_streaming(h);
 	if (rc) return rc;
+	const uint64_t now = h->max_latency_ns ? monotonic_ns() : 0;
+	if (h->fill == 0) h->fill_started_ns = now;
 	while (nbytes) {
 		size_t room = h->slab_bytes - h->fill;
 		size_t n = nbytes < room ? nbytes : room;
@@ -353,8 +365,11 @@ int stream_push(perseus_gpu *h, const uint8_t *buf, size_t nbytes)
 		if (h->fill == h->slab_bytes) {
 			rc = submit_slab(h);
 			if (rc) return rc;
+			h->fill_started_ns = now;
 		}
 	}
+	// latency bound: on a real receiver transfers trickle in (10.8 ms apart at 95 kS/s); do not sit on them
+	if (h->max_latency_ns && h->fill && now - h->fill_started_ns >= h->max_latency_ns) return submit_slab(h);
 	return 0;
 }
 
@@ -442,6 +457,7 @@ int perseus_gpu_open(perseus_gpu **out, const perseus_gpu_config *ucfg)
 	h->nslabs = (int)nslabs;
 	h->nstreams = (int)nstreams;
 	h->slab_bytes = (size_t)slab;
+	h->max_latency_ns = cfg.max_latency_us == 0xFFFFFFFFu ? 0 : (uint64_t)(cfg.max_latency_us ? cfg.max_latency_us : 50000u) * 1000ull;
 	h->chunk_bytes = (size_t)chunk;
 	auto bail = [&](int code) {   // free what exists, keep the message of the original failure
 		char keep[sizeof(g_errstr)];

@@ -445,7 +445,8 @@ def test_callback_trampoline_driven_by_virtual_receiver(pg, coracle, buffersize,
     passed as a C function pointer exactly as a libperseus-sdr user would."""
     ntransfers = 203
     slab = 48 * 1000                                   # not a multiple of the transfer: slabs split transfers
-    with pg.PerseusGpu(device=0, stream_flags=pg.OUT_INT32 | pg.OUT_FLOAT, slab_bytes=slab, nslabs=3, nstreams=2) as h:
+    with pg.PerseusGpu(device=0, stream_flags=pg.OUT_INT32 | pg.OUT_FLOAT, slab_bytes=slab, nslabs=3, nstreams=2,
+                       max_latency_us=0xFFFFFFFF) as h:    # slabs are counted below: size-bounded only
         outs_i, outs_f = [], []
 
         def sink(blk, extra):
@@ -554,6 +555,59 @@ def rq_bytes(n, faults):
     """bytes_received as perseus-in.c:202 counts it: every completed transfer, short ones with their short length."""
     d = faults.get("drop_every", 0)
     return n * 6144 - (6 * (n // d) if d else 0)
+
+
+def test_streaming_latency_bound_submits_partial_slabs(pg, coracle):
+    """A real receiver delivers a 6144-byte transfer every 10.8 ms at 95 kS/s: slabs must go out on time, not when full."""
+    import time
+    wire = coracle.synth_random(6144 * 6, seed=17).reshape(6, 6144)
+    with pg.PerseusGpu(device=0, stream_flags=pg.OUT_FLOAT, slab_bytes=8 << 20, max_latency_us=2000) as h:
+        blocks = []
+        h.set_sink(lambda blk, extra: blocks.append((blk.contents.first_sample, blk.contents.nsamples, blk.contents.dev_f32)))
+        for k in range(6):
+            h.input_callback(wire[k].ctypes.data, 6144)
+            time.sleep(0.004 if k % 2 else 0.0)          # every second transfer arrives after the bound has passed
+        assert len(blocks) >= 2 and sum(b[1] for b in blocks) < 6 * 1024 + 1     # submitted before any flush
+        h.flush()
+        assert sum(b[1] for b in blocks) == 6 * 1024 and [b[0] for b in blocks] == list(np.cumsum([0] + [b[1] for b in blocks[:-1]]))
+        got = np.concatenate([h.to_host(d, n * 8, np.uint32) for _, n, d in blocks])
+        assert np.array_equal(got, coracle.unpack(wire.reshape(-1), O.MODE_F32).view(np.uint32).reshape(-1))
+    with pg.PerseusGpu(device=0, slab_bytes=8 << 20, max_latency_us=0xFFFFFFFF) as h:   # bound disabled: only full slabs or flush
+        blocks = []
+        h.set_sink(lambda blk, extra: blocks.append(blk.contents.nsamples))
+        for k in range(3):
+            h.input_callback(wire[k].ctypes.data, 6144)
+            time.sleep(0.003)
+        assert blocks == []
+        h.flush()
+        assert blocks == [3 * 1024]
+
+
+def test_two_handles_on_two_threads(pg, coracle):
+    """Handles are independent: distinct handles may be driven from distinct threads at the same time."""
+    import threading
+    wire = [coracle.synth_random(6144 * 300 + 6 * k, seed=30 + k) for k in range(2)]
+    out, err = [None, None], []
+
+    def work(k):
+        try:
+            with pg.PerseusGpu(device=0) as h:
+                d = h.to_device(wire[k])
+                ns = wire[k].size // 6
+                o = h.dev_alloc(ns * 8)
+                for _ in range(20):
+                    h.unpack(d, wire[k].size, o, None, pg.OUT_INT32)
+                out[k] = h.to_host(o, ns * 8, np.uint32)
+                h.dev_free(d); h.dev_free(o)
+        except Exception as e:  # pragma: no cover
+            err.append(e)
+
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not err, err
+    for k in range(2):
+        assert np.array_equal(out[k], coracle.unpack(wire[k], O.MODE_I32).view(np.uint32).reshape(-1))
 
 
 def test_callback_errors_are_latched_and_surface_at_flush(pg, coracle):
