@@ -379,7 +379,14 @@ def ours(args):
 
     # -- end to end: pinned host wire -> H2D -> unpack (outputs stay on device) -> D2H of the step's result
     e2e_steps = max(3, min(args.steps, args.e2e_steps))
-    pin = h.host_alloc(nbytes)
+    wc_rt = None
+    if args.pinned_wc:   # experiment: write-combined pinned memory (DMA reads need not snoop the CPU caches)
+        wc_rt = C.CDLL("libcudart.so.12")
+        pp = C.c_void_p()
+        assert wc_rt.cudaHostAlloc(C.byref(pp), C.c_size_t(nbytes), C.c_uint(0x04 | 0x01)) == 0   # WriteCombined | Portable
+        pin = pp.value
+    else:
+        pin = h.host_alloc(nbytes)
     h.memcpy(pin, d_in, nbytes)                                           # the synthetic recording, now in pinned host memory
     h2d_ms = []
     for _ in range(3):                                                    # in-run PCIe H2D roofline: plain pinned copy
@@ -415,7 +422,8 @@ def ours(args):
                    "end-to-end mode specifies)",
            "h2d_gbs_per_gpu": round(6 * ns / (ms_e2e * 1e-3) / 1e9, 2), "pcie_h2d_gbs_measured": round(pcie_gbs, 2),
            "frac_of_measured_pcie": round(6 * ns / (ms_e2e * 1e-3) / 1e9 / pcie_gbs, 4),
-           "frac_of_gen5_x16_theory": round(6 * ns / (ms_e2e * 1e-3) / 1e9 / PCIE_GEN5_X16_GBS, 4)}
+           "frac_of_gen5_x16_theory": round(6 * ns / (ms_e2e * 1e-3) / 1e9 / PCIE_GEN5_X16_GBS, 4),
+           "pinned_memory": "write-combined" if args.pinned_wc else "default (cudaHostAlloc portable)"}
     if pcie_concurrent:
         e2e["pcie_h2d_gbs_all_ranks_at_once"] = round(pcie_concurrent, 2)
         e2e["frac_of_concurrent_pcie"] = round(6 * ns / (ms_e2e * 1e-3) / 1e9 / pcie_concurrent, 4)
@@ -434,7 +442,10 @@ def ours(args):
                   "d2h_bytes_per_step": int((s1["d2h_bytes"] - s0["d2h_bytes"]) // (rt_steps + 1)),
                   "what": "same call with pinned HOST outputs: both formats copied back (16 B/sample D2H, full duplex with the H2D)"}
         h.host_free(po_i); h.host_free(po_f)
-    h.host_free(pin)
+    if wc_rt is not None:
+        wc_rt.cudaFreeHost(C.c_void_p(pin))
+    else:
+        h.host_free(pin)
 
     # -- the literal drop-in: 6144-byte transfers through perseus_gpu_input_callback (one host thread, like the
     #    reference's poll thread), delivered by the virtual receiver from its 8-slot pageable ring
@@ -631,6 +642,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-callback", action="store_true")
     ap.add_argument("--no-probe", action="store_true")
+    ap.add_argument("--pinned-wc", action="store_true", help="experiment: end-to-end input in write-combined pinned memory")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4"],
                     help="cfg2 (default, the headline): 1 GiB per GPU, fused; cfg3: 1024 mixed-rate receivers in one launch; "
                          "cfg4: 64 GiB recording sharded over the GPUs, float only")
