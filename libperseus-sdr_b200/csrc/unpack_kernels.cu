@@ -12,7 +12,7 @@
 //                            mbarrier complete_tx) through a multi-stage ring; 8 consumer warps
 //                            read each 12-byte unit (2 samples) as 3 conflict-free LDS.32
 //                            (stride 3 words is coprime with 32 banks), realign the 3-byte
-//                            fields with funnel shifts, and write one coalesced STG.128 per unit.
+//                            fields with PRMT byte permutes, and write one coalesced STG.128 per unit.
 //   unpack24_direct_kernel   register-only fallback for pointers that are not 16-byte aligned
 //                            (legacy 510-byte transfers, ring seams), and an A/B variant.
 //   verify/checksum/generate test + bench plumbing that must run at HBM scale (64 GiB recordings).
@@ -87,14 +87,16 @@ __device__ __forceinline__ float to_float(uint32_t x) { return (FMT & FMT_POW2) 
 
 // One unit = 12 wire bytes = 2 complex samples, held as three little-endian words:
 //   w0 = I0 I1 I2 Q0   w1 = Q1 Q2 I0' I1'   w2 = I2' Q0' Q1' Q2'
-// Each output word is its 3-byte field moved to bytes 1..3 with byte 0 cleared.
+// Each output word is its 3-byte field moved to bytes 1..3 with byte 0 cleared (MSB aligned, so the field's sign
+// bit becomes the word's sign bit: no separate sign extension).  Done with byte permutes (PRMT): selector nibble k
+// picks the source byte of result byte k from {a.b0..a.b3 = 0..3, b.b0..b.b3 = 4..7}; a zero register supplies byte 0.
 __device__ __forceinline__ uint4 unit_to_i32(uint32_t w0, uint32_t w1, uint32_t w2)
 {
 	uint4 o;
-	o.x = w0 << 8;
-	o.y = __funnelshift_l(w0, w1, 16) & 0xFFFFFF00u;
-	o.z = __funnelshift_r(w1, w2, 8) & 0xFFFFFF00u;
-	o.w = w2 & 0xFFFFFF00u;
+	o.x = __byte_perm(w0, 0u, 0x2104);                          // 00 I0 I1 I2
+	o.y = __byte_perm(__byte_perm(w0, w1, 0x0543), 0u, 0x2104); // 00 Q0 Q1 Q2   (Q0 = w0.b3, Q1 Q2 = w1.b0 b1)
+	o.z = __byte_perm(__byte_perm(w1, w2, 0x0432), 0u, 0x2104); // 00 I0' I1' I2' (w1.b2 b3, w2.b0)
+	o.w = __byte_perm(w2, 0u, 0x3214);                          // 00 Q0' Q1' Q2'
 	return o;
 }
 
