@@ -78,7 +78,7 @@ typedef struct perseus_vrx perseus_vrx;               /* synthetic receiver (sta
 /* flags == 0 means: produce whatever non-NULL output pointers were passed (float = reference scale). */
 
 /* kernel selection (perseus_gpu_tuning.variant) */
-#define PERSEUS_GPU_VARIANT_AUTO    0  /* bulk-copy pipeline when pointers are 16-byte aligned, else direct */
+#define PERSEUS_GPU_VARIANT_AUTO    0  /* bulk-copy pipeline when the outputs are 16-byte aligned, else direct */
 #define PERSEUS_GPU_VARIANT_STREAM  1  /* TMA bulk copy -> shared-memory ring -> coalesced 16-byte stores */
 #define PERSEUS_GPU_VARIANT_DIRECT  2  /* register-only kernel, any alignment */
 
@@ -127,7 +127,8 @@ int perseus_gpu_close(perseus_gpu *h);
  *            device in cfg->chunk_bytes pieces with copies and kernels overlapped.
  *   flags    PERSEUS_GPU_OUT_* | PERSEUS_GPU_ASYNC, or 0.
  * Returns the number of complex samples produced (>= 0) or a negative error.
- * Any alignment is accepted; 16-byte aligned buf/out pointers take the fast path. */
+ * Any alignment is accepted.  The wire pointer never matters for speed; output pointers that are 16-byte aligned
+ * (any cudaMalloc'd buffer) take the fast path, others a slower register-only kernel. */
 int64_t perseus_gpu_unpack(perseus_gpu *h, const void *buf, size_t nbytes,
                            void *out_i32, void *out_f32, unsigned flags);
 

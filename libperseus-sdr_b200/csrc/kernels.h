@@ -45,7 +45,8 @@ cudaError_t launch_unpack(const void *in, size_t nbytes, void *out_i32, void *ou
                           const Tuning &t, int sm_count, cudaStream_t stream, int *launches);
 
 // Batched unpack over nseg segments described on the device; tile map built by the caller
-// with tile size `tile_bytes`.  `all_aligned` = every in/out pointer is 16-byte aligned.
+// with tile size `tile_bytes`.  `all_aligned` = every OUTPUT pointer is 16-byte aligned
+// (wire pointers may have any alignment).
 cudaError_t launch_unpack_batch(const SegDesc *d_segs, const TileRef *d_tiles, uint64_t ntiles, int tile_bytes, unsigned fmt,
                                 bool all_aligned, const Tuning &t, int sm_count, cudaStream_t stream, int *launches);
 

@@ -152,7 +152,7 @@ int check_tuning(const pg::Tuning &t)
 		const pg::Geometry g = pg::resolve_geometry(t, fmt);
 		if ((size_t)g.stages * g.tile_bytes > 200 * 1024)
 			return fail(PERSEUS_GPU_ERRPARAM, "tuning: stages*tile_bytes = %zu exceeds 200 KiB of shared memory", (size_t)g.stages * g.tile_bytes);
-		const int by_smem = (int)((227 * 1024) / ((size_t)g.stages * g.tile_bytes + 1024));
+		const int by_smem = (int)((227 * 1024) / ((size_t)g.stages * (g.tile_bytes + 16) + 1024));
 		const int by_threads = 2048 / (pg::kConsumerThreads + pg::kProducerThreads);
 		if (g.ctas_per_sm > by_smem || g.ctas_per_sm > by_threads)
 			return fail(PERSEUS_GPU_ERRPARAM, "tuning: %d CTAs/SM do not fit (shared memory allows %d, threads allow %d)", g.ctas_per_sm, by_smem, by_threads);
@@ -655,7 +655,7 @@ int perseus_gpu_plan_create(perseus_gpu *h, const perseus_gpu_seg *segs, int nse
 		if (((uintptr_t)s.out_i32 & 3) || ((uintptr_t)s.out_f32 & 3)) return fail(PERSEUS_GPU_ERRPARAM, "segment %d: outputs must be 4-byte aligned", i);
 		hs[(size_t)i] = pg::SegDesc{static_cast<const uint8_t *>(s.in), s.nbytes, (fmt & PERSEUS_GPU_OUT_INT32) ? s.out_i32 : nullptr,
 		                            (fmt & (PERSEUS_GPU_OUT_FLOAT | PERSEUS_GPU_OUT_FLOAT_POW2)) ? s.out_f32 : nullptr};
-		if (((uintptr_t)s.in | (uintptr_t)hs[(size_t)i].out_i32 | (uintptr_t)hs[(size_t)i].out_f32) & 15) aligned = false;
+		if (((uintptr_t)hs[(size_t)i].out_i32 | (uintptr_t)hs[(size_t)i].out_f32) & 15) aligned = false;   // wire pointers may be unaligned
 		const uint64_t nt = (used + (uint64_t)tile - 1) / (uint64_t)tile;
 		if (nt > 0xFFFFFFFFull) return fail(PERSEUS_GPU_BUFFERSIZE, "segment %d too large", i);
 		for (uint64_t t = 0; t < nt; ++t) ht.push_back(pg::TileRef{(uint32_t)i, (uint32_t)t});

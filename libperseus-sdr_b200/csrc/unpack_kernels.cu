@@ -134,7 +134,7 @@ __device__ __forceinline__ void emit_sample_bytes(const uint8_t *src, uint8_t *o
 
 // ------------------------------------------------------------------ stream kernel
 struct StreamParams {
-	const uint8_t *in;        // flat: wire bytes (16-byte aligned)
+	const uint8_t *in;        // flat: wire bytes (any alignment; the outputs are 16-byte aligned)
 	uint8_t *out_i32, *out_f32;
 	uint64_t in_bytes;        // flat: 6 * nsamples
 	uint64_t ntiles;
@@ -144,11 +144,13 @@ struct StreamParams {
 };
 
 struct TileHdr {              // written by the producer lane, read by the consumers of that stage
-	const uint8_t *src;
+	const uint8_t *src;       // first wire byte of the tile (any alignment)
 	uint8_t *o_i32, *o_f32;
 	uint32_t valid;           // wire bytes of this tile that hold whole samples (<= TILE)
-	uint32_t pad;
+	uint32_t bulk;            // bytes the bulk copy brought in, starting at the 16-byte boundary at or below src
 };
+
+constexpr int kStagePad = 16;   // a misaligned tile spills into one more 16-byte granule
 
 template <unsigned FMT, int TILE, int ST, bool BATCHED>
 __global__ void __launch_bounds__(kConsumerThreads + kProducerThreads)
@@ -182,6 +184,7 @@ unpack24_stream_kernel(const __grid_constant__ StreamParams p)
 			uint32_t phase = 0;
 			for (uint64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
 				TileHdr h;
+				uint64_t left;                                     // whole-sample bytes from this tile's start to the end of its buffer
 				if (BATCHED) {
 					const TileRef r = p.tiles[tile];
 					const SegDesc sd = p.segs[r.seg];
@@ -190,26 +193,31 @@ unpack24_stream_kernel(const __grid_constant__ StreamParams p)
 					uint8_t *oi = static_cast<uint8_t *>(sd.out_i32);
 					uint8_t *of = static_cast<uint8_t *>(sd.out_f32);
 					const uint64_t off = (uint64_t)r.tile * TILE;
-					const uint64_t left = used - off;
+					left = used - off;
 					h.src = seg_in + off;
 					h.o_i32 = oi + off / 6 * 8;
 					h.o_f32 = of + off / 6 * 8;
 					h.valid = left < (uint64_t)TILE ? (uint32_t)left : (uint32_t)TILE;
 				} else {
 					const uint64_t off = tile * TILE;
-					const uint64_t left = p.in_bytes - off;
+					left = p.in_bytes - off;
 					h.src = p.in + off;
 					h.o_i32 = p.out_i32 + off / 6 * 8;
 					h.o_f32 = p.out_f32 + off / 6 * 8;
 					h.valid = left < (uint64_t)TILE ? (uint32_t)left : (uint32_t)TILE;
 				}
-				h.pad = 0;
+				// The TMA moves 16-byte granules between 16-byte aligned addresses.  A tile that starts `delta` bytes
+				// into a granule is copied from the granule boundary below it, as far as the granule that holds its
+				// last byte -- but never past the last whole granule of the caller's buffer (`left` bytes remain).
+				const uint32_t delta = (uint32_t)(reinterpret_cast<uintptr_t>(h.src) & 15u);
+				const uint64_t reach = (delta + left) & ~(uint64_t)15;                 // readable without passing the end
+				const uint32_t want = (delta + h.valid + 15u) & ~15u;
+				h.bulk = reach < (uint64_t)want ? (uint32_t)reach : want;
 				mbar_wait(smem_u32(&empty_bar[s]), phase ^ 1);   // consumers released this stage
 				hdr[s] = h;
-				const uint32_t bulk = h.valid & ~15u;             // bulk copies move multiples of 16 bytes
-				if (bulk) {
-					mbar_arrive_expect_tx(smem_u32(&full_bar[s]), bulk);
-					bulk_g2s(smem_u32(ring + (size_t)s * TILE), h.src, bulk, smem_u32(&full_bar[s]), pol);
+				if (h.bulk) {
+					mbar_arrive_expect_tx(smem_u32(&full_bar[s]), h.bulk);
+					bulk_g2s(smem_u32(ring + (size_t)s * (TILE + kStagePad)), h.src - delta, h.bulk, smem_u32(&full_bar[s]), pol);
 				} else {
 					mbar_arrive(smem_u32(&full_bar[s]));
 				}
@@ -225,27 +233,49 @@ unpack24_stream_kernel(const __grid_constant__ StreamParams p)
 	for (uint64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
 		mbar_wait(smem_u32(&full_bar[s]), phase);
 		const TileHdr h = hdr[s];
-		const uint32_t *w = reinterpret_cast<const uint32_t *>(ring + (size_t)s * TILE);
-		if (h.valid == (uint32_t)TILE) {
+		// the tile's byte j sits at shared-memory byte delta + j: word offset dw, then a byte shift of 0..3 inside the word
+		const uint32_t delta = (uint32_t)(reinterpret_cast<uintptr_t>(h.src) & 15u);
+		const uint32_t *w = reinterpret_cast<const uint32_t *>(ring + (size_t)s * (TILE + kStagePad)) + (delta >> 2);
+		const uint32_t sh = (delta & 3u) * 8u;
+		if (h.valid == (uint32_t)TILE && h.bulk >= delta + (uint32_t)TILE) {
 			uint32_t r[kPasses][3];
+			if (sh == 0) {
 #pragma unroll
-			for (int k = 0; k < kPasses; ++k) {
-				const int u = k * kConsumerThreads + tid;
-				r[k][0] = w[3 * u];
-				r[k][1] = w[3 * u + 1];
-				r[k][2] = w[3 * u + 2];
+				for (int k = 0; k < kPasses; ++k) {
+					const int u = k * kConsumerThreads + tid;
+					r[k][0] = w[3 * u];
+					r[k][1] = w[3 * u + 1];
+					r[k][2] = w[3 * u + 2];
+				}
+			} else {
+#pragma unroll
+				for (int k = 0; k < kPasses; ++k) {
+					const int u = k * kConsumerThreads + tid;
+					const uint32_t a0 = w[3 * u], a1 = w[3 * u + 1], a2 = w[3 * u + 2], a3 = w[3 * u + 3];
+					r[k][0] = __funnelshift_r(a0, a1, sh);
+					r[k][1] = __funnelshift_r(a1, a2, sh);
+					r[k][2] = __funnelshift_r(a2, a3, sh);
+				}
 			}
 #pragma unroll
 			for (int k = 0; k < kPasses; ++k)
 				emit_unit<FMT, ST>(r[k][0], r[k][1], r[k][2], h.o_i32, h.o_f32, (size_t)(k * kConsumerThreads + tid));
 		} else {
-			// ragged last tile of a buffer/segment: units that lie inside the bulk-copied part
-			// come from smem, the (at most 5) samples after it straight from global memory.
-			const uint32_t nunits = (h.valid & ~15u) / 12;
-			for (uint32_t u = tid; u < nunits; u += kConsumerThreads)
-				emit_unit<FMT, ST>(w[3 * u], w[3 * u + 1], w[3 * u + 2], h.o_i32, h.o_f32, u);
+			// ragged last tile of a buffer/segment: units that lie inside the bulk-copied part come from shared
+			// memory, the few samples after it (at most 5) straight from global memory.
+			const uint32_t nunits = h.bulk > delta ? (h.bulk - delta) / 12 : 0;
+			const uint32_t full_units = h.valid / 12 < nunits ? h.valid / 12 : nunits;
+			for (uint32_t u = tid; u < full_units; u += kConsumerThreads) {
+				const uint32_t a0 = w[3 * u], a1 = w[3 * u + 1], a2 = w[3 * u + 2];
+				if (sh == 0) {
+					emit_unit<FMT, ST>(a0, a1, a2, h.o_i32, h.o_f32, u);
+				} else {
+					const uint32_t a3 = w[3 * u + 3];
+					emit_unit<FMT, ST>(__funnelshift_r(a0, a1, sh), __funnelshift_r(a1, a2, sh), __funnelshift_r(a2, a3, sh), h.o_i32, h.o_f32, u);
+				}
+			}
 			const uint32_t ns = h.valid / 6;
-			for (uint32_t k = 2 * nunits + tid; k < ns; k += kConsumerThreads)
+			for (uint32_t k = 2 * full_units + tid; k < ns; k += kConsumerThreads)
 				emit_sample_bytes<FMT>(h.src, h.o_i32, h.o_f32, k);
 		}
 		// every consumer thread releases the stage itself: its own shared-memory reads are ordered before its own
@@ -465,17 +495,17 @@ template <unsigned FMT, int TILE, int ST, bool BATCHED>
 cudaError_t launch_stream_inst(const StreamParams &p, int grid, cudaStream_t stream)
 {
 	auto kern = unpack24_stream_kernel<FMT, TILE, ST, BATCHED>;
-	const size_t smem = (size_t)p.stages * TILE;
+	const size_t smem = (size_t)p.stages * (TILE + kStagePad);
 	static bool configured[64] = {};                      // per instantiation: devices whose smem limit is raised
 	int dev = 0;
 	cudaGetDevice(&dev);
 	if (dev < 0 || dev >= 64 || !configured[dev]) {
-		constexpr int kMaxSmem = kMaxStages * TILE > 200 * 1024 ? 200 * 1024 : kMaxStages * TILE;
+		constexpr int kMaxSmem = kMaxStages * (TILE + kStagePad) > 201 * 1024 ? 201 * 1024 : kMaxStages * (TILE + kStagePad);
 		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
 		if (e != cudaSuccess) return e;
 		if (dev >= 0 && dev < 64) configured[dev] = true;
 	}
-	if (smem > 200 * 1024) return cudaErrorInvalidValue;
+	if (smem > 201 * 1024) return cudaErrorInvalidValue;
 	kern<<<grid, kConsumerThreads + kProducerThreads, smem, stream>>>(p);
 	return cudaGetLastError();
 }
@@ -569,7 +599,7 @@ cudaError_t launch_unpack(const void *in, size_t nbytes, void *out_i32, void *ou
 	if (!(fmt & FMT_I32)) out_i32 = nullptr;
 	if (!(fmt & (FMT_F32 | FMT_POW2))) out_f32 = nullptr;
 	const bool out16 = aligned_to(out_i32, 16) && aligned_to(out_f32, 16);
-	const bool can_stream = aligned_to(in, 16) && out16;
+	const bool can_stream = out16;   // the wire pointer may have any alignment (see the producer), the STG.128 targets may not
 	const bool use_stream = t.variant == 2 ? false : can_stream;   // variant 1 (STREAM) degrades to direct when unaligned
 
 	const Geometry g = resolve_geometry(t, fmt);

@@ -37,12 +37,12 @@ class DevBuf:
         self.h.dev_free(self.p)
 
 
-def run_unpack(pg, h, wire, flags, in_off=0, out_off=0, fill=0xA5):
+def run_unpack(pg, h, wire, flags, in_off=0, out_off=0, fill=0xA5, tail_pad=64):
     """Unpacks `wire` (numpy u8) placed at device offset in_off; returns (i32 words | None, f32 words | None).
     The output buffers are pre-filled and carry guard bytes so out-of-range writes are caught."""
     ns = wire.size // 6
     guard = 256
-    with DevBuf(h, in_off + wire.size + 64) as din, DevBuf(h, out_off + ns * 8 + guard) as di, DevBuf(h, out_off + ns * 8 + guard) as df:
+    with DevBuf(h, max(1, in_off + wire.size + tail_pad)) as din, DevBuf(h, out_off + ns * 8 + guard) as di, DevBuf(h, out_off + ns * 8 + guard) as df:
         if wire.size:
             h.memcpy(din.p + in_off, wire.ctypes.data, wire.size)
         h.memset(di.p, fill, di.n)
@@ -63,9 +63,9 @@ def run_unpack(pg, h, wire, flags, in_off=0, out_off=0, fill=0xA5):
         return res
 
 
-def check_against_oracle(pg, h, coracle, wire, in_off=0, out_off=0, cases=None):
+def check_against_oracle(pg, h, coracle, wire, in_off=0, out_off=0, cases=None, tail_pad=64):
     for name, flags, modes in (cases or fmt_cases(pg)):
-        got = run_unpack(pg, h, wire, flags, in_off, out_off)
+        got = run_unpack(pg, h, wire, flags, in_off, out_off, tail_pad=tail_pad)
         for g, m in zip(got, modes):
             if m is None:
                 assert g is None
@@ -173,6 +173,20 @@ def test_unaligned_pointers_take_the_direct_path_and_stay_exact(pg, gpu, coracle
         for out_off in (0, 4, 8, 12):
             check_against_oracle(pg, gpu, coracle, wire, in_off=in_off, out_off=out_off,
                                  cases=[c for c in fmt_cases(pg) if c[0] in ("i32+f32", "pow2")])
+
+
+@pytest.mark.parametrize("tile", [6144, 12288, 24576])
+def test_stream_kernel_any_wire_alignment(pg, gpu, coracle, tile):
+    """The TMA pipeline copies from the 16-byte boundary below the wire pointer and shifts inside shared memory, so
+    every misalignment 0..15 takes the fast kernel.  The wire data ends exactly at the end of its allocation
+    (tail_pad=0): with compute-sanitizer memcheck this proves the bulk copies never read past the caller's buffer."""
+    gpu.set_tuning(variant=pg.VARIANT_STREAM, tile_bytes=tile, stages=3, ctas_per_sm=2)
+    big = coracle.synth_random(tile * 5 + 4000, seed=tile)
+    cases = [c for c in fmt_cases(pg) if c[0] == "i32+f32"]
+    for delta in range(16):
+        for n in (tile * 3, tile * 3 + 6, tile * 2 + 4000, tile - 6, tile + 48, tile * 4 + 16 - delta, 30, 6 * 7):
+            check_against_oracle(pg, gpu, coracle, big[:n], in_off=delta, cases=cases, tail_pad=0)
+    gpu.set_tuning()
 
 
 @pytest.mark.parametrize("tile", [6144, 9216, 12288, 18432, 24576])

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--fmt", default="both", choices=["i32", "f32", "both", "pow2"])
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--buffers", type=int, default=NBUF)
+    ap.add_argument("--in-offset", type=int, default=0, help="misalign the wire pointer by this many bytes (exercises the direct kernel)")
     ap.add_argument("--sweep", action="store_true")
     ap.add_argument("--fine", action="store_true", help="few CTAs/SM, all tile sizes, every ring depth, 3 repeats each")
     for k in ("variant", "tile", "stages", "ctas", "store"):
@@ -38,7 +39,8 @@ def main():
     with pg.PerseusGpu(device=0) as h:
         n = a.buffers * BUF
         ns = n // 6
-        d_in, d_i, d_f = h.dev_alloc(n), h.dev_alloc(ns * 8), h.dev_alloc(ns * 8)
+        d_in0, d_i, d_f = h.dev_alloc(n + 64), h.dev_alloc(ns * 8), h.dev_alloc(ns * 8)
+        d_in = d_in0 + a.in_offset
         h.generate(d_in, n)
         fmts = {"i32": (pg.OUT_INT32, d_i, None, 14), "f32": (pg.OUT_FLOAT, None, d_f, 14), "pow2": (pg.OUT_FLOAT_POW2, None, d_f, 14),
                 "both": (pg.OUT_INT32 | pg.OUT_FLOAT, d_i, d_f, 22)}
@@ -85,7 +87,7 @@ def main():
                     r = run(fmt, variant=pg.VARIANT_STREAM, tile_bytes=tile, stages=stages, ctas_per_sm=ctas, store_mode=store)
                     if r:
                         print(json.dumps(r), flush=True)
-        for p in (d_in, d_i, d_f):
+        for p in (d_in0, d_i, d_f):
             h.dev_free(p)
 
 
