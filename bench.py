@@ -306,7 +306,12 @@ def ours(args):
     h = pg.PerseusGpu(device=local, chunk_bytes=args.chunk_mib << 20, nstreams=args.streams)
     if args.tile or args.stages or args.ctas or args.variant or args.store:
         h.set_tuning(variant=args.variant, tile_bytes=args.tile, stages=args.stages, ctas_per_sm=args.ctas, store_mode=args.store)
+    if args.autotune:
+        tuning_gbs = h.autotune()
     tuning = h.get_tuning()
+    tuning["geometry_fused"] = h.get_geometry(pg.OUT_INT32 | pg.OUT_FLOAT)
+    tuning["geometry_single"] = h.get_geometry(pg.OUT_FLOAT)
+    tuning["autotuned"] = bool(args.autotune)
     tuning["auto_rule"] = "0 = per format: tile 12288 B, ring of 3 stages when int32+float are fused, 4 stages for one format, 1 CTA/SM"
 
     nbuf = args.buffers
@@ -642,6 +647,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-callback", action="store_true")
     ap.add_argument("--no-probe", action="store_true")
+    ap.add_argument("--autotune", action="store_true", help="let the library measure its pipeline geometry on this device first")
     ap.add_argument("--pinned-wc", action="store_true", help="experiment: end-to-end input in write-combined pinned memory")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4"],
                     help="cfg2 (default, the headline): 1 GiB per GPU, fused; cfg3: 1024 mixed-rate receivers in one launch; "

@@ -205,8 +205,16 @@ typedef struct perseus_gpu_stats {
 } perseus_gpu_stats;
 int perseus_gpu_get_stats(perseus_gpu *h, perseus_gpu_stats *out);
 
+/* Optional self-calibration.  The pipeline's best geometry is a narrow optimum of the wire bytes in flight per SM
+ * (DESIGN.md §4); the built-in defaults were measured on B200.  This call measures a dozen candidate geometries on
+ * scratch memory of THIS device (about 50 ms, ~2 GB of temporary device memory) for one-format and for fused
+ * launches and keeps the winners for the handle; fields set explicitly with perseus_gpu_set_tuning still win.
+ * gbs_single / gbs_fused (optional) receive the algorithmic GB/s of the winners. */
+int perseus_gpu_autotune(perseus_gpu *h, double *gbs_single, double *gbs_fused);
 int perseus_gpu_set_tuning(perseus_gpu *h, const perseus_gpu_tuning *t);   /* NULL = defaults */
-int perseus_gpu_get_tuning(perseus_gpu *h, perseus_gpu_tuning *t);         /* resolved values */
+int perseus_gpu_get_tuning(perseus_gpu *h, perseus_gpu_tuning *t);         /* what was set; 0 = automatic */
+/* The geometry a launch producing `flags` (PERSEUS_GPU_OUT_*) would use now: explicit > autotuned > default. */
+int perseus_gpu_get_geometry(perseus_gpu *h, unsigned flags, int *tile_bytes, int *stages, int *ctas_per_sm);
 
 /* Last error message of the calling thread (cf. perseus_errorstr(), perseuserr.c:36-42). */
 const char *perseus_gpu_errorstr(void);

@@ -117,6 +117,8 @@ def lib() -> C.CDLL:
         "perseus_gpu_stream_to_file": (ci, [vp, C.c_char_p]),
         "perseus_gpu_flush": (ci, [vp]),
         "perseus_gpu_get_stats": (ci, [vp, P(Stats)]),
+        "perseus_gpu_autotune": (ci, [vp, P(C.c_double), P(C.c_double)]),
+        "perseus_gpu_get_geometry": (ci, [vp, C.c_uint, P(ci), P(ci), P(ci)]),
         "perseus_gpu_set_tuning": (ci, [vp, P(Tuning)]),
         "perseus_gpu_get_tuning": (ci, [vp, P(Tuning)]),
         "perseus_gpu_errorstr": (C.c_char_p, []),
@@ -276,6 +278,17 @@ class PerseusGpu:
         for k, v in kw.items():
             setattr(t, k, v)
         check(self.L.perseus_gpu_set_tuning(self.h, C.byref(t)))
+
+    def autotune(self) -> tuple[float, float]:
+        """Measures candidate geometries on this device; returns (GB/s one format, GB/s fused) of the winners."""
+        a, b = C.c_double(), C.c_double()
+        check(self.L.perseus_gpu_autotune(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def get_geometry(self, flags: int) -> dict:
+        t, s, c = C.c_int(), C.c_int(), C.c_int()
+        check(self.L.perseus_gpu_get_geometry(self.h, flags, C.byref(t), C.byref(s), C.byref(c)))
+        return {"tile_bytes": t.value, "stages": s.value, "ctas_per_sm": c.value}
 
     def get_tuning(self) -> dict:
         t = Tuning()

@@ -14,22 +14,25 @@ constexpr int kConsumerThreads = 256;                  // threads that convert +
 constexpr int kProducerThreads = 32;                   // one warp; lane 0 issues the bulk copies
 constexpr int kMaxStages       = 8;
 
+struct Geometry { int tile_bytes, stages, ctas_per_sm; };
+
 struct Tuning {            // copy of perseus_gpu_tuning; 0 in tile_bytes/stages/ctas_per_sm = pick by output format
 	int variant, tile_bytes, stages, ctas_per_sm, store_mode;
+	Geometry tuned[2];     // perseus_gpu_autotune results: [0] one output format, [1] int32+float fused; zeros = none
 };
 
 // Pipeline geometry actually used for a launch.  The defaults come from the sweep committed in
 // profiles/ (round 1): what matters is the wire bytes in flight per SM -- about 48 KiB when one
 // 8-byte output is written per sample, about 36 KiB when both are (fewer read bytes per byte of
 // traffic); more read-ahead than that starves the write stream and costs 5-10 % of HBM bandwidth.
-struct Geometry { int tile_bytes, stages, ctas_per_sm; };
 inline Geometry resolve_geometry(const Tuning &t, unsigned fmt)
 {
 	const bool fused = (fmt & FMT_I32) && (fmt & (FMT_F32 | FMT_POW2));
-	Geometry g;
-	g.tile_bytes = t.tile_bytes ? t.tile_bytes : 12288;     // two 6144-byte transfers per stage
-	g.stages = t.stages ? t.stages : (fused ? 3 : 4);
-	g.ctas_per_sm = t.ctas_per_sm ? t.ctas_per_sm : 1;
+	const Geometry &m = t.tuned[fused ? 1 : 0];             // measured on this device, if the caller asked for it
+	Geometry g;                                             // explicit settings win, then measured, then the defaults
+	g.tile_bytes = t.tile_bytes ? t.tile_bytes : m.tile_bytes ? m.tile_bytes : 12288;   // two 6144-byte transfers per stage
+	g.stages = t.stages ? t.stages : m.stages ? m.stages : (fused ? 3 : 4);
+	g.ctas_per_sm = t.ctas_per_sm ? t.ctas_per_sm : m.ctas_per_sm ? m.ctas_per_sm : 1;
 	return g;
 }
 inline bool valid_tile(int tile) { return tile == 6144 || tile == 9216 || tile == 12288 || tile == 18432 || tile == 24576; }

@@ -807,7 +807,71 @@ int perseus_gpu_set_tuning(perseus_gpu *h, const perseus_gpu_tuning *t)
 	pg::Tuning r = resolve_tuning(t);
 	int rc = check_tuning(r);
 	if (rc) return rc;
+	memcpy(r.tuned, h->tune.tuned, sizeof(r.tuned));   // autotune results survive; explicit fields take precedence anyway
 	h->tune = r;
+	return 0;
+}
+
+int perseus_gpu_get_geometry(perseus_gpu *h, unsigned flags, int *tile_bytes, int *stages, int *ctas_per_sm)
+{
+	if (!h) return fail(PERSEUS_GPU_NULLHANDLE, "null handle");
+	const pg::Geometry g = pg::resolve_geometry(h->tune, flags & 7u);
+	if (tile_bytes) *tile_bytes = g.tile_bytes;
+	if (stages) *stages = g.stages;
+	if (ctas_per_sm) *ctas_per_sm = g.ctas_per_sm;
+	return 0;
+}
+
+int perseus_gpu_autotune(perseus_gpu *h, double *gbs_single, double *gbs_fused)
+{
+	int rc = bind(h);
+	if (rc) return rc;
+	rc = perseus_gpu_sync(h);
+	if (rc) return rc;
+	const size_t nbytes = (size_t)87381 * 6144;            // 512 MiB of wire: far beyond L2, 0.15-0.3 ms per launch
+	const size_t ns = nbytes / 6;
+	uint8_t *in = nullptr, *oi = nullptr, *of = nullptr;
+	cudaError_t e = cudaMalloc(&in, nbytes);
+	if (e == cudaSuccess) e = cudaMalloc(&oi, ns * 8);
+	if (e == cudaSuccess) e = cudaMalloc(&of, ns * 8);
+	cudaStream_t st = h->streams[0];
+	if (e == cudaSuccess) e = cudaMemsetAsync(in, 0x5A, nbytes, st);
+	static const pg::Geometry cand[] = {{12288, 2, 1}, {12288, 3, 1}, {12288, 4, 1}, {12288, 5, 1}, {12288, 6, 1}, {6144, 5, 1},
+	                                    {6144, 6, 1},  {6144, 8, 1},  {18432, 2, 1}, {18432, 3, 1}, {24576, 2, 1}, {12288, 2, 2}};
+	cudaEvent_t e0 = h->events[kEventSlots - 2], e1 = h->events[kEventSlots - 1];
+	double best_gbs[2] = {0.0, 0.0};
+	pg::Geometry best[2] = {};
+	for (int cls = 0; cls < 2 && e == cudaSuccess; ++cls) {
+		const unsigned fmt = cls ? (pg::FMT_I32 | pg::FMT_F32) : pg::FMT_F32;
+		for (const pg::Geometry &g : cand) {
+			pg::Tuning t{};
+			t.store_mode = h->tune.store_mode;
+			t.tile_bytes = g.tile_bytes; t.stages = g.stages; t.ctas_per_sm = g.ctas_per_sm;
+			int n = 0;
+			float ms = 0.f;
+			e = pg::launch_unpack(in, nbytes, cls ? oi : nullptr, of, fmt, t, h->sm_count, st, &n);        // warm
+			if (e == cudaSuccess) e = cudaEventRecord(e0, st);
+			for (int r = 0; r < 3 && e == cudaSuccess; ++r) e = pg::launch_unpack(in, nbytes, cls ? oi : nullptr, of, fmt, t, h->sm_count, st, &n);
+			if (e == cudaSuccess) e = cudaEventRecord(e1, st);
+			if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+			if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+			if (e != cudaSuccess) break;
+			h->stats.kernel_launches += 4;
+			const double gbs = (cls ? 22.0 : 14.0) * (double)ns * 3.0 / (ms * 1e-3) / 1e9;
+			if (gbs > best_gbs[cls]) { best_gbs[cls] = gbs; best[cls] = g; }
+		}
+	}
+	if (in) cudaFree(in);
+	if (oi) cudaFree(oi);
+	if (of) cudaFree(of);
+	if (e != cudaSuccess) {
+		cudaGetLastError();
+		return fail(PERSEUS_GPU_CUDAERR, "autotune failed: %s", cudaGetErrorString(e));
+	}
+	h->tune.tuned[0] = best[0];
+	h->tune.tuned[1] = best[1];
+	if (gbs_single) *gbs_single = best_gbs[0];
+	if (gbs_fused) *gbs_fused = best_gbs[1];
 	return 0;
 }
 

@@ -20,6 +20,14 @@ def replay_bin(tmp_path_factory):
     return out
 
 
+@pytest.fixture(scope="module")
+def shard_bin(tmp_path_factory):
+    out = tmp_path_factory.mktemp("bin") / "perseus_gpu_shard"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", str(ROOT / "include"),
+                    str(ROOT / "examples" / "perseus_gpu_shard.c"), "-L", str(LIBDIR), "-lperseus_gpu", "-o", str(out)], check=True)
+    return out
+
+
 def run(binary, *args):
     env = dict(os.environ, LD_LIBRARY_PATH=f"{LIBDIR}:{os.environ.get('LD_LIBRARY_PATH', '')}")
     return subprocess.run([str(binary), *args], capture_output=True, text=True, env=env, timeout=120)
@@ -63,3 +71,27 @@ def test_example_paced_run_streams_at_the_sample_rate(replay_bin, tmp_path):
     assert 1.5e6 < nsamples < 2.6e6 and out.stat().st_size % 8192 == 0
     wire = O.COracle().synth_random(6144 * 8)
     assert out.read_bytes()[: 8 * 8192] == O.COracle().unpack(wire, O.MODE_F32).tobytes()
+
+
+def test_shard_example_builds_and_fails_loudly_without_a_gpu(shard_bin):
+    import torch
+    if not torch.cuda.is_available():
+        r = run(shard_bin, "-n", "64")
+        assert r.returncode == 1 and "no usable GPU" in r.stderr
+
+
+@pytest.mark.gpu
+def test_shard_example_checksum_equals_oracle_whole_recording(shard_bin, coracle):
+    """One host thread, one handle per device, no collective: the per-shard checksums add up to the oracle's
+    checksum of the whole recording, however many GPUs the box has."""
+    import json
+    import torch
+    n = 4099
+    wire = coracle.synth_random(n * 6144)
+    for flag, mode in (((), O.MODE_I32), (("-p",), O.MODE_F32)):
+        want = coracle.checksum32(coracle.unpack(wire, mode, nthreads=O.host_threads()))
+        for g in sorted({1, torch.cuda.device_count()}):
+            r = run(shard_bin, "-n", str(n), "-g", str(g), "-r", "3", *flag)
+            assert r.returncode == 0, r.stderr
+            d = json.loads(r.stdout)
+            assert d["gpus"] == g and int(d["recording_checksum"], 16) == want

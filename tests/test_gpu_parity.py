@@ -307,6 +307,21 @@ def test_overlapped_checksum_flag(pg, coracle):
         h.dev_free(d_in)
 
 
+def test_autotune_measures_and_keeps_a_geometry(pg, coracle):
+    with pg.PerseusGpu(device=0) as h:
+        assert h.get_geometry(pg.OUT_FLOAT) == {"tile_bytes": 12288, "stages": 4, "ctas_per_sm": 1}              # B200 defaults
+        assert h.get_geometry(pg.OUT_INT32 | pg.OUT_FLOAT) == {"tile_bytes": 12288, "stages": 3, "ctas_per_sm": 1}
+        single, fused = h.autotune()
+        assert single > 4000 and fused > 4000, (single, fused)            # GB/s of the winners on a B200-class device
+        tuned = (h.get_geometry(pg.OUT_INT32), h.get_geometry(pg.OUT_INT32 | pg.OUT_FLOAT_POW2))
+        assert all(g["tile_bytes"] in (6144, 12288, 18432, 24576) and 2 <= g["stages"] <= 8 for g in tuned)
+        check_against_oracle(pg, h, coracle, coracle.synth_random(12288 * 300 + 30, seed=3))                      # still bit-exact
+        h.set_tuning(stages=2)                                            # explicit settings win over measured ones
+        assert h.get_geometry(pg.OUT_FLOAT)["stages"] == 2
+        h.set_tuning()
+        assert (h.get_geometry(pg.OUT_INT32), h.get_geometry(pg.OUT_INT32 | pg.OUT_FLOAT_POW2)) == tuned
+
+
 def test_argument_errors(pg, gpu):
     with DevBuf(gpu, 6144) as d, DevBuf(gpu, 8192) as o:
         for args, code in (((d.p, 6144, o.p, o.p, pg.OUT_FLOAT | pg.OUT_FLOAT_POW2), "ERRPARAM"),
