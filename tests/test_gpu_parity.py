@@ -639,6 +639,35 @@ def test_two_handles_on_two_threads(pg, coracle):
         assert np.array_equal(out[k], coracle.unpack(wire[k], O.MODE_I32).view(np.uint32).reshape(-1))
 
 
+def test_several_receivers_served_by_one_thread(pg, coracle):
+    """libperseus-sdr serves up to 8 receivers from ONE poll thread (perseus-sdr.c:43,736-770): their callbacks interleave
+    on that thread, each with its own `extra`.  One perseus_gpu handle per receiver; streams and slabs are independent."""
+    nrx, ntransfers = 4, 37
+    wires = [coracle.synth_random(ntransfers * 6144, seed=500 + r).reshape(ntransfers, 6144) for r in range(nrx)]
+    handles = [pg.PerseusGpu(device=0, stream_flags=pg.OUT_FLOAT if r % 2 else pg.OUT_INT32, slab_bytes=6144 * (3 + r), nslabs=2,
+                             max_latency_us=0xFFFFFFFF) for r in range(nrx)]
+    outs = [[] for _ in range(nrx)]
+
+    def make_sink(r):
+        def sink(blk, extra):
+            b = blk.contents
+            handles[r].sync()
+            outs[r].append(handles[r].to_host(b.dev_f32 if r % 2 else b.dev_i32, b.nsamples * 8, np.uint32))
+        return sink
+
+    for r, h in enumerate(handles):
+        h.set_sink(make_sink(r))
+    for k in range(ntransfers):                      # the poll thread's view: transfers of all receivers, interleaved
+        for r, h in enumerate(handles):
+            h.input_callback(wires[r][k].ctypes.data, 6144)
+    for r, h in enumerate(handles):
+        h.flush()
+        want = coracle.unpack(wires[r].reshape(-1), O.MODE_F32 if r % 2 else O.MODE_I32).view(np.uint32).reshape(-1)
+        assert np.array_equal(np.concatenate(outs[r]), want), r
+        assert h.stats()["callbacks"] == ntransfers
+        h.close()
+
+
 def test_callback_errors_are_latched_and_surface_at_flush(pg, coracle):
     """The reference ignores callback return values (perseus-in.c:207), so the trampoline returns 0 even when it fails;
     the failure is reported by the next perseus_gpu_flush / close, once, and the handle stays usable."""
