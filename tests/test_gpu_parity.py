@@ -154,7 +154,7 @@ def test_verify_detects_single_corruption(pg, gpu, coracle):
         assert gpu.verify(din.p, wire.size, di.p, None, pg.OUT_INT32) == (1, 4321)
 
 
-SIZES = sorted(set(list(range(0, 100)) + [510, 1020, 16320, 6143, 6144, 6145, 6150, 12287, 12288, 12289, 12294, 12300, 12288 + 48,
+SIZES = sorted(set(list(range(0, 100)) + [510 * k for k in range(1, 33)] + [510, 1020, 16320, 6143, 6144, 6145, 6150, 12287, 12288, 12289, 12294, 12300, 12288 + 48,
                                           24575, 24576, 24582, 3 * 12288 - 6, 3 * 12288 + 18, 510 * 7, 49152, 100_003]))
 
 

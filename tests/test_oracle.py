@@ -128,6 +128,16 @@ def test_ragged_sizes_ignore_trailing_bytes(coracle, maybe_ref, nbytes):
             assert np.array_equal(maybe_ref.unpack(b, mode, chunk=nbytes).view(np.uint32), c.view(np.uint32))
 
 
+def test_every_legal_transfer_size(coracle, ref):
+    """perseus-sdr.c:662-680: 6144 and 12288 with the shipped firmware, 510*k (k = 1..32, <= 16320) with the legacy one."""
+    wire = coracle.synth_random(16320 * 3, seed=12)
+    for size in [6144, 12288] + [510 * k for k in range(1, 33)]:
+        assert size % 6 == 0 and size <= 16320
+        for mode in (O.MODE_I32, O.MODE_F32):
+            a = ref.unpack(wire[: size * 3], mode, chunk=size).view(np.uint32)       # three transfers of that size
+            assert np.array_equal(a, coracle.unpack(wire[: size * 3], mode).view(np.uint32))
+
+
 def test_per_transfer_chunking_is_stateless(coracle, ref):
     """Every legal transfer size is a whole number of samples (perseus-sdr.c:671-676), so
     calling the callback per transfer == unpacking the concatenation."""
