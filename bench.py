@@ -471,6 +471,19 @@ def ours(args):
                   "what": "perseus_vrx_run -> perseus_gpu_input_callback per 6144-byte transfer (memcpy into a pinned 16 MiB slab, "
                           "H2D + fused unpack per slab on 2 streams), one host thread; bounded by that thread's memcpy"}
         v.close(); hs.close()
+        # hand-off latency of ONE transfer: callback + flush (slab of 1024 samples: H2D 6 KiB, one kernel, sync)
+        hl = pg.PerseusGpu(device=local, stream_flags=FUSED, slab_bytes=BUF * 8, nslabs=2, nstreams=1)
+        one = np.frombuffer(pg.synth_fill(BUF).tobytes(), np.uint8).copy()
+        for _ in range(20):
+            hl.input_callback(one.ctypes.data, BUF); hl.flush()
+        lat = []
+        for _ in range(200):
+            t0 = time.perf_counter()
+            hl.input_callback(one.ctypes.data, BUF); hl.flush()
+            lat.append((time.perf_counter() - t0) * 1e6)
+        hl.close()
+        e2e_cb["one_transfer_latency_us"] = {"median": round(statistics.median(lat), 1), "p95": round(sorted(lat)[189], 1),
+                                             "what": "wall time of perseus_gpu_input_callback(6144 B) + perseus_gpu_flush: samples resident on the device"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

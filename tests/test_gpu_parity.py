@@ -126,6 +126,15 @@ def test_exhaustive_2p24_all_formats(pg, gpu, coracle, variant):
                 assert f"{coracle.fnv1a64(out):016x}" == g["int32_fnv1a64"]
             if m == O.MODE_F32:
                 assert f"{coracle.fnv1a64(out):016x}" == g["float_fnv1a64"]
+    # The ramp puts even codes of I in the first sample of every 12-byte unit and odd codes in the second; shifting the
+    # ramp by one sample swaps them, so every code has now been through every one of the four output positions.
+    shifted = coracle.synth_ramp(1 << 24, first_sample=1)
+    with DevBuf(gpu, n) as din:
+        gpu.generate(din.p, n, pg.SYNTH_RAMP, 0, 6)
+        assert np.array_equal(gpu.to_host(din.p, n, np.uint8), shifted)
+    i32, f32 = run_unpack(pg, gpu, shifted, pg.OUT_INT32 | pg.OUT_FLOAT)
+    assert np.array_equal(i32, coracle.unpack(shifted, O.MODE_I32, nthreads=O.host_threads()).view(np.uint32).reshape(-1))
+    assert np.array_equal(f32, coracle.unpack(shifted, O.MODE_F32, nthreads=O.host_threads()).view(np.uint32).reshape(-1))
 
 
 def test_multiply_equals_ieee_division_on_device(pg, gpu):
