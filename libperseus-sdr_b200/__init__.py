@@ -15,7 +15,7 @@ from pathlib import Path
 
 PKG_DIR = Path(__file__).resolve().parent
 REPO = PKG_DIR.parent
-LIB_PATH = PKG_DIR / "lib" / "libperseus_gpu.so"
+LIB_PATH = Path(os.environ.get("PERSEUS_GPU_LIB", PKG_DIR / "lib" / "libperseus_gpu.so"))   # override: A/B builds in tools/
 HEADER = REPO / "include" / "perseus-gpu.h"
 
 # include/perseus-gpu.h
