@@ -654,8 +654,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--buffers", type=int, default=CFG2_BUFFERS, help="transfers per GPU (default: cfg2, 1 GiB)")
     ap.add_argument("--e2e-steps", type=int, default=10)
-    ap.add_argument("--chunk-mib", type=int, default=32)
-    ap.add_argument("--streams", type=int, default=3)
+    ap.add_argument("--chunk-mib", type=int, default=0, help="staging chunk for host pointers (0 = library default, 32 MiB)")
+    ap.add_argument("--streams", type=int, default=0, help="CUDA streams per handle (0 = library default, 2)")
     ap.add_argument("--no-roundtrip", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-callback", action="store_true")
