@@ -437,6 +437,30 @@ def test_cfg3_mixed_rate_batch_small_against_oracle(pg, gpu, coracle):
                     gpu.dev_free(b.p)
 
 
+def test_batch_plan_edge_cases(pg, gpu, coracle):
+    """Empty batches, and a plan outliving a change of the handle's tuning (it keeps the tile size it was built with)."""
+    assert gpu.unpack_batch([], pg.OUT_INT32) == 0
+    wires = [coracle.synth_random(6144 * (5 + 3 * r) + 6 * r, seed=900 + r) for r in range(7)]
+    devs = [(gpu.to_device(w), DevBuf(gpu, w.size // 6 * 8 + 16)) for w in wires]
+    segs = [(d, w.size, o.p, None) for (d, o), w in zip(devs, wires)]
+    plan = gpu.plan_create(segs, pg.OUT_INT32)
+    for tune in (dict(), dict(tile_bytes=6144, stages=5), dict(tile_bytes=24576, stages=2, ctas_per_sm=2), dict(variant=pg.VARIANT_DIRECT)):
+        gpu.set_tuning(**tune)
+        for _, o in devs:
+            gpu.memset(o.p, 0, o.n)
+        assert gpu.plan_run(plan) == sum(w.size // 6 for w in wires)
+        for (d, o), w in zip(devs, wires):
+            assert np.array_equal(gpu.to_host(o.p, w.size // 6 * 8, np.uint32), coracle.unpack(w, O.MODE_I32).view(np.uint32).reshape(-1)), tune
+    gpu.set_tuning()
+    gpu.plan_destroy(plan)
+    for d, o in devs:
+        gpu.dev_free(d)
+        gpu.dev_free(o.p)
+    with pytest.raises(pg.PerseusGpuError) as e:
+        gpu.unpack_batch([(devs[0][0], 6144, None, None)], pg.OUT_INT32)          # output missing
+    assert e.value.code == pg.ERR["ERRPARAM"]
+
+
 def test_cfg3_full_size_1024_receivers_one_launch(pg, gpu, coracle):
     """BASELINE config 3 at full size: 1024 receivers, 652 956 transfers = 4 011 761 664 B in one launch.
     Checked on the device by the independent per-sample kernel over everything, and against the CPU oracle
