@@ -311,6 +311,10 @@ int perseus_vrx_get_sampling_rates(int *buf, unsigned int size);
 /* Nearest-rate selection with the reference's midpoint rule; returns the rate chosen. */
 int perseus_vrx_nearest_rate(int requested);
 int perseus_vrx_get_sampling_rate(perseus_vrx *v);
+/* Name of the FPGA bitstream that produces `rate` (one of the ten table rates), e.g. 2000000 -> "perseus2m24v21";
+ * the names are the reference's *.rbs files (generate_fpga_code.sh:71-97).  NULL for a rate not in the table.
+ * All ten are 24-bit formats ("...24v..."): the wire layout is the same at every rate. */
+const char *perseus_vrx_bitstream_name(int rate);
 /* Same validation and error codes as perseus_start_async_input (perseus-sdr.c:638-692):
  * buffersize <= 16320 and a multiple of 6144 (EP 512) / 510 (EP 510).  Starts a delivery
  * thread.  stop cancels, joins, and fills the statistics. */

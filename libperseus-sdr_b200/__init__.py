@@ -144,6 +144,7 @@ def lib() -> C.CDLL:
         "perseus_vrx_close": (ci, [vp]),
         "perseus_vrx_get_sampling_rates": (ci, [P(ci), C.c_uint]),
         "perseus_vrx_nearest_rate": (ci, [ci]),
+        "perseus_vrx_bitstream_name": (C.c_char_p, [ci]),
         "perseus_vrx_get_sampling_rate": (ci, [vp]),
         "perseus_vrx_start_async_input": (ci, [vp, u32, vp, vp]),
         "perseus_vrx_stop_async_input": (ci, [vp]),
@@ -185,6 +186,11 @@ def sampling_rates() -> list[int]:
     buf = (C.c_int * 16)()
     check(lib().perseus_vrx_get_sampling_rates(buf, 16))
     return [v for v in buf if v]
+
+
+def bitstream_name(rate: int) -> str | None:
+    n = lib().perseus_vrx_bitstream_name(rate)
+    return n.decode() if n else None
 
 
 def nearest_rate(requested: int) -> int:

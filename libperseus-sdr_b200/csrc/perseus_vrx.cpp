@@ -28,6 +28,9 @@ int vfail(int code, const char *fmt, ...);
 // perseus-sdr.h:282-285 / generate_fpga_code.sh:71-97 — rates encoded in the bitstream file names
 const int kRates[] = {48000, 95000, 96000, 125000, 192000, 250000, 500000, 1000000, 1600000, 2000000};
 constexpr int kNumRates = sizeof(kRates) / sizeof(kRates[0]);
+// the bitstream files those rates come from (/root/reference/*.rbs), same order
+const char *const kBitstreams[] = {"perseus48k24v31",  "perseus95k24v31",  "perseus96k24v31", "perseus125k24v21", "perseus192k24v31",
+                                   "perseus250k24v21", "perseus500k24v21", "perseus1m24v21",  "perseus1d6m24v21", "perseus2m24v21"};
 
 using Clock = std::chrono::steady_clock;
 
@@ -206,6 +209,13 @@ int perseus_vrx_get_sampling_rates(int *buf, unsigned int size)
 	}
 	for (int i = 0; i < kNumRates; ++i) buf[i] = kRates[i];
 	return 0;
+}
+
+const char *perseus_vrx_bitstream_name(int rate)
+{
+	for (int i = 0; i < kNumRates; ++i)
+		if (kRates[i] == rate) return kBitstreams[i];
+	return nullptr;
 }
 
 int perseus_vrx_nearest_rate(int requested)

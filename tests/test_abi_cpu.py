@@ -121,6 +121,17 @@ def test_rate_table_and_nearest_rate(pg):
     probes |= {(a + b) // 2 + d for a, b in zip(rates, rates[1:]) for d in (-1, 0, 1)}
     for x in sorted(probes):
         assert pg.nearest_rate(x) == reference_nearest_rate(x, rates), x
+    # bitstream names = the reference's *.rbs files; the rate is encoded in the name (generate_fpga_code.sh:71-97)
+    def rate_from_name(name):
+        m = re.fullmatch(r"perseus(\d+)(d(\d+))?([km])24v\d+", name)
+        mant = float(m.group(1) + ("." + m.group(3) if m.group(3) else ""))
+        return int(round(mant * (1000 if m.group(4) == "k" else 1_000_000)))
+    assert [rate_from_name(pg.bitstream_name(r)) for r in rates] == rates
+    assert pg.bitstream_name(2_000_000) == "perseus2m24v21" and pg.bitstream_name(95_000) == "perseus95k24v31"   # BASELINE configs 2 and 1
+    assert pg.bitstream_name(44_100) is None
+    import os
+    if os.path.isdir("/root/reference"):
+        assert sorted(pg.bitstream_name(r) + ".rbs" for r in rates) == sorted(f for f in os.listdir("/root/reference") if f.endswith(".rbs"))
     buf = (C.c_int * 4)()
     assert pg.lib().perseus_vrx_get_sampling_rates(buf, 4) == pg.ERR["BUFFERSIZE"]   # perseus-sdr.c:825
     assert pg.lib().perseus_vrx_get_sampling_rates(buf, 0) == pg.ERR["ERRPARAM"]     # perseus-sdr.c:830
