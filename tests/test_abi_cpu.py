@@ -38,6 +38,20 @@ def test_header_is_plain_c_and_cites_reference():
                        check=True)
 
 
+def test_header_coexists_with_the_reference_header():
+    """INTEGRATION.md step 1 compiles: the reference's real perseus-sdr.h (libusb stubbed), then perseus-gpu.h, and
+    perseus_gpu_input_callback handed to perseus_start_async_input's own prototype (perseus-sdr.h:247-248)."""
+    import os
+    if not os.path.exists("/root/reference/perseus-sdr.h"):
+        pytest.skip("/root/reference not mounted")
+    with tempfile.TemporaryDirectory() as td:
+        open(f"{td}/t.c", "w").write('#include "perseus-sdr.h"\n#include "perseus-gpu.h"\n'
+                                     "int start(perseus_descr *d, perseus_gpu *g)\n"
+                                     "{ return perseus_start_async_input(d, 6144, perseus_gpu_input_callback, g); }\n")
+        subprocess.run(["gcc", "-std=gnu99", "-Wall", "-Werror=incompatible-pointer-types", "-I", str(ROOT / "oracle" / "stub"),
+                        "-I", "/root/reference", "-I", str(ROOT / "include"), "-c", f"{td}/t.c", "-o", f"{td}/t.o"], check=True)
+
+
 def test_struct_layouts_match_header(pg):
     """ctypes mirrors vs the C compiler's view of the structs."""
     with tempfile.TemporaryDirectory() as td:
