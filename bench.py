@@ -14,6 +14,9 @@ Prints ONE JSON line (rank 0).  `value` = complex Msamples/s, whole job, inputs 
 `e2e` = same metric through perseus_gpu_unpack() with PINNED HOST input (H2D inside the timed region,
 outputs left on the device as north_star's end-to-end mode specifies, plus a D2H read of the step's
 result: the on-device checksums of both outputs); `e2e_roundtrip` additionally copies both outputs back.
+`workloads` carries BASELINE.json's other GPU configurations in the same run, same schema per record:
+cfg3 (1024 mixed-rate receivers, one launch, per GPU) and cfg4 (the 64 GiB recording sharded over the N
+GPUs: strong scaling, whole-recording checksum identical for every N).
 oracle/ is used here only by the cpu_baseline leg and by --impl reference (timed CPU baselines) — never on the measured
 path; the untimed correctness gate before timing uses the library's own independent verify kernel.
 """
@@ -39,6 +42,18 @@ BYTES_PER_SAMPLE_FUSED = 6 + 8 + 8     # algorithmic HBM traffic per complex sam
 BYTES_PER_SAMPLE_SINGLE = 6 + 8
 METRIC, UNIT = "complex_msamples_per_s_unpacked", "Msamples/s"
 PCIE_GEN5_X16_GBS = 63.0        # 32 GT/s * 16 lanes * 128/130 / 8
+CFG4_BUFFERS = 11_184_810       # 64 GiB of 6144-byte transfers, SURVEY.md §8d cfg4
+
+
+def workload_config(world: int, nbuf: int = CFG2_BUFFERS) -> dict:
+    """The `config` object of the JSON line.  Both arms (ours and --impl reference) print exactly this, so the driver can
+    see they ran the same workload; everything specific to one arm (kernel geometry, NUMA binding) lives under `setup`."""
+    nbytes = nbuf * BUF
+    return {"workload": f"cfg2: perseus2m24v21 (2 MS/s) layout, {nbuf} transfers x {BUF} B = {nbytes} wire bytes per GPU "
+                        f"({nbytes // 6} complex samples), each unpacked to int32 AND float; {world} GPU(s): rank r owns transfers "
+                        f"[r*{nbuf},(r+1)*{nbuf}) of the {world}x recording",
+            "transfers_per_gpu": nbuf, "transfer_bytes": BUF, "outputs": "int32+float", "n_gpus": world,
+            "generator": "splitmix64(seed + word index), seed 0x5045525345555300"}
 
 
 def log(*a):
@@ -224,7 +239,10 @@ def cpu_baseline_leg(budget_s: float = 12.0):
 def reference_arm(args):
     """--impl reference: the reference's OWN CPU implementation of the path (user_data_callback_c_u + _c_f,
     compiled verbatim into oracle/_ref) on all host threads, each thread an independent receiver stream fed
-    6144-byte transfers; falls back to the restated port when oracle/_ref is not present."""
+    6144-byte transfers; falls back to the restated port when oracle/_ref is not present.
+    Same workload as our arm: one step = the whole N x cfg2 recording through the int32 callback and the float
+    callback.  The N shards are unpacked one after the other from the same 1 GiB of synthetic wire bytes (the
+    content does not change the work; it keeps host memory at 2.5 GB for every N)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -233,26 +251,30 @@ def reference_arm(args):
     co = O.COracle()
     threads = O.host_threads()
     use_ref = O.Ref.available()
-    per_thread = 4096 if use_ref else 16384           # transfers per thread per step
-    nbuf = min(CFG2_BUFFERS, threads * per_thread)
+    world = max(1, args.gpus)
+    nbuf = args.buffers
     wire = co.synth_random(nbuf * BUF, seed=O.SYNTH_SEED)
     ns = nbuf * 1024
     out = np.empty(ns * 2, np.int32)
     if use_ref:
         ref = O.Ref()
 
-        def step():
+        def shard():
             ref.unpack_mt_raw(False, wire.ctypes.data, wire.size, BUF, out.ctypes.data, out.nbytes, threads)
             ref.unpack_mt_raw(True, wire.ctypes.data, wire.size, BUF, out.ctypes.data, out.nbytes, threads)
         kind, what = "reference", "oracle/_ref: examples/perseustest.c callbacks verbatim (fwrite per sample into a memory FILE*)"
     else:
-        def step():
+        def shard():
             co.unpack_raw(O.MODE_I32, wire.ctypes.data, wire.size, out.ctypes.data, threads)
             co.unpack_raw(O.MODE_F32, wire.ctypes.data, wire.size, out.ctypes.data, threads)
         kind, what = "port", "oracle/perseus_oracle.c restatement (oracle/_ref not present)"
+
+    def step():
+        for _ in range(world):
+            shard()
     # check the arm against the restated oracle on the first transfers (untimed)
     chk = co.unpack(wire[: 8 * BUF], O.MODE_F32).view(np.uint32).reshape(-1)
-    step()
+    shard()
     assert np.array_equal(out[: chk.size].view(np.uint32), chk), "reference arm output differs from the oracle"
     for _ in range(args.warmup):
         step()
@@ -260,12 +282,13 @@ def reference_arm(args):
     for _ in range(args.steps):
         step()
     dt = time.perf_counter() - t0
-    val = ns * args.steps / dt / 1e6
-    sample = f"{nbuf} transfers x {BUF} B per step ({wire.size / 2**20:.0f} MiB wire), int32 callback + float callback, {what}"
+    val = ns * world * args.steps / dt / 1e6
+    sample = (f"the full workload: {world} x {nbuf} transfers x {BUF} B per step ({world * wire.size / 2**20:.0f} MiB wire), int32 callback + "
+              f"float callback on {threads} host threads, {what}")
     line = {"impl": "reference", "metric": METRIC, "value": round(val, 2), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32+f32", "data": "synthetic",
-            "config": {"workload": "cfg2 (perseus2m24v21 layout) bounded sample: " + sample, "threads": threads},
+            "config": workload_config(world, nbuf),
             "cpu_baseline": {"value": round(val, 2), "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": round(val, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -275,39 +298,166 @@ def reference_arm(args):
 
 # ----------------------------------------------------------------------------------------- our arm
 
+class Ctx:
+    """Per-rank plumbing shared by the legs: handle, distributed helpers, timing."""
+
+    def __init__(self, args):
+        import importlib
+        import torch
+        import torch.distributed as dist
+        import __graft_entry__ as G
+        self.args, self.torch, self.dist = args, torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus:
+            log(f"[bench] WORLD_SIZE={self.world} but --gpus {args.gpus}; using {self.world}")
+        self.numa = bind_to_gpu_numa_node(self.local)
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        if self.local == 0:
+            G.ensure_built()
+        self.barrier()
+        self.pg = G.load_package()
+        self.sharding = importlib.import_module("libperseus_sdr_b200.sharding")
+        self.allmax = self.sharding.allreduce_max
+        self.peak, self.peak_src = measured_peak()
+        self.h = self.pg.PerseusGpu(device=self.local, chunk_bytes=args.chunk_mib << 20, stage_slots=args.slots)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+
+    def timed(self, fn, steps, warmup, sampler=None, h=None):
+        """W untimed steps, then exactly K steps between barrier+sync, CUDA events on the launching stream, max over ranks."""
+        h = h or self.h
+        for _ in range(warmup):
+            fn()
+        h.sync(); self.torch.cuda.synchronize(); self.barrier()
+        with (sampler if sampler is not None else _Null()):
+            h.event_record(0)
+            for _ in range(steps):
+                fn()
+            h.event_record(1)
+            h.sync(); self.torch.cuda.synchronize()
+            ms = h.event_elapsed_ms(0, 1)
+        self.barrier()
+        return self.allmax(ms) / steps
+
+    def free_bytes(self):
+        return self.torch.cuda.mem_get_info(self.local)[0]
+
+    def close(self):
+        self.h.close()
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def mixed_rate_buffers(nrx=1024, window_s=1.024):
+    rates = [48000, 96000, 192000, 500000, 1000000, 2000000]          # SURVEY.md §8d cfg3
+    return [max(1, round(rates[r % 6] * window_s / 1024)) for r in range(nrx)]
+
+
+def workload_cfg3(cx, steps, warmup):
+    """BASELINE config 3: 1024 virtual receivers at six rates, every receiver its own input/output segment and seed,
+    unpacked to int32 AND float by ONE launch per step (per GPU; at N GPUs every rank runs its own 1024)."""
+    pg, h = cx.pg, cx.h
+    nbufs = mixed_rate_buffers()
+    total_in = sum(nbufs) * BUF
+    ns = total_in // 6
+    pad = 64                                                            # room to push one receiver's outputs off 16-byte alignment
+    d_in, d_i, d_f = h.dev_alloc(total_in), h.dev_alloc(ns * 8 + pad), h.dev_alloc(ns * 8 + pad)
+    segs, off = [], 0
+    for r, b in enumerate(nbufs):
+        h.generate(d_in + off, b * BUF, pg.SYNTH_RANDOM, pg.SYNTH_SEED + cx.rank * 1024 + r, 0)
+        segs.append((d_in + off, b * BUF, d_i + off // 6 * 8, d_f + off // 6 * 8))
+        off += b * BUF
+    flags = pg.OUT_INT32 | pg.OUT_FLOAT
+    plan = h.plan_create(segs, flags)
+    h.plan_run(plan)
+    bad, _ = h.verify(d_in, total_in, d_i, d_f, flags)
+    assert bad == 0, bad
+    sampler = ClockSampler(cx.local)
+    l0 = h.stats()["kernel_launches"]
+    ms = cx.timed(lambda: h.plan_run(plan, pg.ASYNC), steps, warmup, sampler)
+    launches = h.stats()["kernel_launches"] - l0 - warmup
+    h.plan_destroy(plan)
+    # the same batch with ONE receiver's outputs only 4-byte aligned (the last 2 MS/s receiver, moved 4 bytes up):
+    # its tiles alone take the register-only kernel, as a second launch
+    odd = max(r for r in range(len(nbufs)) if nbufs[r] == max(nbufs))
+    segs2 = list(segs)
+    if odd == len(segs) - 1:
+        a, n, oi, of = segs[odd]
+        segs2[odd] = (a, n, oi + 4, of + 4)
+    else:                                                               # not the last segment: shift it inside its own range
+        a, n, oi, of = segs[odd]
+        segs2[odd] = (a, n - BUF, oi + 4, of + 4)
+    plan2 = h.plan_create(segs2, flags)
+    ms_odd = cx.timed(lambda: h.plan_run(plan2, pg.ASYNC), steps, warmup)
+    h.plan_destroy(plan2)
+    ns2 = sum(n // 6 for _, n, _, _ in segs2)
+    for p_ in (d_in, d_i, d_f):
+        h.dev_free(p_)
+    achieved = BYTES_PER_SAMPLE_FUSED * ns / (ms * 1e-3) / 1e9
+    return {"metric": METRIC, "value": round(ns * cx.world / (ms * 1e-3) / 1e6, 1), "unit": UNIT, "n_gpus": cx.world, "steps": steps,
+            "warmup": warmup, "ms_per_step": round(ms, 4), "scaling": "weak", "dtype": "int32+f32",
+            "config": {"workload": f"cfg3: 1024 virtual receivers at 48k/96k/192k/500k/1M/2M S/s, 1.024 s window = {sum(nbufs)} transfers x {BUF} B "
+                                   f"({total_in} wire bytes) per GPU, own seed per receiver, unpacked to int32 AND float in ONE launch"},
+            "roofline": {"bound": "hbm", "kernel": "unpack24_stream_kernel<I32|F32, batched>", "achieved": round(achieved, 1), "peak": cx.peak,
+                         "unit": "GB/s", "frac": round(achieved / cx.peak, 4), "bytes_per_sample": BYTES_PER_SAMPLE_FUSED},
+            "gpu_launches": int(launches), "clocks": sampler.summary(),
+            "one_misaligned_receiver": {"ms_per_step": round(ms_odd, 4), "vs_all_aligned": round((ms_odd / ns2) / (ms / ns), 4),
+                                        "what": f"receiver {odd} ({nbufs[odd]} transfers) writes to outputs that are only 4-byte aligned: its tiles go to "
+                                                "the register-only kernel in a second launch, the other 1023 receivers stay on the pipeline; ratio of "
+                                                "time per sample"}}
+
+
+def workload_cfg4(cx, steps, warmup):
+    """BASELINE config 4: the 64 GiB recording sharded by contiguous transfer range over the N GPUs (strong scaling),
+    generated on the device, unpacked to float, kernel-only.  Returns None when a shard does not fit this GPU."""
+    pg, h = cx.pg, cx.h
+    first, count = pg.shard_range(CFG4_BUFFERS, cx.world, cx.rank)
+    nbytes = count * BUF
+    ns = nbytes // 6
+    need = nbytes + ns * 8 + (1 << 30)
+    fits = cx.sharding.allreduce_max(0.0 if cx.free_bytes() >= need else 1.0) == 0.0
+    if not fits:
+        return {"skipped": f"a shard needs {need / 2**30:.1f} GiB of device memory, {cx.free_bytes() / 2**30:.1f} GiB free"}
+    d_in, d_f = h.dev_alloc(nbytes), h.dev_alloc(ns * 8)
+    h.generate(d_in, nbytes, pg.SYNTH_RANDOM, pg.SYNTH_SEED, first * BUF)
+    flags = pg.OUT_FLOAT
+    h.unpack(d_in, nbytes, None, d_f, flags)
+    bad, _ = h.verify(d_in, nbytes, None, d_f, flags)
+    assert bad == 0, bad
+    # position-weighted checksum of the whole recording's float output: shard sums add up (mod 2^64), so it must be
+    # the same number whatever N is
+    checksum = cx.sharding.allreduce_sum_u64(h.checksum(d_f, ns * 2, first_index=first * 2048))
+    sampler = ClockSampler(cx.local)
+    l0 = h.stats()["kernel_launches"]
+    ms = cx.timed(lambda: h.unpack(d_in, nbytes, None, d_f, flags | pg.ASYNC), steps, warmup, sampler)
+    launches = h.stats()["kernel_launches"] - l0 - warmup
+    h.dev_free(d_in); h.dev_free(d_f)
+    achieved = BYTES_PER_SAMPLE_SINGLE * ns / (ms * 1e-3) / 1e9          # per GPU; the slowest rank's time
+    return {"metric": METRIC, "value": round(CFG4_BUFFERS * 1024 / (ms * 1e-3) / 1e6, 1), "unit": UNIT, "n_gpus": cx.world, "steps": steps,
+            "warmup": warmup, "ms_per_step": round(ms, 4), "scaling": "strong", "dtype": "f32",
+            "config": {"workload": f"cfg4: 64 GiB recording ({CFG4_BUFFERS} transfers x {BUF} B) sharded by contiguous transfer range over "
+                                   f"{cx.world} GPU(s), rank 0 holds {count} transfers; generated on the device; float output; kernel-only"},
+            "roofline": {"bound": "hbm", "kernel": "unpack24_stream_kernel<F32>", "achieved": round(achieved, 1), "peak": cx.peak, "unit": "GB/s",
+                         "frac": round(achieved / cx.peak, 4), "bytes_per_sample": BYTES_PER_SAMPLE_SINGLE, "what": "per GPU, max-over-ranks time"},
+            "recording_float_checksum": f"{checksum:016x}", "gpu_launches": int(launches), "clocks": sampler.summary()}
+
+
 def ours(args):
     import numpy as np
-    import torch
-    import torch.distributed as dist
-    import __graft_entry__ as G
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        log(f"[bench] WORLD_SIZE={world} but --gpus {args.gpus}; using {world}")
-    numa = bind_to_gpu_numa_node(local)
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-
-    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
-        G.ensure_built()
-    barrier()
-    pg = G.load_package()
-    import importlib
-    sharding = importlib.import_module("libperseus_sdr_b200.sharding")
-    allmax = sharding.allreduce_max
-
-    h = pg.PerseusGpu(device=local, chunk_bytes=args.chunk_mib << 20, nstreams=args.streams)
+    cx = Ctx(args)
+    pg, h, rank, world, local = cx.pg, cx.h, cx.rank, cx.world, cx.local
+    barrier, allmax, timed = cx.barrier, cx.allmax, cx.timed
+    sharding = cx.sharding
     if args.tile or args.stages or args.ctas or args.variant or args.store:
         h.set_tuning(variant=args.variant, tile_bytes=args.tile, stages=args.stages, ctas_per_sm=args.ctas, store_mode=args.store)
     if args.autotune:
-        tuning_gbs = h.autotune()
+        h.autotune()
     tuning = h.get_tuning()
     tuning["geometry_fused"] = h.get_geometry(pg.OUT_INT32 | pg.OUT_FLOAT)
     tuning["geometry_single"] = h.get_geometry(pg.OUT_FLOAT)
@@ -332,21 +482,6 @@ def ours(args):
         raise SystemExit(f"[bench] rank {rank}: {bad} output words differ from the per-sample recomputation (first {where})")
     recording_checksum = sharding.allreduce_sum_u64(h.checksum(d_f32, ns * 2, first_index=first * 2048))   # shard checksums add up
 
-    def timed(fn, steps, warmup, sampler=None):
-        for _ in range(warmup):
-            fn()
-        h.sync(); torch.cuda.synchronize(); barrier()
-        ctx = sampler if sampler is not None else _Null()
-        with ctx:
-            h.event_record(0)
-            for _ in range(steps):
-                fn()
-            h.event_record(1)
-            h.sync(); torch.cuda.synchronize()
-            ms = h.event_elapsed_ms(0, 1)
-        barrier()
-        return allmax(ms) / steps
-
     # -- headline: HBM-resident, fused int32+float pass
     sampler = ClockSampler(local)
     l0 = h.stats()["kernel_launches"]
@@ -355,7 +490,7 @@ def ours(args):
     clocks = sampler.summary()
     total_samples = ns * world
     value = total_samples / (ms_step * 1e-3) / 1e6
-    peak, peak_src = measured_peak()
+    peak, peak_src = cx.peak, cx.peak_src
     achieved = BYTES_PER_SAMPLE_FUSED * ns / (ms_step * 1e-3) / 1e9      # per GPU: each rank runs the same launch
     traffic = None
     try:
@@ -393,19 +528,18 @@ def ours(args):
     else:
         pin = h.host_alloc(nbytes)
     h.memcpy(pin, d_in, nbytes)                                           # the synthetic recording, now in pinned host memory
-    h2d_ms = []
-    for _ in range(3):                                                    # in-run PCIe H2D roofline: plain pinned copy
-        h.event_record(2); h.memcpy(d_in, pin, nbytes); h.event_record(3)
-        h2d_ms.append(h.event_elapsed_ms(2, 3))
-    pcie_gbs = nbytes / (min(h2d_ms) * 1e-3) / 1e9
-    pcie_concurrent = None
-    if world > 1:                                                         # all ranks copying at once: what the host can feed
-        conc = []
-        for _ in range(2):
-            barrier()
-            h.event_record(2); h.memcpy(d_in, pin, nbytes); h.event_record(3)
-            conc.append(allmax(h.event_elapsed_ms(2, 3)))
-        pcie_concurrent = nbytes / (min(conc) * 1e-3) / 1e9
+
+    def pcie(kind, up=256 << 20, down=0):
+        """In-run PCIe roofline: plain pinned copies by the library's probe; with all ranks at once when N > 1 (max over ranks)."""
+        alone = h.probe_pcie(kind, up, down, 3)
+        if world == 1:
+            return alone, None
+        barrier()
+        together = h.probe_pcie(kind, up, down, 3)
+        barrier()
+        return alone, tuple(-allmax(-g) for g in together)                # the slowest rank's rate
+
+    (h2d_gbs, _), h2d_conc = pcie(pg.PCIE_H2D)
     sums = []
 
     def e2e_step():
@@ -420,32 +554,59 @@ def ours(args):
     assert sums[0] == (h.checksum(d_i32, ns * 2), h.checksum(d_f32, ns * 2)), "overlapped checksum differs from the whole-output checksum"
     h2d_per_step = (s1["h2d_bytes"] - s0["h2d_bytes"]) // (e2e_steps + 2)
     e2e_val = total_samples / (ms_e2e * 1e-3) / 1e6
+    e2e_gbs = 6 * ns / (ms_e2e * 1e-3) / 1e9
     e2e = {"value": round(e2e_val, 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d_per_step), "d2h_bytes_per_step": 16,
            "ms_per_step": round(ms_e2e, 3), "steps": e2e_steps,
-           "what": "perseus_gpu_unpack(pinned host wire -> device int32+float, PERSEUS_GPU_CHECKSUM): H2D in chunks overlapped with the "
-                   "unpack and checksum kernels, then the checksums of both outputs read back (outputs stay in HBM, as north_star's "
-                   "end-to-end mode specifies)",
-           "h2d_gbs_per_gpu": round(6 * ns / (ms_e2e * 1e-3) / 1e9, 2), "pcie_h2d_gbs_measured": round(pcie_gbs, 2),
-           "frac_of_measured_pcie": round(6 * ns / (ms_e2e * 1e-3) / 1e9 / pcie_gbs, 4),
-           "frac_of_gen5_x16_theory": round(6 * ns / (ms_e2e * 1e-3) / 1e9 / PCIE_GEN5_X16_GBS, 4),
+           "what": "perseus_gpu_unpack(pinned host wire -> device int32+float, PERSEUS_GPU_CHECKSUM): H2D in chunks on the copy-in stream, "
+                   "unpack and checksum kernels behind them on the launch stream, then the checksums of both outputs read back (outputs stay "
+                   "in HBM, as north_star's end-to-end mode specifies)",
+           "h2d_gbs_per_gpu": round(e2e_gbs, 2), "pcie_h2d_gbs_measured": round(h2d_gbs, 2),
+           "frac_of_measured_pcie": round(e2e_gbs / h2d_gbs, 4),
+           "frac_of_gen5_x16_theory": round(e2e_gbs / PCIE_GEN5_X16_GBS, 4),
            "pinned_memory": "write-combined" if args.pinned_wc else "default (cudaHostAlloc portable)"}
-    if pcie_concurrent:
-        e2e["pcie_h2d_gbs_all_ranks_at_once"] = round(pcie_concurrent, 2)
-        e2e["frac_of_concurrent_pcie"] = round(6 * ns / (ms_e2e * 1e-3) / 1e9 / pcie_concurrent, 4)
+    if h2d_conc:
+        e2e["pcie_h2d_gbs_all_ranks_at_once"] = round(h2d_conc[0], 2)
+        e2e["frac_of_concurrent_pcie"] = round(e2e_gbs / h2d_conc[0], 4)
 
     e2e_rt = None
     if not args.no_roundtrip:
         po_i, po_f = h.host_alloc(ns * 8), h.host_alloc(ns * 8)
         rt_steps = max(2, min(e2e_steps, 5))
+        (_, d2h_gbs), d2h_conc = pcie(pg.PCIE_D2H)
+        # plain copies of the round trip's own traffic mix, both directions at once: 6 B up per 16 B (fused) / 8 B (one format) down
+        (dup16_up, dup16_down), dup16_conc = pcie(pg.PCIE_DUPLEX, 96 << 20, 256 << 20)
+        (dup8_up, dup8_down), _ = pcie(pg.PCIE_DUPLEX, 192 << 20, 256 << 20)
+
+        def copy_bound_ms(up_gbs, down_gbs, down_bytes_per_sample):
+            return max(6 * ns / (up_gbs * 1e9), down_bytes_per_sample * ns / (down_gbs * 1e9)) * 1e3
+
         s0 = h.stats()
         ms_rt = timed(lambda: h.unpack(pin, nbytes, po_i, po_f, FUSED), rt_steps, 1)
         s1 = h.stats()
         tail = np.ctypeslib.as_array((C.c_uint32 * 2048).from_address(po_f + ns * 8 - 8192))
         assert np.array_equal(tail, h.to_host(d_f32 + ns * 8 - 8192, 8192, np.uint32)), "round-trip output differs"
+        ms_rt1 = timed(lambda: h.unpack(pin, nbytes, None, po_f, pg.OUT_FLOAT), rt_steps, 1)
+        d2h_rate = 16 * ns / (ms_rt * 1e-3) / 1e9
         e2e_rt = {"value": round(total_samples / (ms_rt * 1e-3) / 1e6, 1), "unit": UNIT, "ms_per_step": round(ms_rt, 3),
                   "h2d_bytes_per_step": int((s1["h2d_bytes"] - s0["h2d_bytes"]) // (rt_steps + 1)),
                   "d2h_bytes_per_step": int((s1["d2h_bytes"] - s0["d2h_bytes"]) // (rt_steps + 1)),
-                  "what": "same call with pinned HOST outputs: both formats copied back (16 B/sample D2H, full duplex with the H2D)"}
+                  "what": "same call with pinned HOST outputs: both formats copied back (16 B/sample D2H, full duplex with the 6 B/sample H2D); "
+                          "copy-in, kernels and copy-out each on their own stream, three staging slots",
+                  "d2h_gbs_per_gpu": round(d2h_rate, 2), "pcie_d2h_gbs_measured": round(d2h_gbs, 2),
+                  "frac_of_d2h_peak": round(d2h_rate / d2h_gbs, 4),
+                  "duplex_plain_copies_gbs": {"h2d": round(dup16_up, 2), "d2h": round(dup16_down, 2),
+                                              "what": "plain pinned copies, 6 B up per 16 B down, both directions at once (perseus_gpu_probe_pcie)"},
+                  "frac_of_duplex_copy_bound": round(copy_bound_ms(dup16_up, dup16_down, 16) / ms_rt, 4),
+                  "single_format": {"value": round(total_samples / (ms_rt1 * 1e-3) / 1e6, 1), "ms_per_step": round(ms_rt1, 3),
+                                    "d2h_gbs_per_gpu": round(8 * ns / (ms_rt1 * 1e-3) / 1e9, 2),
+                                    "frac_of_d2h_peak": round(8 * ns / (ms_rt1 * 1e-3) / 1e9 / d2h_gbs, 4),
+                                    "frac_of_duplex_copy_bound": round(copy_bound_ms(dup8_up, dup8_down, 8) / ms_rt1, 4),
+                                    "what": "float only: 8 B/sample D2H against 6 B/sample H2D"}}
+        if d2h_conc:
+            e2e_rt["pcie_d2h_gbs_all_ranks_at_once"] = round(d2h_conc[1], 2)
+            e2e_rt["frac_of_concurrent_d2h"] = round(d2h_rate / d2h_conc[1], 4)
+            e2e_rt["duplex_plain_copies_gbs_all_ranks_at_once"] = {"h2d": round(dup16_conc[0], 2), "d2h": round(dup16_conc[1], 2)}
+            e2e_rt["frac_of_concurrent_duplex_copy_bound"] = round(copy_bound_ms(dup16_conc[0], dup16_conc[1], 16) / ms_rt, 4)
         h.host_free(po_i); h.host_free(po_f)
     if wc_rt is not None:
         wc_rt.cudaFreeHost(C.c_void_p(pin))
@@ -485,15 +646,20 @@ def ours(args):
         e2e_cb["one_transfer_latency_us"] = {"median": round(statistics.median(lat), 1), "p95": round(sorted(lat)[189], 1),
                                              "what": "wall time of perseus_gpu_input_callback(6144 B) + perseus_gpu_flush: samples resident on the device"}
 
+    for p in (d_in, d_i32, d_f32):
+        h.dev_free(p)
+
+    # -- BASELINE.json's other GPU configurations, in the same driver-run line
+    workloads = None
+    if not args.no_workloads:
+        wsteps = max(3, min(args.steps, 20))
+        workloads = {"cfg3": workload_cfg3(cx, wsteps, 3), "cfg4": workload_cfg4(cx, max(3, min(args.steps, 10)), 3)}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline_leg(args.cpu_budget_s)
 
-    for p in (d_in, d_i32, d_f32):
-        h.dev_free(p)
-    h.close()
-    if world > 1:
-        dist.destroy_process_group()
+    cx.close()
     if rank != 0:
         return 0
 
@@ -501,12 +667,12 @@ def ours(args):
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32+f32", "data": "synthetic",
-        "config": {"workload": f"cfg2: perseus2m24v21 (2 MS/s) layout, {nbuf} transfers x {BUF} B = {nbytes} wire bytes per GPU "
-                               f"({ns} complex samples), unpacked to int32 AND float in one fused pass; rank r owns transfers "
-                               f"[r*{nbuf},(r+1)*{nbuf}) of the {world}x recording (perseus_gpu_shard_range)",
-                   "l2": "no flush needed: inputs (1.07 GB) and outputs (2.86 GB) per step are far larger than the 126 MB L2",
-                   "generator": "splitmix64(seed + word index), seed 0x5045525345555300, generated on the device",
-                   "parallelism": f"{world} independent shard(s), no data-path collective", "tuning": tuning, "numa_node": numa},
+        "config": workload_config(world, nbuf),
+        "setup": {"l2": "no flush needed: inputs (1.07 GB) and outputs (2.86 GB) per step are far larger than the 126 MB L2",
+                  "generated": "on the device (perseus_gpu_generate), rank r at byte offset r * shard size of the recording",
+                  "pass": "int32 AND float written by one fused kernel launch per step",
+                  "parallelism": f"{world} independent shard(s) (perseus_gpu_shard_range), no data-path collective", "tuning": tuning,
+                  "numa_node": cx.numa},
         "roofline": {"bound": "hbm", "kernel": "unpack24_stream_kernel<I32|F32>", "achieved": round(achieved, 1), "peak": peak,
                      "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": BYTES_PER_SAMPLE_FUSED * ns, "bytes_per_sample": BYTES_PER_SAMPLE_FUSED,
@@ -521,120 +687,24 @@ def ours(args):
         line["e2e_roundtrip"] = e2e_rt
     if e2e_cb:
         line["e2e_callback"] = e2e_cb
+    if workloads:
+        line["workloads"] = workloads
     if cpu:
         line["cpu_baseline"] = cpu
     emit(line)
     return 0
 
 
-def dist_setup():
-    import torch
-    import torch.distributed as dist
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    return rank, world, local
-
-
-def timed_region(h, fn, steps, warmup, world, sampler=None):
-    """W untimed steps, then exactly K steps between barrier+sync, CUDA events on the launching stream, max over ranks."""
-    import importlib
-    import torch
-    import torch.distributed as dist
-    sharding = importlib.import_module("libperseus_sdr_b200.sharding")
-    for _ in range(warmup):
-        fn()
-    h.sync(); torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    with (sampler if sampler is not None else _Null()):
-        h.event_record(0)
-        for _ in range(steps):
-            fn()
-        h.event_record(1)
-        h.sync(); torch.cuda.synchronize()
-        ms = h.event_elapsed_ms(0, 1)
-    if world > 1:
-        dist.barrier()
-    return sharding.allreduce_max(ms) / steps
-
-
-def mixed_rate_buffers(nrx=1024, window_s=1.024):
-    rates = [48000, 96000, 192000, 500000, 1000000, 2000000]          # SURVEY.md §8d cfg3
-    return [max(1, round(rates[r % 6] * window_s / 1024)) for r in range(nrx)]
-
-
 def other_workload(args):
-    """cfg3 / cfg4 of BASELINE.json: kernel-only lines with the same schema (no e2e legs)."""
-    import torch.distributed as dist
-    import __graft_entry__ as G
-    rank, world, local = dist_setup()
-    if local == 0:
-        G.ensure_built()
-    if world > 1:
-        dist.barrier()
-    pg = G.load_package()
-    h = pg.PerseusGpu(device=local)
-    peak, peak_src = measured_peak()
-    sampler = ClockSampler(local)
-    if args.workload == "cfg3":
-        nbufs = mixed_rate_buffers()
-        total_in = sum(nbufs) * BUF
-        ns = total_in // 6
-        d_in, d_i, d_f = h.dev_alloc(total_in), h.dev_alloc(ns * 8), h.dev_alloc(ns * 8)
-        segs, off = [], 0
-        for r, b in enumerate(nbufs):
-            h.generate(d_in + off, b * BUF, pg.SYNTH_RANDOM, pg.SYNTH_SEED + r, 0)
-            segs.append((d_in + off, b * BUF, d_i + off // 6 * 8, d_f + off // 6 * 8))
-            off += b * BUF
-        flags = pg.OUT_INT32 | pg.OUT_FLOAT
-        plan = h.plan_create(segs, flags)
-        h.plan_run(plan)
-        bad, _ = h.verify(d_in, total_in, d_i, d_f, flags)
-        assert bad == 0, bad
-        l0 = h.stats()["kernel_launches"]
-        ms = timed_region(h, lambda: h.plan_run(plan, pg.ASYNC), args.steps, args.warmup, world, sampler)
-        launches = h.stats()["kernel_launches"] - l0 - args.warmup
-        h.plan_destroy(plan)
-        bps, scaling = BYTES_PER_SAMPLE_FUSED, "weak"
-        samples_all = ns * world
-        workload = (f"cfg3: 1024 virtual receivers at 48k/96k/192k/500k/1M/2M S/s, 1.024 s window = {sum(nbufs)} transfers x {BUF} B "
-                    f"({total_in} wire bytes) per GPU, own seed per receiver, unpacked to int32 AND float in ONE launch")
-        kernel = "unpack24_stream_kernel<I32|F32, batched>"
-    else:
-        total_buffers = 11_184_810                                    # 64 GiB of 6144-byte transfers, SURVEY.md §8d cfg4
-        first, count = pg.shard_range(total_buffers, world, rank)
-        nbytes = count * BUF
-        ns = nbytes // 6
-        d_in, d_i, d_f = h.dev_alloc(nbytes), None, h.dev_alloc(ns * 8)
-        h.generate(d_in, nbytes, pg.SYNTH_RANDOM, pg.SYNTH_SEED, first * BUF)
-        flags = pg.OUT_FLOAT
-        h.unpack(d_in, nbytes, None, d_f, flags)
-        bad, _ = h.verify(d_in, nbytes, None, d_f, flags)
-        assert bad == 0, bad
-        l0 = h.stats()["kernel_launches"]
-        ms = timed_region(h, lambda: h.unpack(d_in, nbytes, None, d_f, flags | pg.ASYNC), args.steps, args.warmup, world, sampler)
-        launches = h.stats()["kernel_launches"] - l0 - args.warmup
-        bps, scaling = BYTES_PER_SAMPLE_SINGLE, "strong"
-        samples_all = total_buffers * 1024
-        workload = (f"cfg4: 64 GiB recording ({total_buffers} transfers x {BUF} B) sharded by contiguous transfer range over {world} GPU(s), "
-                    f"this rank {count} transfers; generated on the device; float output; kernel-only")
-        kernel = "unpack24_stream_kernel<F32>"
-    achieved = bps * ns / (ms * 1e-3) / 1e9
-    if world > 1:
-        dist.destroy_process_group()
-    if rank == 0:
-        emit({
-            "metric": METRIC, "value": round(samples_all / (ms * 1e-3) / 1e6, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
-            "dtype": "int32+f32" if bps == BYTES_PER_SAMPLE_FUSED else "f32", "data": "synthetic",
-            "config": {"workload": workload, "l2": "no flush needed: working set per step is far larger than the 126 MB L2"},
-            "roofline": {"bound": "hbm", "kernel": kernel, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src, "bytes_per_sample": bps},
-            "e2e": None, "gpu_launches": int(launches), "clocks": sampler.summary()})
+    """--workload cfg3 / cfg4 alone: the sub-record of the default run as the whole line (e2e: null)."""
+    cx = Ctx(args)
+    rec = (workload_cfg3 if args.workload == "cfg3" else workload_cfg4)(cx, args.steps, args.warmup)
+    cx.close()
+    if cx.rank == 0:
+        rec.update({"higher_is_better": True, "vs_baseline": None, "data": "synthetic", "e2e": None})
+        rec.setdefault("roofline", {}).update({"traffic": None, "peak_source": cx.peak_src})
+        rec.setdefault("config", {})["l2"] = "no flush needed: working set per step is far larger than the 126 MB L2"
+        emit(rec)
     return 0
 
 
@@ -655,7 +725,8 @@ def main():
     ap.add_argument("--buffers", type=int, default=CFG2_BUFFERS, help="transfers per GPU (default: cfg2, 1 GiB)")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--chunk-mib", type=int, default=0, help="staging chunk for host pointers (0 = library default, 32 MiB)")
-    ap.add_argument("--streams", type=int, default=0, help="CUDA streams per handle (0 = library default, 2)")
+    ap.add_argument("--slots", type=int, default=0, help="staging slots of the host-pointer pipeline (0 = library default, 3)")
+    ap.add_argument("--no-workloads", action="store_true", help="skip the cfg3 / cfg4 sub-records")
     ap.add_argument("--no-roundtrip", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-callback", action="store_true")

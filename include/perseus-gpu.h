@@ -14,14 +14,22 @@
  * Plain C ABI: opaque handles, pointers and sizes only.  No CUDA or C++ types appear
  * in any signature, so the header can be bound from C, cgo, ctypes, JNI...
  * It deliberately does NOT include perseus-sdr.h (which drags in <libusb-1.0/libusb.h>,
- * perseus-sdr.h:35); the one shared type, perseus_input_callback, is re-declared
- * below under the reference's own include guard.
+ * perseus-sdr.h:35) and re-declares none of its names, so the two headers can be included
+ * in either order; the one shared type, perseus_input_callback (perseus-sdr.h:81), appears
+ * here under the library's own name perseus_gpu_input_fn (identical signature).
  *
  * Conventions mirror the reference (perseus-sdr.h:317-366): functions return 0 (or a
  * non-negative count) on success and a negative code on failure; a human-readable
  * message for the calling thread's last failure is returned by perseus_gpu_errorstr().
  * There is NO CPU fallback: every entry point that computes fails with
  * PERSEUS_GPU_NODEVICE / PERSEUS_GPU_BADARCH when no sm_100 device is usable.
+ *
+ * Threads: a handle is a monitor -- every entry point takes the handle's lock, so the callback
+ * thread, the application thread and the library's own latency watchdog may touch the same
+ * handle; they serialise.  The lock is recursive: a sink may call the synchronous plumbing
+ * (sync, memcpy, get_stats) of its own handle, but not flush/close/unpack.  Every entry
+ * point that takes a handle leaves the CALLING thread's current CUDA device set to the
+ * handle's device (cudaSetDevice, not restored).
  *
  * Wire format (perseustest.c:434,450-455): 6 bytes per complex sample,
  *     I0 I1 I2 Q0 Q1 Q2      (24-bit little-endian two's complement I, then Q)
@@ -41,12 +49,11 @@
 extern "C" {
 #endif
 
-#define PERSEUS_GPU_ABI_VERSION 1
+#define PERSEUS_GPU_ABI_VERSION 2
 
-/* perseus-sdr.h:81 — identical typedef; skipped when perseus-sdr.h was included first. */
-#ifndef _perseus_sdr_h
-typedef int (*perseus_input_callback)(void *buf, int buf_size, void *extra);
-#endif
+/* Same signature as perseus_input_callback (perseus-sdr.h:81): a pointer of either type converts to the
+ * other without a cast.  Declared under its own name so this header never collides with perseus-sdr.h. */
+typedef int (*perseus_gpu_input_fn)(void *buf, int buf_size, void *extra);
 
 typedef struct perseus_gpu perseus_gpu;               /* one per (device, receiver stream) */
 typedef struct perseus_gpu_plan perseus_gpu_plan;     /* a reusable batched-launch layout  */
@@ -98,7 +105,7 @@ typedef struct perseus_gpu_config {
 	uint32_t stream_flags;    /* PERSEUS_GPU_OUT_* produced by the callback (streaming) path; 0 = INT32 */
 	uint32_t nslabs;          /* pinned slabs in the hand-off ring, >= 2          (0 = 4)       */
 	uint64_t slab_bytes;      /* bytes per slab, rounded down to a multiple of 48 (0 = 8 MiB)   */
-	uint32_t nstreams;        /* CUDA streams used for copy/compute overlap, 1..8 (0 = 2)       */
+	uint32_t nstreams;        /* CUDA streams the streaming path rotates its slabs over, 1..8 (0 = 2) */
 	uint32_t max_latency_us;  /* streaming path: a partly filled slab is submitted once its oldest transfer has
 	                             waited this long, checked at every callback (0 = 50 000 us; 0xFFFFFFFF = only
 	                             when full).  At 95 kS/s a transfer arrives every 10.8 ms, so slabs are
@@ -106,7 +113,14 @@ typedef struct perseus_gpu_config {
 	uint64_t chunk_bytes;     /* host<->device staging chunk for perseus_gpu_unpack with host
 	                             pointers, rounded down to a multiple of 48       (0 = 32 MiB)  */
 	perseus_gpu_tuning tuning;
+	uint32_t options;         /* PERSEUS_GPU_OPT_*                                              */
+	uint32_t stage_slots;     /* staging slots of the host-pointer pipeline, 2..8   (0 = 3): chunk c is copied in while
+	                             chunk c-1 is unpacked and chunk c-2 is copied out, each on its own stream */
+	uint32_t reserved[2];
 } perseus_gpu_config;
+
+/* perseus_gpu_config.options */
+#define PERSEUS_GPU_OPT_NO_WATCHDOG 0x0001u  /* do not start the latency watchdog thread (see perseus_gpu_poll) */
 
 /* ---- life cycle (names fixed by BASELINE.json north_star) ------------------------------ */
 
@@ -127,8 +141,9 @@ int perseus_gpu_close(perseus_gpu *h);
  *            device in cfg->chunk_bytes pieces with copies and kernels overlapped.
  *   flags    PERSEUS_GPU_OUT_* | PERSEUS_GPU_ASYNC, or 0.
  * Returns the number of complex samples produced (>= 0) or a negative error.
- * Any alignment is accepted.  The wire pointer never matters for speed; output pointers that are 16-byte aligned
- * (any cudaMalloc'd buffer) take the fast path, others a slower register-only kernel. */
+ * The wire pointer may have ANY alignment and never matters for speed.  Output pointers must be 4-byte aligned
+ * (PERSEUS_GPU_ERRPARAM otherwise; they hold int32 / float); those that are 16-byte aligned (any cudaMalloc'd
+ * buffer) take the fast path, others a slower register-only kernel. */
 int64_t perseus_gpu_unpack(perseus_gpu *h, const void *buf, size_t nbytes,
                            void *out_i32, void *out_f32, unsigned flags);
 
@@ -158,18 +173,31 @@ int     perseus_gpu_plan_destroy(perseus_gpu *h, perseus_gpu_plan *plan);
 
 /* ---- streaming hand-off: the drop-in for the reference's user callback -------------------
  *
- * perseus_gpu_input_callback has the type perseus_input_callback (perseus-sdr.h:81) with
+ * perseus_gpu_input_callback has the signature of perseus_input_callback (perseus-sdr.h:81) with
  * extra = perseus_gpu*, so existing code does
  *     perseus_start_async_input(descr, 6144, perseus_gpu_input_callback, h);
  * It copies buf (valid only during the call: the transfer is resubmitted right after,
  * perseus-in.c:263) into the current pinned slab; a full slab is sent H2D and unpacked on
  * one of the handle's streams while the next slab fills.  Never blocks on the GPU except
- * for back-pressure when every slab is in flight (counted in perseus_gpu_stats.stalls).
- * Always returns 0, like the reference's callbacks (perseustest.c:459,501). */
+ * for back-pressure when every slab is in flight (counted in perseus_gpu_stats.stalls; the
+ * wait sleeps, it does not spin: the reference calls this on a SCHED_FIFO thread,
+ * perseus-sdr.c:749-753).  Always returns 0, like the reference's callbacks
+ * (perseustest.c:459,501); after an error has been latched, further transfers are counted
+ * in perseus_gpu_stats.dropped_callbacks / dropped_bytes until flush/sync/close reports it. */
 int perseus_gpu_input_callback(void *buf, int buf_size, void *extra);
 
+/* Latency bound without a following callback.  A partly filled slab is submitted once its oldest
+ * transfer has waited cfg.max_latency_us.  That is checked at every callback and, because a stream
+ * can stall (USB error, the last transfers before perseus_stop_async_input), also by a small
+ * watchdog thread the handle starts with its first callback (period = max_latency_us / 4,
+ * PERSEUS_GPU_OPT_NO_WATCHDOG disables it).  Applications that prefer to drive it themselves call
+ * perseus_gpu_poll() from any thread: it submits the partial slab if it is over age and returns the
+ * number of slabs it submitted (0 or 1), or a negative error. */
+int perseus_gpu_poll(perseus_gpu *h);
+
 /* A block of unpacked samples resident in device memory.  Passed to the sink on the thread
- * that called the callback/flush, right after the unpack kernel was ENQUEUED on `stream`
+ * that submitted the slab (the callback thread, the caller of flush/poll, or the watchdog),
+ * under the handle's lock, right after the unpack kernel was ENQUEUED on `stream`
  * (a cudaStream_t): work the sink enqueues on that stream runs after the unpack and before
  * the block's memory is reused. */
 typedef struct perseus_gpu_block {
@@ -201,7 +229,10 @@ typedef struct perseus_gpu_stats {
 	uint64_t callbacks;         /* perseus_gpu_input_callback invocations              */
 	uint64_t slabs;             /* slabs submitted by the streaming path               */
 	uint64_t stalls;            /* times the callback had to wait for a free slab      */
-	uint64_t reserved[4];
+	uint64_t dropped_callbacks; /* callbacks ignored because an error was latched      */
+	uint64_t dropped_bytes;     /* wire bytes of those callbacks                       */
+	uint64_t watchdog_submits;  /* partial slabs submitted by the watchdog / poll      */
+	uint64_t reserved[1];
 } perseus_gpu_stats;
 int perseus_gpu_get_stats(perseus_gpu *h, perseus_gpu_stats *out);
 
@@ -233,7 +264,8 @@ int   perseus_gpu_memcpy(perseus_gpu *h, void *dst, const void *src, size_t nbyt
 int   perseus_gpu_memset(perseus_gpu *h, void *dev, int byte, size_t nbytes);
 void *perseus_gpu_get_stream(perseus_gpu *h, int idx);               /* cudaStream_t idx of the handle */
 /* Timing on the stream the kernels are launched on: records event slot `slot` (0..31) on
- * stream 0 of the handle; elapsed time between two recorded slots in milliseconds. */
+ * stream 0 of the handle; elapsed time between two recorded slots in milliseconds.  All 32
+ * slots belong to the caller (autotune and the probes time with private events). */
 int   perseus_gpu_event_record(perseus_gpu *h, int slot);
 int   perseus_gpu_event_elapsed_ms(perseus_gpu *h, int slot_start, int slot_stop, float *ms);
 
@@ -267,6 +299,16 @@ int perseus_gpu_verify(perseus_gpu *h, const void *dev_in, size_t nbytes, const 
 #define PERSEUS_GPU_PROBE_COPY  2
 int perseus_gpu_probe_hbm(perseus_gpu *h, int kind, size_t nbytes, int reps, double *gbs);
 
+/* ---- in-run PCIe roofline: plain pinned-memory copies, best of `reps` ---------------------------------------
+ * kind H2D: nbytes host->device alone; D2H: d2h_nbytes device->host alone; DUPLEX: both queued at once on two
+ * streams -- each direction's rate over its own copy, so with d2h_nbytes = nbytes/6*16 (the fused round trip's
+ * mix) max(nbytes/h2d, d2h_nbytes/d2h) is what plain copies need for that traffic.  d2h_nbytes 0 = nbytes.
+ * *h2d_gbs / *d2h_gbs receive GB/s (0 for a direction not run). */
+#define PERSEUS_GPU_PCIE_H2D    0
+#define PERSEUS_GPU_PCIE_D2H    1
+#define PERSEUS_GPU_PCIE_DUPLEX 2
+int perseus_gpu_probe_pcie(perseus_gpu *h, int kind, size_t nbytes, size_t d2h_nbytes, int reps, double *h2d_gbs, double *d2h_gbs);
+
 /* ---- multi-GPU sharding: contiguous ranges of whole transfers, no exchange --- */
 /* Shard `shard` of `nshards` of a recording of `total_buffers` transfers gets
  * [*first, *first + *count) with first = floor(shard*total/nshards). */
@@ -292,8 +334,21 @@ typedef struct perseus_vrx_config {
 	uint32_t swap_every;       /* every Nth transfer completes out of sequence -> not delivered */
 	uint32_t replay;           /* non-zero: generate only the first 8 transfers and re-deliver the ring's contents
 	                              (stream repeats every 8 transfers): isolates the hand-off cost in benchmarks */
-	uint32_t reserved[4];
+	/* transfer statuses other than COMPLETED (perseus-in.c:218-257) */
+	uint32_t timeout_every;    /* every Nth transfer completes TIMED_OUT: nothing delivered or counted, slot re-armed */
+	uint32_t fail_at;          /* the Nth transfer (1-based; 0 = never) completes with fail_status: its slot is retired */
+	uint32_t fail_status;      /* PERSEUS_VRX_STATUS_*: ERROR, STALL, NO_DEVICE or OVERFLOW                             */
+	uint32_t reserved[1];
 } perseus_vrx_config;
+
+/* libusb transfer statuses the reference's completion handler distinguishes (values = enum libusb_transfer_status) */
+#define PERSEUS_VRX_STATUS_COMPLETED 0
+#define PERSEUS_VRX_STATUS_ERROR     1
+#define PERSEUS_VRX_STATUS_TIMED_OUT 2
+#define PERSEUS_VRX_STATUS_CANCELLED 3
+#define PERSEUS_VRX_STATUS_STALL     4
+#define PERSEUS_VRX_STATUS_NO_DEVICE 5
+#define PERSEUS_VRX_STATUS_OVERFLOW  6
 
 typedef struct perseus_vrx_stats {        /* cf. perseus-sdr.c:719-722 */
 	uint64_t bytes_received;   /* counts every completed transfer, delivered or not (perseus-in.c:202) */
@@ -302,6 +357,8 @@ typedef struct perseus_vrx_stats {        /* cf. perseus-sdr.c:719-722 */
 	uint64_t dropped_sequence; /* perseus-in.c:213-216                             */
 	double   elapsed_s;
 	double   ksamples_per_s;   /* bytes_received / elapsed / 6000, as the reference prints it */
+	uint64_t timed_out;        /* perseus-in.c:218-221: logged, slot re-armed                 */
+	uint64_t retired;          /* perseus-in.c:222-257: slots taken out of the ring for good  */
 } perseus_vrx_stats;
 
 int perseus_vrx_open(perseus_vrx **v, const perseus_vrx_config *cfg);
@@ -318,11 +375,11 @@ const char *perseus_vrx_bitstream_name(int rate);
 /* Same validation and error codes as perseus_start_async_input (perseus-sdr.c:638-692):
  * buffersize <= 16320 and a multiple of 6144 (EP 512) / 510 (EP 510).  Starts a delivery
  * thread.  stop cancels, joins, and fills the statistics. */
-int perseus_vrx_start_async_input(perseus_vrx *v, uint32_t buffersize, perseus_input_callback callback, void *cb_extra);
+int perseus_vrx_start_async_input(perseus_vrx *v, uint32_t buffersize, perseus_gpu_input_fn callback, void *cb_extra);
 int perseus_vrx_stop_async_input(perseus_vrx *v);
 /* Synchronous variant for benchmarks and tests: delivers exactly `ntransfers` completed
  * transfers on the calling thread (dropped ones count), then returns. */
-int perseus_vrx_run(perseus_vrx *v, uint32_t buffersize, perseus_input_callback callback, void *cb_extra,
+int perseus_vrx_run(perseus_vrx *v, uint32_t buffersize, perseus_gpu_input_fn callback, void *cb_extra,
                     uint64_t ntransfers);
 int perseus_vrx_get_stats(perseus_vrx *v, perseus_vrx_stats *out);
 

@@ -26,6 +26,10 @@ SYNTH_SEED = 0x5045525345555300
 ERR = {"NOERROR": 0, "NULLHANDLE": -2, "IOERROR": -13, "ASYNCSTARTED": -19, "NOMEM": -20, "ERRPARAM": -22,
        "BUFFERSIZE": -24, "CUDAERR": -40, "NODEVICE": -41, "BADARCH": -42, "MISMATCH": -43}
 VRX_QUEUE_SIZE, VRX_MAX_BUFFER = 8, 16320
+OPT_NO_WATCHDOG = 0x1
+PCIE_H2D, PCIE_D2H, PCIE_DUPLEX = 0, 1, 2
+# enum libusb_transfer_status values, PERSEUS_VRX_STATUS_*
+STATUS = {"COMPLETED": 0, "ERROR": 1, "TIMED_OUT": 2, "CANCELLED": 3, "STALL": 4, "NO_DEVICE": 5, "OVERFLOW": 6}
 
 INPUT_CALLBACK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p)   # perseus-sdr.h:81
 
@@ -45,7 +49,7 @@ class Tuning(C.Structure):
 class Config(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("stream_flags", C.c_uint32), ("nslabs", C.c_uint32),
                 ("slab_bytes", C.c_uint64), ("nstreams", C.c_uint32), ("max_latency_us", C.c_uint32), ("chunk_bytes", C.c_uint64),
-                ("tuning", Tuning)]
+                ("tuning", Tuning), ("options", C.c_uint32), ("stage_slots", C.c_uint32), ("reserved", C.c_uint32 * 2)]
 
 
 class Seg(C.Structure):
@@ -62,7 +66,8 @@ SINK = C.CFUNCTYPE(None, C.POINTER(Block), C.c_void_p)
 
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("kernel_launches", "samples", "bytes_in", "h2d_bytes", "d2h_bytes", "callbacks",
-                                          "slabs", "stalls")] + [("reserved", C.c_uint64 * 4)]
+                                          "slabs", "stalls", "dropped_callbacks", "dropped_bytes", "watchdog_submits")] + \
+               [("reserved", C.c_uint64 * 1)]
 
     def asdict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_[:-1]}
@@ -71,12 +76,14 @@ class Stats(C.Structure):
 class VrxConfig(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("sample_rate", C.c_int32), ("ep_max_packet", C.c_int32), ("pattern", C.c_int32),
                 ("seed", C.c_uint64), ("realtime", C.c_int32), ("drop_every", C.c_uint32), ("swap_every", C.c_uint32),
-                ("replay", C.c_uint32), ("reserved", C.c_uint32 * 4)]
+                ("replay", C.c_uint32), ("timeout_every", C.c_uint32), ("fail_at", C.c_uint32), ("fail_status", C.c_uint32),
+                ("reserved", C.c_uint32 * 1)]
 
 
 class VrxStats(C.Structure):
     _fields_ = [("bytes_received", C.c_uint64), ("delivered", C.c_uint64), ("dropped_short", C.c_uint64),
-                ("dropped_sequence", C.c_uint64), ("elapsed_s", C.c_double), ("ksamples_per_s", C.c_double)]
+                ("dropped_sequence", C.c_uint64), ("elapsed_s", C.c_double), ("ksamples_per_s", C.c_double),
+                ("timed_out", C.c_uint64), ("retired", C.c_uint64)]
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -116,6 +123,7 @@ def lib() -> C.CDLL:
         "perseus_gpu_set_sink": (ci, [vp, SINK, vp]),
         "perseus_gpu_stream_to_file": (ci, [vp, C.c_char_p]),
         "perseus_gpu_flush": (ci, [vp]),
+        "perseus_gpu_poll": (ci, [vp]),
         "perseus_gpu_get_stats": (ci, [vp, P(Stats)]),
         "perseus_gpu_autotune": (ci, [vp, P(C.c_double), P(C.c_double)]),
         "perseus_gpu_get_geometry": (ci, [vp, C.c_uint, P(ci), P(ci), P(ci)]),
@@ -140,6 +148,7 @@ def lib() -> C.CDLL:
         "perseus_gpu_verify": (ci, [vp, vp, sz, vp, vp, C.c_uint, P(u64), P(u64)]),
         "perseus_gpu_shard_range": (ci, [u64, ci, ci, P(u64), P(u64)]),
         "perseus_gpu_probe_hbm": (ci, [vp, ci, sz, ci, P(C.c_double)]),
+        "perseus_gpu_probe_pcie": (ci, [vp, ci, sz, sz, ci, P(C.c_double), P(C.c_double)]),
         "perseus_vrx_open": (ci, [P(vp), P(VrxConfig)]),
         "perseus_vrx_close": (ci, [vp]),
         "perseus_vrx_get_sampling_rates": (ci, [P(ci), C.c_uint]),
@@ -201,12 +210,13 @@ class PerseusGpu:
     """perseus_gpu handle.  Pointers are plain integers (device or host addresses)."""
 
     def __init__(self, device: int = 0, stream_flags: int = 0, nslabs: int = 0, slab_bytes: int = 0, nstreams: int = 0,
-                 chunk_bytes: int = 0, max_latency_us: int = 0, **tuning):
+                 chunk_bytes: int = 0, max_latency_us: int = 0, options: int = 0, stage_slots: int = 0, **tuning):
         L = lib()
         cfg = Config()
         cfg.struct_size = C.sizeof(Config)
         cfg.device, cfg.stream_flags, cfg.nslabs, cfg.slab_bytes = device, stream_flags, nslabs, slab_bytes
         cfg.nstreams, cfg.chunk_bytes, cfg.max_latency_us = nstreams, chunk_bytes, max_latency_us
+        cfg.options, cfg.stage_slots = options, stage_slots
         for k, v in tuning.items():
             setattr(cfg.tuning, k, v)
         self.h = C.c_void_p()
@@ -273,6 +283,10 @@ class PerseusGpu:
 
     def flush(self) -> None:
         check(self.L.perseus_gpu_flush(self.h))
+
+    def poll(self) -> int:
+        """Submits the partial slab if it is over age; returns how many slabs that submitted (0 or 1)."""
+        return check(self.L.perseus_gpu_poll(self.h))
 
     def stats(self) -> dict:
         s = Stats()
@@ -351,6 +365,12 @@ class PerseusGpu:
         check(self.L.perseus_gpu_probe_hbm(self.h, kind, nbytes, reps, C.byref(g)))
         return g.value
 
+    def probe_pcie(self, kind: int, nbytes: int = 256 << 20, d2h_nbytes: int = 0, reps: int = 3) -> tuple[float, float]:
+        """(H2D GB/s, D2H GB/s) of plain pinned copies: one direction alone, or both at once (PCIE_DUPLEX)."""
+        a, b = C.c_double(), C.c_double()
+        check(self.L.perseus_gpu_probe_pcie(self.h, kind, nbytes, d2h_nbytes, reps, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def verify(self, dev_in: int, nbytes: int, dev_i32: int | None, dev_f32: int | None, flags: int = 0) -> tuple[int, int]:
         """Returns (mismatching words, first bad word); raises only on errors other than MISMATCH."""
         n, first = C.c_uint64(), C.c_uint64()
@@ -378,11 +398,13 @@ class VirtualReceiver:
     """perseus_vrx handle: the reference's transfer delivery (8-slot ring, in-order callbacks) over synthetic data."""
 
     def __init__(self, sample_rate: int = 95000, ep_max_packet: int = 0, pattern: int = SYNTH_RANDOM, seed: int = 0,
-                 realtime: bool = False, drop_every: int = 0, swap_every: int = 0, replay: bool = False):
+                 realtime: bool = False, drop_every: int = 0, swap_every: int = 0, replay: bool = False,
+                 timeout_every: int = 0, fail_at: int = 0, fail_status: int = 0):
         cfg = VrxConfig()
         cfg.struct_size = C.sizeof(VrxConfig)
         cfg.sample_rate, cfg.ep_max_packet, cfg.pattern, cfg.seed = sample_rate, ep_max_packet, pattern, seed
         cfg.realtime, cfg.drop_every, cfg.swap_every, cfg.replay = int(realtime), drop_every, swap_every, int(replay)
+        cfg.timeout_every, cfg.fail_at, cfg.fail_status = timeout_every, fail_at, fail_status
         self.v = C.c_void_p()
         self.L = lib()
         check(self.L.perseus_vrx_open(C.byref(self.v), C.byref(cfg)))

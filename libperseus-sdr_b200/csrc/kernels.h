@@ -5,6 +5,8 @@
 #include <cstddef>
 #include <cstdint>
 
+#include "host_common.h"
+
 namespace pg {
 
 // output-format bits, same values as PERSEUS_GPU_OUT_* in include/perseus-gpu.h
@@ -47,25 +49,25 @@ struct SegDesc { const uint8_t *in; uint64_t nbytes; void *out_i32; void *out_f3
 cudaError_t launch_unpack(const void *in, size_t nbytes, void *out_i32, void *out_f32, unsigned fmt,
                           const Tuning &t, int sm_count, cudaStream_t stream, int *launches);
 
-// Batched unpack over nseg segments described on the device; tile map built by the caller
-// with tile size `tile_bytes`.  `all_aligned` = every OUTPUT pointer is 16-byte aligned
-// (wire pointers may have any alignment).
-cudaError_t launch_unpack_batch(const SegDesc *d_segs, const TileRef *d_tiles, uint64_t ntiles, int tile_bytes, unsigned fmt,
-                                bool all_aligned, const Tuning &t, int sm_count, cudaStream_t stream, int *launches);
+// Batched unpack over segments described on the device; the caller built two tile maps with tile size
+// `tile_bytes`: `d_tiles_stream` lists the tiles of segments whose OUTPUT pointers are 16-byte aligned (wire
+// pointers may have any alignment) -- they go through the bulk-copy pipeline -- and `d_tiles_direct` the tiles of
+// the others, which take the register-only kernel.  One misaligned receiver therefore costs only its own tiles.
+// The two launches go back to back on `stream`.
+cudaError_t launch_unpack_batch(const SegDesc *d_segs, const TileRef *d_tiles_stream, uint64_t ntiles_stream,
+                                const TileRef *d_tiles_direct, uint64_t ntiles_direct, int tile_bytes, unsigned fmt,
+                                const Tuning &t, int sm_count, cudaStream_t stream, int *launches);
 
-cudaError_t launch_generate(void *dst, size_t nbytes, int pattern, uint64_t seed, uint64_t byte_offset,
+cudaError_t launch_generate(void *dst, size_t nbytes, int pattern, uint64_t seed, uint64_t byte_offset, int sm_count,
                             cudaStream_t stream);
 // *d_sum (device; zeroed first unless `accumulate`) += checksum of nwords 32-bit words
-cudaError_t launch_checksum(const void *words, size_t nwords, uint64_t first_index, unsigned long long *d_sum,
+cudaError_t launch_checksum(const void *words, size_t nwords, uint64_t first_index, unsigned long long *d_sum, int sm_count,
                             cudaStream_t stream, bool accumulate = false);
 // d_result[0] = mismatching words, d_result[1] = lowest mismatching word index (callee initialises)
 cudaError_t launch_verify(const void *in, size_t nbytes, const void *out_i32, const void *out_f32, unsigned fmt,
-                          unsigned long long *d_result, cudaStream_t stream);
+                          unsigned long long *d_result, int sm_count, cudaStream_t stream);
 
 // One-directional HBM streams for in-run roofline context: kind 0 = read src, 1 = write dst, 2 = copy src -> dst.
 cudaError_t launch_probe(int kind, const void *src, void *dst, size_t nbytes, int sm_count, int ctas_per_sm, cudaStream_t stream);
-
-// Host mirror of the device generator (bit-identical), for perseus_synth_fill and the virtual receiver.
-void host_generate(uint8_t *dst, size_t nbytes, int pattern, uint64_t seed, uint64_t byte_offset);
 
 }  // namespace pg

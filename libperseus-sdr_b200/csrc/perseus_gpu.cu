@@ -8,12 +8,16 @@
 #include "../../include/perseus-gpu.h"
 #include "kernels.h"
 
-#include <atomic>
+#include <chrono>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <string>
+#include <thread>
 #include <vector>
 #include <time.h>
 #if defined(__SSE2__)
@@ -22,21 +26,13 @@
 
 namespace {
 
-thread_local char g_errstr[1024] = "";
-
-int fail(int code, const char *fmt, ...)
-{
-	va_list ap;
-	va_start(ap, fmt);
-	vsnprintf(g_errstr, sizeof(g_errstr), fmt, ap);
-	va_end(ap);
-	return code;
-}
+using pg::fail;
 inline int ok(int v = 0) { return v; }
 
 constexpr int kMaxStreams = 8;
 constexpr int kMaxSlabs = 64;
 constexpr int kEventSlots = 32;
+constexpr int kMaxStageSlots = 8;
 
 struct Slab {
 	uint8_t *host = nullptr;       // pinned wire bytes being filled by the callback
@@ -53,20 +49,29 @@ struct Slab {
 }  // namespace
 
 struct perseus_gpu {
+	// Monitor lock: every C-ABI entry point that takes a handle holds it, so the callback thread, the application
+	// thread and the watchdog serialise on the handle's state.
+	std::recursive_mutex mu;   // recursive: a sink runs under it and may call the plumbing (sync, memcpy) of its own handle
 	int device = 0;
 	int sm_count = 0;
 	perseus_gpu_config cfg{};
 	pg::Tuning tune{};
 	int nstreams = 0;
-	cudaStream_t streams[kMaxStreams]{};
-	cudaEvent_t events[kEventSlots]{};
+	cudaStream_t streams[kMaxStreams]{};        // [0] = the launch stream of everything device-resident; slabs rotate over all
+	cudaStream_t s_in = nullptr, s_out = nullptr;   // copy-in / copy-out streams of the host-pointer pipeline
+	cudaEvent_t events[kEventSlots]{};          // the caller's timing slots (perseus_gpu_event_*)
+	cudaEvent_t tev[4]{};                       // private timing events (autotune, probes)
 	unsigned long long *d_scratch = nullptr;   // 2 x u64: checksum / verify results
 	unsigned long long *h_scratch = nullptr;   // pinned mirror
 	unsigned long long *d_sums = nullptr;      // 2 x u64: running checksums of PERSEUS_GPU_CHECKSUM calls (int32, float)
-	// staging for perseus_gpu_unpack with host pointers (one slot per stream)
+	// host-pointer pipeline of perseus_gpu_unpack: chunk c lives in slot c % nslots; per slot three events order
+	// copy-in -> kernel -> copy-out and protect the slot's reuse
 	size_t chunk_bytes = 0;
-	uint8_t *stage_in[kMaxStreams]{};
-	uint8_t *stage_out[kMaxStreams][2]{};
+	int nslots = 0;
+	uint64_t stage_seq = 0;                     // chunks staged so far (slot rotation continues across calls)
+	uint8_t *stage_in[kMaxStageSlots]{};
+	uint8_t *stage_out[kMaxStageSlots][2]{};
+	cudaEvent_t ev_in[kMaxStageSlots]{}, ev_k[kMaxStageSlots]{}, ev_out[kMaxStageSlots]{};
 	// streaming (callback) path
 	unsigned stream_fmt = 0;
 	size_t slab_bytes = 0;
@@ -82,6 +87,10 @@ struct perseus_gpu {
 	perseus_gpu_sink sink = nullptr;
 	void *sink_extra = nullptr;
 	FILE *fout = nullptr;
+	// latency watchdog (started with the first callback unless PERSEUS_GPU_OPT_NO_WATCHDOG)
+	std::thread watchdog;
+	std::condition_variable_any wd_cv;
+	bool wd_started = false, wd_stop = false;
 	// bookkeeping
 	perseus_gpu_stats stats{};
 	int latched = 0;           // first asynchronous error (surfaced at flush/sync/close)
@@ -90,11 +99,10 @@ struct perseus_gpu {
 
 struct perseus_gpu_plan {
 	pg::SegDesc *d_segs = nullptr;
-	pg::TileRef *d_tiles = nullptr;
-	uint64_t ntiles = 0, nsamples = 0, nbytes = 0;
+	pg::TileRef *d_tiles = nullptr;            // tiles of segments with 16-byte aligned outputs, then the others
+	uint64_t ntiles_stream = 0, ntiles_direct = 0, nsamples = 0, nbytes = 0;
 	unsigned fmt = 0;
 	int tile_bytes = 0;
-	bool all_aligned = false;
 };
 
 namespace {
@@ -112,7 +120,7 @@ void latch(perseus_gpu *h, int code)
 {
 	if (h && !h->latched) {
 		h->latched = code;
-		snprintf(h->latched_msg, sizeof(h->latched_msg), "%.*s", (int)sizeof(h->latched_msg) - 1, g_errstr);
+		snprintf(h->latched_msg, sizeof(h->latched_msg), "%.*s", (int)sizeof(h->latched_msg) - 1, pg::last_error());
 	}
 }
 
@@ -201,10 +209,13 @@ int bind(perseus_gpu *h)
 
 int ensure_staging(perseus_gpu *h, bool need_in, bool need_i32, bool need_f32)
 {
-	for (int s = 0; s < h->nstreams; ++s) {
+	for (int s = 0; s < h->nslots; ++s) {
 		if (need_in && !h->stage_in[s]) CU(h, cudaMalloc(&h->stage_in[s], h->chunk_bytes));
 		if (need_i32 && !h->stage_out[s][0]) CU(h, cudaMalloc(&h->stage_out[s][0], h->chunk_bytes / 6 * 8));
 		if (need_f32 && !h->stage_out[s][1]) CU(h, cudaMalloc(&h->stage_out[s][1], h->chunk_bytes / 6 * 8));
+		if (!h->ev_in[s]) CU(h, cudaEventCreateWithFlags(&h->ev_in[s], cudaEventDisableTiming));
+		if (!h->ev_k[s]) CU(h, cudaEventCreateWithFlags(&h->ev_k[s], cudaEventDisableTiming));
+		if (!h->ev_out[s]) CU(h, cudaEventCreateWithFlags(&h->ev_out[s], cudaEventDisableTiming));
 	}
 	return 0;
 }
@@ -226,7 +237,7 @@ int queue_checksums(perseus_gpu *h, const void *o_i32, const void *o_f32, uint64
 	const void *outs[2] = {o_i32, o_f32};
 	for (int k = 0; k < 2; ++k) {
 		if (!outs[k] || nsamples == 0) continue;
-		cudaError_t e = pg::launch_checksum(outs[k], nsamples * 2, first_sample * 2, h->d_sums + k, st, /*accumulate=*/true);
+		cudaError_t e = pg::launch_checksum(outs[k], nsamples * 2, first_sample * 2, h->d_sums + k, h->sm_count, st, /*accumulate=*/true);
 		if (e != cudaSuccess) return fail(PERSEUS_GPU_CUDAERR, "checksum launch failed: %s", cudaGetErrorString(e));
 		h->stats.kernel_launches++;
 	}
@@ -234,10 +245,12 @@ int queue_checksums(perseus_gpu *h, const void *o_i32, const void *o_f32, uint64
 }
 
 // ---- streaming path -------------------------------------------------------------------------
+// All functions below this line that take a handle expect h->mu to be held by the caller.
 
 int ensure_streaming(perseus_gpu *h)
 {
 	if (h->streaming_ready) return 0;
+	CU(h, cudaSetDevice(h->device));   // first callback on a foreign thread (the reference's libusb poll thread)
 	const bool want_i32 = h->stream_fmt & PERSEUS_GPU_OUT_INT32;
 	const bool want_f32 = h->stream_fmt & (PERSEUS_GPU_OUT_FLOAT | PERSEUS_GPU_OUT_FLOAT_POW2);
 	for (int k = 0; k < h->nslabs; ++k) {
@@ -247,7 +260,9 @@ int ensure_streaming(perseus_gpu *h)
 		if (!s.dev_in) CU(h, cudaMalloc(&s.dev_in, h->slab_bytes));
 		if (want_i32 && !s.dev_i32) CU(h, cudaMalloc(&s.dev_i32, h->slab_bytes / 6 * 8));
 		if (want_f32 && !s.dev_f32) CU(h, cudaMalloc(&s.dev_f32, h->slab_bytes / 6 * 8));
-		if (!s.done) CU(h, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+		// BlockingSync: back-pressure waits happen on the caller of the callback -- in the reference a SCHED_FIFO
+		// thread (perseus-sdr.c:749-753) -- and must sleep, not spin
+		if (!s.done) CU(h, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming | cudaEventBlockingSync));
 	}
 	h->streaming_ready = true;
 	return 0;
@@ -277,6 +292,7 @@ int submit_slab(perseus_gpu *h)
 	Slab &s = h->slabs[h->cur];
 	const size_t nbytes = h->fill;
 	if (nbytes == 0) return 0;
+	CU(h, cudaSetDevice(h->device));   // the only place the callback path needs the device: once per slab, not per transfer
 	cudaStream_t st = h->streams[h->cur % h->nstreams];
 	s.first_sample = h->samples_submitted;
 #if defined(__SSE2__)
@@ -349,10 +365,61 @@ inline uint64_t monotonic_ns()
 	return (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec;
 }
 
+// Submits the partial slab if its oldest transfer is over age.  Returns 1 if it did, 0 if not, < 0 on error.
+int submit_if_over_age(perseus_gpu *h, uint64_t now)
+{
+	if (!h->max_latency_ns || !h->fill || h->latched) return 0;
+	if (now - h->fill_started_ns < h->max_latency_ns) return 0;
+	const int rc = submit_slab(h);
+	return rc ? rc : 1;
+}
+
+// The latency bound must hold when no further callback comes (a stalled stream, the tail before
+// perseus_stop_async_input): this thread sleeps until the current partial slab's deadline and submits it.
+void watchdog_main(perseus_gpu *h)
+{
+	std::unique_lock<std::recursive_mutex> lk(h->mu);
+	while (!h->wd_stop) {
+		uint64_t wait_ns = h->max_latency_ns;
+		if (h->fill) {
+			const uint64_t now = monotonic_ns(), due = h->fill_started_ns + h->max_latency_ns;
+			wait_ns = due > now ? due - now : 0;
+		}
+		if (wait_ns) h->wd_cv.wait_for(lk, std::chrono::nanoseconds(wait_ns));
+		if (h->wd_stop) break;
+		const int rc = submit_if_over_age(h, monotonic_ns());
+		if (rc < 0) latch(h, rc);
+		else if (rc > 0) h->stats.watchdog_submits++;
+		else if (!wait_ns) h->wd_cv.wait_for(lk, std::chrono::milliseconds(1));   // latched error: nothing to do, do not spin
+	}
+}
+
+void start_watchdog(perseus_gpu *h)
+{
+	if (h->wd_started || !h->max_latency_ns || (h->cfg.options & PERSEUS_GPU_OPT_NO_WATCHDOG)) return;
+	h->wd_started = true;   // one attempt only
+	try {
+		h->watchdog = std::thread(watchdog_main, h);
+	} catch (...) {
+		// no thread available: the bound is still checked at every callback and by perseus_gpu_poll
+	}
+}
+
+void stop_watchdog(perseus_gpu *h)   // called WITHOUT h->mu
+{
+	{
+		std::lock_guard<std::recursive_mutex> lk(h->mu);
+		h->wd_stop = true;
+	}
+	h->wd_cv.notify_all();
+	if (h->watchdog.joinable()) h->watchdog.join();
+}
+
 int stream_push(perseus_gpu *h, const uint8_t *buf, size_t nbytes)
 {
 	int rc = ensure_streaming(h);
 	if (rc) return rc;
+	start_watchdog(h);
 	const uint64_t now = h->max_latency_ns ? monotonic_ns() : 0;
 	if (h->fill == 0) h->fill_started_ns = now;
 	while (nbytes) {
@@ -369,9 +436,140 @@ int stream_push(perseus_gpu *h, const uint8_t *buf, size_t nbytes)
 		}
 	}
 	// latency bound: on a real receiver transfers trickle in (10.8 ms apart at 95 kS/s); do not sit on them
-	if (h->max_latency_ns && h->fill && now - h->fill_started_ns >= h->max_latency_ns) return submit_slab(h);
+	rc = submit_if_over_age(h, now);
+	return rc < 0 ? rc : 0;
+}
+
+int sync_locked(perseus_gpu *h)
+{
+	cudaStream_t all[kMaxStreams + 2];
+	int n = 0;
+	for (int s = 0; s < h->nstreams; ++s) all[n++] = h->streams[s];
+	all[n++] = h->s_in;
+	all[n++] = h->s_out;
+	for (int s = 0; s < n; ++s) {
+		if (!all[s]) continue;
+		cudaError_t e = cudaStreamSynchronize(all[s]);
+		if (e != cudaSuccess) {
+			fail(PERSEUS_GPU_CUDAERR, "stream %d: %s", s, cudaGetErrorString(e));
+			latch(h, PERSEUS_GPU_CUDAERR);
+		}
+	}
+	return surface_latched(h);
+}
+
+int flush_locked(perseus_gpu *h)
+{
+	int rc;
+	if (h->streaming_ready) {
+		if (h->fill && !h->latched) {
+			rc = submit_slab(h);
+			if (rc) latch(h, rc);
+		}
+		rc = drain_file(h, h->nslabs);   // oldest first, so the file keeps stream order
+		if (rc) latch(h, rc);
+		h->next_to_write = h->cur;       // nothing in flight: the next slab submitted is the oldest
+		if (h->fout) fflush(h->fout);
+	}
+	return sync_locked(h);
+}
+
+void destroy_plan(perseus_gpu_plan *p)
+{
+	if (p->d_segs) cudaFree(p->d_segs);
+	if (p->d_tiles) cudaFree(p->d_tiles);
+	delete p;
+}
+
+int plan_create_locked(perseus_gpu *h, const perseus_gpu_seg *segs, int nseg, unsigned flags, perseus_gpu_plan **out)
+{
+	if (!out) return fail(PERSEUS_GPU_ERRPARAM, "null plan pointer");
+	*out = nullptr;
+	if (nseg < 0 || (nseg > 0 && !segs)) return fail(PERSEUS_GPU_ERRPARAM, "bad segment table");
+	unsigned fmt = flags & (PERSEUS_GPU_OUT_INT32 | PERSEUS_GPU_OUT_FLOAT | PERSEUS_GPU_OUT_FLOAT_POW2);
+	if (fmt == 0 && nseg > 0) fmt = (segs[0].out_i32 ? PERSEUS_GPU_OUT_INT32 : 0u) | (segs[0].out_f32 ? PERSEUS_GPU_OUT_FLOAT : 0u);
+	if ((fmt & PERSEUS_GPU_OUT_FLOAT) && (fmt & PERSEUS_GPU_OUT_FLOAT_POW2))
+		return fail(PERSEUS_GPU_ERRPARAM, "OUT_FLOAT and OUT_FLOAT_POW2 are mutually exclusive");
+	if (fmt == 0 && nseg > 0) return fail(PERSEUS_GPU_ERRPARAM, "no output requested");
+
+	const int tile = pg::resolve_geometry(h->tune, fmt).tile_bytes;
+	std::vector<pg::SegDesc> hs((size_t)nseg);
+	// Tiles are split by the alignment of their segment's OUTPUT pointers: 16-byte aligned ones (any cudaMalloc'd
+	// buffer) go to the bulk-copy pipeline, the rest to the register-only kernel -- per segment, so one odd
+	// receiver does not drag the whole batch onto the slow kernel.  Wire pointers may have any alignment.
+	std::vector<pg::TileRef> fast, slow;
+	uint64_t nsamples = 0, nbytes = 0;
+	for (int i = 0; i < nseg; ++i) {
+		const perseus_gpu_seg &s = segs[i];
+		const uint64_t used = (uint64_t)s.nbytes / 6 * 6;
+		if (used && !s.in) return fail(PERSEUS_GPU_ERRPARAM, "segment %d: in is NULL", i);
+		if (used && (fmt & PERSEUS_GPU_OUT_INT32) && !s.out_i32) return fail(PERSEUS_GPU_ERRPARAM, "segment %d: out_i32 is NULL", i);
+		if (used && (fmt & (PERSEUS_GPU_OUT_FLOAT | PERSEUS_GPU_OUT_FLOAT_POW2)) && !s.out_f32)
+			return fail(PERSEUS_GPU_ERRPARAM, "segment %d: out_f32 is NULL", i);
+		if (((uintptr_t)s.out_i32 & 3) || ((uintptr_t)s.out_f32 & 3)) return fail(PERSEUS_GPU_ERRPARAM, "segment %d: outputs must be 4-byte aligned", i);
+		hs[(size_t)i] = pg::SegDesc{static_cast<const uint8_t *>(s.in), s.nbytes, (fmt & PERSEUS_GPU_OUT_INT32) ? s.out_i32 : nullptr,
+		                            (fmt & (PERSEUS_GPU_OUT_FLOAT | PERSEUS_GPU_OUT_FLOAT_POW2)) ? s.out_f32 : nullptr};
+		const bool out16 = ((((uintptr_t)hs[(size_t)i].out_i32 | (uintptr_t)hs[(size_t)i].out_f32) & 15) == 0) && h->tune.variant != PERSEUS_GPU_VARIANT_DIRECT;
+		const uint64_t nt = (used + (uint64_t)tile - 1) / (uint64_t)tile;
+		if (nt > 0xFFFFFFFFull) return fail(PERSEUS_GPU_BUFFERSIZE, "segment %d too large", i);
+		std::vector<pg::TileRef> &dst = out16 ? fast : slow;
+		for (uint64_t t = 0; t < nt; ++t) dst.push_back(pg::TileRef{(uint32_t)i, (uint32_t)t});
+		nsamples += used / 6;
+		nbytes += used;
+	}
+	perseus_gpu_plan *p = new (std::nothrow) perseus_gpu_plan();
+	if (!p) return fail(PERSEUS_GPU_NOMEM, "out of memory");
+	p->ntiles_stream = fast.size();
+	p->ntiles_direct = slow.size();
+	p->nsamples = nsamples;
+	p->nbytes = nbytes;
+	p->fmt = fmt;
+	p->tile_bytes = tile;
+	fast.insert(fast.end(), slow.begin(), slow.end());   // one upload: [stream tiles | direct tiles]
+	cudaError_t e = cudaSuccess;
+	if (nseg) e = cudaMalloc(&p->d_segs, hs.size() * sizeof(pg::SegDesc));
+	if (e == cudaSuccess && !fast.empty()) e = cudaMalloc(&p->d_tiles, fast.size() * sizeof(pg::TileRef));
+	if (e == cudaSuccess && nseg) e = cudaMemcpyAsync(p->d_segs, hs.data(), hs.size() * sizeof(pg::SegDesc), cudaMemcpyHostToDevice, h->streams[0]);
+	if (e == cudaSuccess && !fast.empty())
+		e = cudaMemcpyAsync(p->d_tiles, fast.data(), fast.size() * sizeof(pg::TileRef), cudaMemcpyHostToDevice, h->streams[0]);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(h->streams[0]);   // hs/fast die with this frame
+	if (e != cudaSuccess) {
+		cudaGetLastError();
+		destroy_plan(p);
+		return fail(PERSEUS_GPU_CUDAERR, "plan upload failed: %s", cudaGetErrorString(e));
+	}
+	*out = p;
 	return 0;
 }
+
+int64_t plan_run_locked(perseus_gpu *h, perseus_gpu_plan *p, unsigned flags)
+{
+	if (!p) return fail(PERSEUS_GPU_ERRPARAM, "null plan");
+	int n = 0;   // the plan keeps the tile size and the split it was built with; stages / CTAs per SM follow the handle's current tuning
+	cudaError_t e = pg::launch_unpack_batch(p->d_segs, p->d_tiles, p->ntiles_stream, p->d_tiles + p->ntiles_stream, p->ntiles_direct,
+	                                        p->tile_bytes, p->fmt, h->tune, h->sm_count, h->streams[0], &n);
+	if (e != cudaSuccess) return fail(PERSEUS_GPU_CUDAERR, "batched unpack launch failed: %s", cudaGetErrorString(e));
+	h->stats.kernel_launches += (uint64_t)n;
+	h->stats.samples += p->nsamples;
+	h->stats.bytes_in += p->nbytes;
+	if (!(flags & PERSEUS_GPU_ASYNC)) {
+		int rc = sync_locked(h);
+		if (rc) return rc;
+	}
+	return (int64_t)p->nsamples;
+}
+
+// Locks the handle and makes its device current on the calling thread.
+struct Entry {
+	std::unique_lock<std::recursive_mutex> lk;
+	int rc = 0;
+	explicit Entry(perseus_gpu *h)
+	{
+		if (!h) { rc = fail(PERSEUS_GPU_NULLHANDLE, "null handle"); return; }
+		lk = std::unique_lock<std::recursive_mutex>(h->mu);
+		rc = bind(h);
+	}
+};
 
 }  // namespace
 
@@ -379,9 +577,7 @@ int stream_push(perseus_gpu *h, const uint8_t *buf, size_t nbytes)
 
 extern "C" {
 
-const char *perseus_gpu_errorstr(void) { return g_errstr; }
-
-const char *perseus_gpu_version(void) { return "perseus-gpu abi 1, sm_100a, " __DATE__; }
+const char *perseus_gpu_version(void) { return "perseus-gpu abi 2, sm_100a, " __DATE__; }
 
 int perseus_gpu_device_count(void)
 {
@@ -437,10 +633,13 @@ int perseus_gpu_open(perseus_gpu **out, const perseus_gpu_config *ucfg)
 		return fail(PERSEUS_GPU_ERRPARAM, "stream_flags 0x%x has unknown bits", sfmt);
 	if ((sfmt & PERSEUS_GPU_OUT_FLOAT) && (sfmt & PERSEUS_GPU_OUT_FLOAT_POW2))
 		return fail(PERSEUS_GPU_ERRPARAM, "stream_flags: OUT_FLOAT and OUT_FLOAT_POW2 are mutually exclusive");
+	if (cfg.options & ~PERSEUS_GPU_OPT_NO_WATCHDOG) return fail(PERSEUS_GPU_ERRPARAM, "options 0x%x has unknown bits", cfg.options);
 	const uint32_t nslabs = cfg.nslabs ? cfg.nslabs : 4;
 	if (nslabs < 2 || nslabs > (uint32_t)kMaxSlabs) return fail(PERSEUS_GPU_ERRPARAM, "nslabs %u not in 2..%d", nslabs, kMaxSlabs);
 	const uint32_t nstreams = cfg.nstreams ? cfg.nstreams : 2;
 	if (nstreams < 1 || nstreams > (uint32_t)kMaxStreams) return fail(PERSEUS_GPU_ERRPARAM, "nstreams %u not in 1..%d", nstreams, kMaxStreams);
+	const uint32_t nslots = cfg.stage_slots ? cfg.stage_slots : 3;
+	if (nslots < 2 || nslots > (uint32_t)kMaxStageSlots) return fail(PERSEUS_GPU_ERRPARAM, "stage_slots %u not in 2..%d", nslots, kMaxStageSlots);
 	uint64_t slab = cfg.slab_bytes ? cfg.slab_bytes : (8ull << 20);
 	slab -= slab % 48;
 	uint64_t chunk = cfg.chunk_bytes ? cfg.chunk_bytes : (32ull << 20);
@@ -456,14 +655,14 @@ int perseus_gpu_open(perseus_gpu **out, const perseus_gpu_config *ucfg)
 	h->stream_fmt = sfmt;
 	h->nslabs = (int)nslabs;
 	h->nstreams = (int)nstreams;
+	h->nslots = (int)nslots;
 	h->slab_bytes = (size_t)slab;
 	h->max_latency_ns = cfg.max_latency_us == 0xFFFFFFFFu ? 0 : (uint64_t)(cfg.max_latency_us ? cfg.max_latency_us : 50000u) * 1000ull;
 	h->chunk_bytes = (size_t)chunk;
 	auto bail = [&](int code) {   // free what exists, keep the message of the original failure
-		char keep[sizeof(g_errstr)];
-		memcpy(keep, g_errstr, sizeof(keep));
+		const std::string keep = pg::last_error();
 		perseus_gpu_close(h);
-		memcpy(g_errstr, keep, sizeof(keep));
+		pg::set_last_error(keep.c_str());
 		return code;
 	};
 	cudaError_t e = cudaSetDevice(h->device);
@@ -472,10 +671,12 @@ int perseus_gpu_open(perseus_gpu **out, const perseus_gpu_config *ucfg)
 		e = cudaStreamCreateWithFlags(&h->streams[s], cudaStreamNonBlocking);
 		if (e != cudaSuccess) return bail(fail(PERSEUS_GPU_CUDAERR, "cudaStreamCreate: %s", cudaGetErrorString(e)));
 	}
-	for (int k = 0; k < kEventSlots; ++k) {
-		e = cudaEventCreate(&h->events[k]);
-		if (e != cudaSuccess) return bail(fail(PERSEUS_GPU_CUDAERR, "cudaEventCreate: %s", cudaGetErrorString(e)));
-	}
+	e = cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking);
+	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking);
+	if (e != cudaSuccess) return bail(fail(PERSEUS_GPU_CUDAERR, "cudaStreamCreate: %s", cudaGetErrorString(e)));
+	for (int k = 0; k < kEventSlots && e == cudaSuccess; ++k) e = cudaEventCreate(&h->events[k]);
+	for (int k = 0; k < 4 && e == cudaSuccess; ++k) e = cudaEventCreate(&h->tev[k]);
+	if (e != cudaSuccess) return bail(fail(PERSEUS_GPU_CUDAERR, "cudaEventCreate: %s", cudaGetErrorString(e)));
 	e = cudaMalloc(&h->d_scratch, 2 * sizeof(unsigned long long));
 	if (e == cudaSuccess) e = cudaMalloc(&h->d_sums, 2 * sizeof(unsigned long long));
 	if (e == cudaSuccess) e = cudaMemset(h->d_sums, 0, 2 * sizeof(unsigned long long));
@@ -488,37 +689,45 @@ int perseus_gpu_open(perseus_gpu **out, const perseus_gpu_config *ucfg)
 int perseus_gpu_close(perseus_gpu *h)
 {
 	if (!h) return fail(PERSEUS_GPU_NULLHANDLE, "null handle");
+	stop_watchdog(h);
 	int rc = 0;
-	if (cudaSetDevice(h->device) == cudaSuccess) {
-		if (h->streaming_ready) rc = perseus_gpu_flush(h);
-		for (int s = 0; s < h->nstreams; ++s)
-			if (h->streams[s]) cudaStreamSynchronize(h->streams[s]);
-		if (!rc) rc = surface_latched(h);
-		for (int k = 0; k < kMaxSlabs; ++k) {
-			Slab &s = h->slabs[k];
-			if (s.host) cudaFreeHost(s.host);
-			if (s.host_out) cudaFreeHost(s.host_out);
-			if (s.dev_in) cudaFree(s.dev_in);
-			if (s.dev_i32) cudaFree(s.dev_i32);
-			if (s.dev_f32) cudaFree(s.dev_f32);
-			if (s.done) cudaEventDestroy(s.done);
+	{
+		std::lock_guard<std::recursive_mutex> lk(h->mu);
+		if (cudaSetDevice(h->device) == cudaSuccess) {
+			rc = flush_locked(h);
+			for (int k = 0; k < kMaxSlabs; ++k) {
+				Slab &s = h->slabs[k];
+				if (s.host) cudaFreeHost(s.host);
+				if (s.host_out) cudaFreeHost(s.host_out);
+				if (s.dev_in) cudaFree(s.dev_in);
+				if (s.dev_i32) cudaFree(s.dev_i32);
+				if (s.dev_f32) cudaFree(s.dev_f32);
+				if (s.done) cudaEventDestroy(s.done);
+			}
+			for (int s = 0; s < kMaxStageSlots; ++s) {
+				if (h->stage_in[s]) cudaFree(h->stage_in[s]);
+				if (h->stage_out[s][0]) cudaFree(h->stage_out[s][0]);
+				if (h->stage_out[s][1]) cudaFree(h->stage_out[s][1]);
+				if (h->ev_in[s]) cudaEventDestroy(h->ev_in[s]);
+				if (h->ev_k[s]) cudaEventDestroy(h->ev_k[s]);
+				if (h->ev_out[s]) cudaEventDestroy(h->ev_out[s]);
+			}
+			if (h->d_scratch) cudaFree(h->d_scratch);
+			if (h->d_sums) cudaFree(h->d_sums);
+			if (h->h_scratch) cudaFreeHost(h->h_scratch);
+			for (int k = 0; k < kEventSlots; ++k)
+				if (h->events[k]) cudaEventDestroy(h->events[k]);
+			for (int k = 0; k < 4; ++k)
+				if (h->tev[k]) cudaEventDestroy(h->tev[k]);
+			for (int s = 0; s < h->nstreams; ++s)
+				if (h->streams[s]) cudaStreamDestroy(h->streams[s]);
+			if (h->s_in) cudaStreamDestroy(h->s_in);
+			if (h->s_out) cudaStreamDestroy(h->s_out);
+			cudaGetLastError();
 		}
-		for (int s = 0; s < kMaxStreams; ++s) {
-			if (h->stage_in[s]) cudaFree(h->stage_in[s]);
-			if (h->stage_out[s][0]) cudaFree(h->stage_out[s][0]);
-			if (h->stage_out[s][1]) cudaFree(h->stage_out[s][1]);
+		if (h->fout) {
+			if (fclose(h->fout) != 0 && !rc) rc = fail(PERSEUS_GPU_IOERROR, "closing stream file failed");
 		}
-		if (h->d_scratch) cudaFree(h->d_scratch);
-		if (h->d_sums) cudaFree(h->d_sums);
-		if (h->h_scratch) cudaFreeHost(h->h_scratch);
-		for (int k = 0; k < kEventSlots; ++k)
-			if (h->events[k]) cudaEventDestroy(h->events[k]);
-		for (int s = 0; s < h->nstreams; ++s)
-			if (h->streams[s]) cudaStreamDestroy(h->streams[s]);
-		cudaGetLastError();
-	}
-	if (h->fout) {
-		if (fclose(h->fout) != 0 && !rc) rc = fail(PERSEUS_GPU_IOERROR, "closing stream file failed");
 	}
 	delete h;
 	return rc;
@@ -526,21 +735,15 @@ int perseus_gpu_close(perseus_gpu *h)
 
 int perseus_gpu_sync(perseus_gpu *h)
 {
-	int rc = bind(h);
-	if (rc) return rc;
-	for (int s = 0; s < h->nstreams; ++s) {
-		cudaError_t e = cudaStreamSynchronize(h->streams[s]);
-		if (e != cudaSuccess) {
-			fail(PERSEUS_GPU_CUDAERR, "stream %d: %s", s, cudaGetErrorString(e));
-			latch(h, PERSEUS_GPU_CUDAERR);
-		}
-	}
-	return surface_latched(h);
+	Entry en(h);
+	if (en.rc) return en.rc;
+	return sync_locked(h);
 }
 
 int64_t perseus_gpu_unpack(perseus_gpu *h, const void *buf, size_t nbytes, void *out_i32, void *out_f32, unsigned flags)
 {
-	int rc = bind(h);
+	Entry en(h);
+	int rc = en.rc;
 	if (rc) return rc;
 	if (flags & ~(PERSEUS_GPU_OUT_INT32 | PERSEUS_GPU_OUT_FLOAT | PERSEUS_GPU_OUT_FLOAT_POW2 | PERSEUS_GPU_ASYNC | PERSEUS_GPU_CHECKSUM))
 		return fail(PERSEUS_GPU_ERRPARAM, "unknown flag bits 0x%x", flags);
@@ -551,63 +754,73 @@ int64_t perseus_gpu_unpack(perseus_gpu *h, const void *buf, size_t nbytes, void 
 	if (!(fmt & PERSEUS_GPU_OUT_INT32)) out_i32 = nullptr;
 	if (!(fmt & (PERSEUS_GPU_OUT_FLOAT | PERSEUS_GPU_OUT_FLOAT_POW2))) out_f32 = nullptr;
 	const uint64_t ns = nbytes / 6;
-	if (ns == 0) return 0;
-	if (!buf) return fail(PERSEUS_GPU_ERRPARAM, "buf is NULL");
+	if (ns && !buf) return fail(PERSEUS_GPU_ERRPARAM, "buf is NULL");
 	if ((out_i32 && ((uintptr_t)out_i32 & 3)) || (out_f32 && ((uintptr_t)out_f32 & 3)))
 		return fail(PERSEUS_GPU_ERRPARAM, "output pointers must be 4-byte aligned");
 
-	if (want_sums) {   // totals restart with this call; everything queued earlier has to be done with them first
-		rc = perseus_gpu_sync(h);
+	if (want_sums) {   // totals restart with this call (even an empty one); everything queued earlier has to be done with them first
+		rc = sync_locked(h);
 		if (rc) return rc;
 		CU(h, cudaMemsetAsync(h->d_sums, 0, 2 * sizeof(unsigned long long), h->streams[0]));
 		CU(h, cudaStreamSynchronize(h->streams[0]));
 	}
+	if (ns == 0) return 0;
 	const Mem min_ = classify(buf);
 	const Mem mi = out_i32 ? classify(out_i32) : Mem::Device;
 	const Mem mf = out_f32 ? classify(out_f32) : Mem::Device;
 	const bool in_dev = min_ == Mem::Device, oi_dev = mi == Mem::Device, of_dev = mf == Mem::Device;
+	cudaStream_t sk = h->streams[0];
 
 	if (in_dev && oi_dev && of_dev) {
-		rc = do_launch(h, buf, ns * 6, out_i32, out_f32, fmt, h->streams[0]);
+		rc = do_launch(h, buf, ns * 6, out_i32, out_f32, fmt, sk);
 		if (rc) return rc;
-		if (want_sums && (rc = queue_checksums(h, out_i32, out_f32, ns, 0, h->streams[0]))) return rc;
+		if (want_sums && (rc = queue_checksums(h, out_i32, out_f32, ns, 0, sk))) return rc;
 	} else {
-		// staged pipeline: chunk c uses stream/slot c % nstreams; H2D, kernel and D2H of
-		// neighbouring chunks overlap, stream order protects slot reuse.
+		// Three-stage pipeline over `nslots` staging slots: copy-in on s_in, kernel (+ checksums) on streams[0], copy-out
+		// on s_out, ordered per slot by events.  The copy engines of both directions and the SMs each work on a
+		// different chunk at the same time; neither copy stream ever waits behind a copy of the other direction.
+		const bool host_out = (out_i32 && !oi_dev) || (out_f32 && !of_dev);
 		rc = ensure_staging(h, !in_dev, out_i32 && !oi_dev, out_f32 && !of_dev);
 		if (rc) return rc;
 		const uint8_t *src = static_cast<const uint8_t *>(buf);
 		const size_t total = ns * 6;
-		size_t off = 0;
-		for (int c = 0; off < total; ++c) {
-			const int s = c % h->nstreams;
-			cudaStream_t st = h->streams[s];
+		for (size_t off = 0; off < total;) {
+			const int s = (int)(h->stage_seq++ % (uint64_t)h->nslots);
 			const size_t n = total - off < h->chunk_bytes ? total - off : h->chunk_bytes;
 			const size_t o = off / 6 * 8, on = n / 6 * 8;
 			const uint8_t *kin = src + off;
 			if (!in_dev) {
-				CU(h, cudaMemcpyAsync(h->stage_in[s], src + off, n, cudaMemcpyHostToDevice, st));
+				CU(h, cudaStreamWaitEvent(h->s_in, h->ev_k[s], 0));       // the kernel that last read this slot's input is done
+				CU(h, cudaMemcpyAsync(h->stage_in[s], src + off, n, cudaMemcpyHostToDevice, h->s_in));
+				CU(h, cudaEventRecord(h->ev_in[s], h->s_in));
+				CU(h, cudaStreamWaitEvent(sk, h->ev_in[s], 0));
 				h->stats.h2d_bytes += n;
 				kin = h->stage_in[s];
 			}
+			if (host_out) CU(h, cudaStreamWaitEvent(sk, h->ev_out[s], 0));   // the copy-out that last read this slot's outputs is done
 			uint8_t *ki = out_i32 ? (oi_dev ? static_cast<uint8_t *>(out_i32) + o : h->stage_out[s][0]) : nullptr;
 			uint8_t *kf = out_f32 ? (of_dev ? static_cast<uint8_t *>(out_f32) + o : h->stage_out[s][1]) : nullptr;
-			rc = do_launch(h, kin, n, ki, kf, fmt, st);
+			rc = do_launch(h, kin, n, ki, kf, fmt, sk);
 			if (rc) return rc;
-			if (want_sums && (rc = queue_checksums(h, ki, kf, n / 6, off / 6, st))) return rc;
-			if (out_i32 && !oi_dev) {
-				CU(h, cudaMemcpyAsync(static_cast<uint8_t *>(out_i32) + o, ki, on, cudaMemcpyDeviceToHost, st));
-				h->stats.d2h_bytes += on;
-			}
-			if (out_f32 && !of_dev) {
-				CU(h, cudaMemcpyAsync(static_cast<uint8_t *>(out_f32) + o, kf, on, cudaMemcpyDeviceToHost, st));
-				h->stats.d2h_bytes += on;
+			if (want_sums && (rc = queue_checksums(h, ki, kf, n / 6, off / 6, sk))) return rc;
+			CU(h, cudaEventRecord(h->ev_k[s], sk));
+			if (host_out) {
+				CU(h, cudaStreamWaitEvent(h->s_out, h->ev_k[s], 0));
+				if (out_i32 && !oi_dev) {
+					CU(h, cudaMemcpyAsync(static_cast<uint8_t *>(out_i32) + o, ki, on, cudaMemcpyDeviceToHost, h->s_out));
+					h->stats.d2h_bytes += on;
+				}
+				if (out_f32 && !of_dev) {
+					CU(h, cudaMemcpyAsync(static_cast<uint8_t *>(out_f32) + o, kf, on, cudaMemcpyDeviceToHost, h->s_out));
+					h->stats.d2h_bytes += on;
+				}
+				CU(h, cudaEventRecord(h->ev_out[s], h->s_out));
 			}
 			off += n;
 		}
 	}
 	if (!(flags & PERSEUS_GPU_ASYNC)) {
-		rc = perseus_gpu_sync(h);
+		rc = sync_locked(h);
 		if (rc) return rc;
 	}
 	return (int64_t)ns;
@@ -615,7 +828,9 @@ int64_t perseus_gpu_unpack(perseus_gpu *h, const void *buf, size_t nbytes, void 
 
 int perseus_gpu_get_checksums(perseus_gpu *h, uint64_t *sum_i32, uint64_t *sum_f32)
 {
-	int rc = perseus_gpu_sync(h);
+	Entry en(h);
+	if (en.rc) return en.rc;
+	int rc = sync_locked(h);
 	if (rc) return rc;
 	CU(h, cudaMemcpyAsync(h->h_scratch, h->d_sums, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->streams[0]));
 	CU(h, cudaStreamSynchronize(h->streams[0]));
@@ -629,102 +844,38 @@ int perseus_gpu_get_checksums(perseus_gpu *h, uint64_t *sum_i32, uint64_t *sum_f
 
 int perseus_gpu_plan_create(perseus_gpu *h, const perseus_gpu_seg *segs, int nseg, unsigned flags, perseus_gpu_plan **out)
 {
-	int rc = bind(h);
-	if (rc) return rc;
-	if (!out) return fail(PERSEUS_GPU_ERRPARAM, "null plan pointer");
-	*out = nullptr;
-	if (nseg < 0 || (nseg > 0 && !segs)) return fail(PERSEUS_GPU_ERRPARAM, "bad segment table");
-	unsigned fmt = flags & (PERSEUS_GPU_OUT_INT32 | PERSEUS_GPU_OUT_FLOAT | PERSEUS_GPU_OUT_FLOAT_POW2);
-	if (fmt == 0 && nseg > 0) fmt = (segs[0].out_i32 ? PERSEUS_GPU_OUT_INT32 : 0u) | (segs[0].out_f32 ? PERSEUS_GPU_OUT_FLOAT : 0u);
-	if ((fmt & PERSEUS_GPU_OUT_FLOAT) && (fmt & PERSEUS_GPU_OUT_FLOAT_POW2))
-		return fail(PERSEUS_GPU_ERRPARAM, "OUT_FLOAT and OUT_FLOAT_POW2 are mutually exclusive");
-	if (fmt == 0 && nseg > 0) return fail(PERSEUS_GPU_ERRPARAM, "no output requested");
-
-	const int tile = pg::resolve_geometry(h->tune, fmt).tile_bytes;
-	std::vector<pg::SegDesc> hs((size_t)nseg);
-	std::vector<pg::TileRef> ht;
-	bool aligned = true;
-	uint64_t nsamples = 0, nbytes = 0;
-	for (int i = 0; i < nseg; ++i) {
-		const perseus_gpu_seg &s = segs[i];
-		const uint64_t used = (uint64_t)s.nbytes / 6 * 6;
-		if (used && !s.in) return fail(PERSEUS_GPU_ERRPARAM, "segment %d: in is NULL", i);
-		if (used && (fmt & PERSEUS_GPU_OUT_INT32) && !s.out_i32) return fail(PERSEUS_GPU_ERRPARAM, "segment %d: out_i32 is NULL", i);
-		if (used && (fmt & (PERSEUS_GPU_OUT_FLOAT | PERSEUS_GPU_OUT_FLOAT_POW2)) && !s.out_f32)
-			return fail(PERSEUS_GPU_ERRPARAM, "segment %d: out_f32 is NULL", i);
-		if (((uintptr_t)s.out_i32 & 3) || ((uintptr_t)s.out_f32 & 3)) return fail(PERSEUS_GPU_ERRPARAM, "segment %d: outputs must be 4-byte aligned", i);
-		hs[(size_t)i] = pg::SegDesc{static_cast<const uint8_t *>(s.in), s.nbytes, (fmt & PERSEUS_GPU_OUT_INT32) ? s.out_i32 : nullptr,
-		                            (fmt & (PERSEUS_GPU_OUT_FLOAT | PERSEUS_GPU_OUT_FLOAT_POW2)) ? s.out_f32 : nullptr};
-		if (((uintptr_t)hs[(size_t)i].out_i32 | (uintptr_t)hs[(size_t)i].out_f32) & 15) aligned = false;   // wire pointers may be unaligned
-		const uint64_t nt = (used + (uint64_t)tile - 1) / (uint64_t)tile;
-		if (nt > 0xFFFFFFFFull) return fail(PERSEUS_GPU_BUFFERSIZE, "segment %d too large", i);
-		for (uint64_t t = 0; t < nt; ++t) ht.push_back(pg::TileRef{(uint32_t)i, (uint32_t)t});
-		nsamples += used / 6;
-		nbytes += used;
-	}
-	perseus_gpu_plan *p = new (std::nothrow) perseus_gpu_plan();
-	if (!p) return fail(PERSEUS_GPU_NOMEM, "out of memory");
-	p->ntiles = ht.size();
-	p->nsamples = nsamples;
-	p->nbytes = nbytes;
-	p->fmt = fmt;
-	p->tile_bytes = tile;
-	p->all_aligned = aligned;
-	cudaError_t e = cudaSuccess;
-	if (nseg) e = cudaMalloc(&p->d_segs, hs.size() * sizeof(pg::SegDesc));
-	if (e == cudaSuccess && !ht.empty()) e = cudaMalloc(&p->d_tiles, ht.size() * sizeof(pg::TileRef));
-	if (e == cudaSuccess && nseg) e = cudaMemcpyAsync(p->d_segs, hs.data(), hs.size() * sizeof(pg::SegDesc), cudaMemcpyHostToDevice, h->streams[0]);
-	if (e == cudaSuccess && !ht.empty())
-		e = cudaMemcpyAsync(p->d_tiles, ht.data(), ht.size() * sizeof(pg::TileRef), cudaMemcpyHostToDevice, h->streams[0]);
-	if (e == cudaSuccess) e = cudaStreamSynchronize(h->streams[0]);   // hs/ht die with this frame
-	if (e != cudaSuccess) {
-		if (p->d_segs) cudaFree(p->d_segs);
-		if (p->d_tiles) cudaFree(p->d_tiles);
-		delete p;
-		return fail(PERSEUS_GPU_CUDAERR, "plan upload failed: %s", cudaGetErrorString(e));
-	}
-	*out = p;
-	return 0;
+	Entry en(h);
+	if (en.rc) return en.rc;
+	return plan_create_locked(h, segs, nseg, flags, out);
 }
 
 int64_t perseus_gpu_plan_run(perseus_gpu *h, perseus_gpu_plan *p, unsigned flags)
 {
-	int rc = bind(h);
-	if (rc) return rc;
-	if (!p) return fail(PERSEUS_GPU_ERRPARAM, "null plan");
-	int n = 0;   // the plan keeps the tile size it was built with; stages / CTAs per SM follow the handle's current tuning
-	cudaError_t e = pg::launch_unpack_batch(p->d_segs, p->d_tiles, p->ntiles, p->tile_bytes, p->fmt, p->all_aligned, h->tune, h->sm_count,
-	                                        h->streams[0], &n);
-	if (e != cudaSuccess) return fail(PERSEUS_GPU_CUDAERR, "batched unpack launch failed: %s", cudaGetErrorString(e));
-	h->stats.kernel_launches += (uint64_t)n;
-	h->stats.samples += p->nsamples;
-	h->stats.bytes_in += p->nbytes;
-	if (!(flags & PERSEUS_GPU_ASYNC)) {
-		rc = perseus_gpu_sync(h);
-		if (rc) return rc;
-	}
-	return (int64_t)p->nsamples;
+	Entry en(h);
+	if (en.rc) return en.rc;
+	return plan_run_locked(h, p, flags);
 }
 
 int perseus_gpu_plan_destroy(perseus_gpu *h, perseus_gpu_plan *p)
 {
-	int rc = bind(h);
-	if (rc) return rc;
+	Entry en(h);
+	if (en.rc) return en.rc;
 	if (!p) return 0;
 	cudaStreamSynchronize(h->streams[0]);
-	if (p->d_segs) cudaFree(p->d_segs);
-	if (p->d_tiles) cudaFree(p->d_tiles);
-	delete p;
+	destroy_plan(p);
 	return 0;
 }
 
 int64_t perseus_gpu_unpack_batch(perseus_gpu *h, const perseus_gpu_seg *segs, int nseg, unsigned flags)
 {
+	Entry en(h);
+	if (en.rc) return en.rc;
 	perseus_gpu_plan *p = nullptr;
-	int rc = perseus_gpu_plan_create(h, segs, nseg, flags, &p);
+	int rc = plan_create_locked(h, segs, nseg, flags, &p);
 	if (rc) return rc;
-	int64_t n = perseus_gpu_plan_run(h, p, 0);   // the plan is freed below, so always synchronous
-	perseus_gpu_plan_destroy(h, p);
+	int64_t n = plan_run_locked(h, p, 0);   // the plan is freed below, so always synchronous
+	cudaStreamSynchronize(h->streams[0]);
+	destroy_plan(p);
 	return n;
 }
 
@@ -734,23 +885,34 @@ int perseus_gpu_input_callback(void *buf, int buf_size, void *extra)
 {
 	perseus_gpu *h = static_cast<perseus_gpu *>(extra);
 	if (!h || !buf || buf_size < 6) return 0;
-	if (h->latched) return 0;                      // a previous failure is waiting to be reported
-	h->stats.callbacks++;
-	if (cudaSetDevice(h->device) != cudaSuccess) { // foreign thread (libusb poll thread): bind first
-		fail(PERSEUS_GPU_CUDAERR, "cudaSetDevice(%d) failed in callback", h->device);
-		latch(h, PERSEUS_GPU_CUDAERR);
-		return 0;
-	}
 	// perseustest.c:443 — only whole samples of THIS transfer count
 	const size_t n = (size_t)buf_size / 6 * 6;
+	std::lock_guard<std::recursive_mutex> lk(h->mu);
+	if (h->latched) {                              // a previous failure is waiting to be reported: count what is lost
+		h->stats.dropped_callbacks++;
+		h->stats.dropped_bytes += n;
+		return 0;
+	}
+	h->stats.callbacks++;
 	int rc = stream_push(h, static_cast<const uint8_t *>(buf), n);
 	if (rc) latch(h, rc);
 	return 0;
 }
 
+int perseus_gpu_poll(perseus_gpu *h)
+{
+	Entry en(h);
+	if (en.rc) return en.rc;
+	if (!h->streaming_ready) return 0;
+	const int rc = submit_if_over_age(h, monotonic_ns());
+	if (rc > 0) h->stats.watchdog_submits++;
+	return rc;
+}
+
 int perseus_gpu_set_sink(perseus_gpu *h, perseus_gpu_sink sink, void *extra)
 {
 	if (!h) return fail(PERSEUS_GPU_NULLHANDLE, "null handle");
+	std::lock_guard<std::recursive_mutex> lk(h->mu);
 	h->sink = sink;
 	h->sink_extra = extra;
 	return 0;
@@ -758,9 +920,9 @@ int perseus_gpu_set_sink(perseus_gpu *h, perseus_gpu_sink sink, void *extra)
 
 int perseus_gpu_stream_to_file(perseus_gpu *h, const char *path)
 {
-	int rc = bind(h);
-	if (rc) return rc;
-	rc = perseus_gpu_flush(h);
+	Entry en(h);
+	if (en.rc) return en.rc;
+	int rc = flush_locked(h);
 	if (rc) return rc;
 	if (h->fout) {
 		FILE *f = h->fout;
@@ -778,25 +940,16 @@ int perseus_gpu_stream_to_file(perseus_gpu *h, const char *path)
 
 int perseus_gpu_flush(perseus_gpu *h)
 {
-	int rc = bind(h);
-	if (rc) return rc;
-	if (h->streaming_ready) {
-		if (h->fill && !h->latched) {
-			rc = submit_slab(h);
-			if (rc) latch(h, rc);
-		}
-		rc = drain_file(h, h->nslabs);   // oldest first, so the file keeps stream order
-		if (rc) latch(h, rc);
-		h->next_to_write = h->cur;       // nothing in flight: the next slab submitted is the oldest
-		if (h->fout) fflush(h->fout);
-	}
-	return perseus_gpu_sync(h);
+	Entry en(h);
+	if (en.rc) return en.rc;
+	return flush_locked(h);
 }
 
 int perseus_gpu_get_stats(perseus_gpu *h, perseus_gpu_stats *out)
 {
 	if (!h) return fail(PERSEUS_GPU_NULLHANDLE, "null handle");
 	if (!out) return fail(PERSEUS_GPU_ERRPARAM, "null stats pointer");
+	std::lock_guard<std::recursive_mutex> lk(h->mu);
 	*out = h->stats;
 	return 0;
 }
@@ -807,6 +960,7 @@ int perseus_gpu_set_tuning(perseus_gpu *h, const perseus_gpu_tuning *t)
 	pg::Tuning r = resolve_tuning(t);
 	int rc = check_tuning(r);
 	if (rc) return rc;
+	std::lock_guard<std::recursive_mutex> lk(h->mu);
 	memcpy(r.tuned, h->tune.tuned, sizeof(r.tuned));   // autotune results survive; explicit fields take precedence anyway
 	h->tune = r;
 	return 0;
@@ -815,6 +969,7 @@ int perseus_gpu_set_tuning(perseus_gpu *h, const perseus_gpu_tuning *t)
 int perseus_gpu_get_geometry(perseus_gpu *h, unsigned flags, int *tile_bytes, int *stages, int *ctas_per_sm)
 {
 	if (!h) return fail(PERSEUS_GPU_NULLHANDLE, "null handle");
+	std::lock_guard<std::recursive_mutex> lk(h->mu);
 	const pg::Geometry g = pg::resolve_geometry(h->tune, flags & 7u);
 	if (tile_bytes) *tile_bytes = g.tile_bytes;
 	if (stages) *stages = g.stages;
@@ -824,9 +979,9 @@ int perseus_gpu_get_geometry(perseus_gpu *h, unsigned flags, int *tile_bytes, in
 
 int perseus_gpu_autotune(perseus_gpu *h, double *gbs_single, double *gbs_fused)
 {
-	int rc = bind(h);
-	if (rc) return rc;
-	rc = perseus_gpu_sync(h);
+	Entry en(h);
+	if (en.rc) return en.rc;
+	int rc = sync_locked(h);
 	if (rc) return rc;
 	const size_t nbytes = (size_t)87381 * 6144;            // 512 MiB of wire: far beyond L2, 0.15-0.3 ms per launch
 	const size_t ns = nbytes / 6;
@@ -838,7 +993,7 @@ int perseus_gpu_autotune(perseus_gpu *h, double *gbs_single, double *gbs_fused)
 	if (e == cudaSuccess) e = cudaMemsetAsync(in, 0x5A, nbytes, st);
 	static const pg::Geometry cand[] = {{12288, 2, 1}, {12288, 3, 1}, {12288, 4, 1}, {12288, 5, 1}, {12288, 6, 1}, {6144, 5, 1},
 	                                    {6144, 6, 1},  {6144, 8, 1},  {18432, 2, 1}, {18432, 3, 1}, {24576, 2, 1}, {12288, 2, 2}};
-	cudaEvent_t e0 = h->events[kEventSlots - 2], e1 = h->events[kEventSlots - 1];
+	cudaEvent_t e0 = h->tev[0], e1 = h->tev[1];
 	double best_gbs[2] = {0.0, 0.0};
 	pg::Geometry best[2] = {};
 	for (int cls = 0; cls < 2 && e == cudaSuccess; ++cls) {
@@ -879,6 +1034,7 @@ int perseus_gpu_get_tuning(perseus_gpu *h, perseus_gpu_tuning *t)
 {
 	if (!h) return fail(PERSEUS_GPU_NULLHANDLE, "null handle");
 	if (!t) return fail(PERSEUS_GPU_ERRPARAM, "null tuning pointer");
+	std::lock_guard<std::recursive_mutex> lk(h->mu);
 	memset(t, 0, sizeof(*t));
 	t->variant = h->tune.variant;
 	t->tile_bytes = h->tune.tile_bytes;
@@ -892,7 +1048,8 @@ int perseus_gpu_get_tuning(perseus_gpu *h, perseus_gpu_tuning *t)
 
 void *perseus_gpu_dev_alloc(perseus_gpu *h, size_t nbytes)
 {
-	if (bind(h)) return nullptr;
+	Entry en(h);
+	if (en.rc) return nullptr;
 	void *p = nullptr;
 	cudaError_t e = cudaMalloc(&p, nbytes ? nbytes : 1);
 	if (e != cudaSuccess) {
@@ -905,15 +1062,16 @@ void *perseus_gpu_dev_alloc(perseus_gpu *h, size_t nbytes)
 
 int perseus_gpu_dev_free(perseus_gpu *h, void *p)
 {
-	int rc = bind(h);
-	if (rc) return rc;
+	Entry en(h);
+	if (en.rc) return en.rc;
 	CU(h, cudaFree(p));
 	return 0;
 }
 
 void *perseus_gpu_host_alloc(perseus_gpu *h, size_t nbytes)
 {
-	if (bind(h)) return nullptr;
+	Entry en(h);
+	if (en.rc) return nullptr;
 	void *p = nullptr;
 	cudaError_t e = cudaHostAlloc(&p, nbytes ? nbytes : 1, cudaHostAllocPortable);
 	if (e != cudaSuccess) {
@@ -926,16 +1084,16 @@ void *perseus_gpu_host_alloc(perseus_gpu *h, size_t nbytes)
 
 int perseus_gpu_host_free(perseus_gpu *h, void *p)
 {
-	int rc = bind(h);
-	if (rc) return rc;
+	Entry en(h);
+	if (en.rc) return en.rc;
 	CU(h, cudaFreeHost(p));
 	return 0;
 }
 
 int perseus_gpu_memcpy(perseus_gpu *h, void *dst, const void *src, size_t nbytes)
 {
-	int rc = bind(h);
-	if (rc) return rc;
+	Entry en(h);
+	if (en.rc) return en.rc;
 	if (nbytes == 0) return 0;
 	CU(h, cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDefault, h->streams[0]));
 	CU(h, cudaStreamSynchronize(h->streams[0]));
@@ -944,8 +1102,8 @@ int perseus_gpu_memcpy(perseus_gpu *h, void *dst, const void *src, size_t nbytes
 
 int perseus_gpu_memset(perseus_gpu *h, void *dev, int byte, size_t nbytes)
 {
-	int rc = bind(h);
-	if (rc) return rc;
+	Entry en(h);
+	if (en.rc) return en.rc;
 	if (nbytes == 0) return 0;
 	CU(h, cudaMemsetAsync(dev, byte, nbytes, h->streams[0]));
 	CU(h, cudaStreamSynchronize(h->streams[0]));
@@ -963,8 +1121,8 @@ void *perseus_gpu_get_stream(perseus_gpu *h, int idx)
 
 int perseus_gpu_event_record(perseus_gpu *h, int slot)
 {
-	int rc = bind(h);
-	if (rc) return rc;
+	Entry en(h);
+	if (en.rc) return en.rc;
 	if (slot < 0 || slot >= kEventSlots) return fail(PERSEUS_GPU_ERRPARAM, "event slot %d not in 0..%d", slot, kEventSlots - 1);
 	CU(h, cudaEventRecord(h->events[slot], h->streams[0]));
 	return 0;
@@ -972,8 +1130,8 @@ int perseus_gpu_event_record(perseus_gpu *h, int slot)
 
 int perseus_gpu_event_elapsed_ms(perseus_gpu *h, int a, int b, float *ms)
 {
-	int rc = bind(h);
-	if (rc) return rc;
+	Entry en(h);
+	if (en.rc) return en.rc;
 	if (a < 0 || a >= kEventSlots || b < 0 || b >= kEventSlots || !ms) return fail(PERSEUS_GPU_ERRPARAM, "bad event slots");
 	CU(h, cudaEventSynchronize(h->events[b]));
 	CU(h, cudaEventElapsedTime(ms, h->events[a], h->events[b]));
@@ -984,34 +1142,25 @@ int perseus_gpu_event_elapsed_ms(perseus_gpu *h, int a, int b, float *ms)
 
 int perseus_gpu_generate(perseus_gpu *h, void *dev_dst, size_t nbytes, int pattern, uint64_t seed, uint64_t byte_offset)
 {
-	int rc = bind(h);
-	if (rc) return rc;
+	Entry en(h);
+	if (en.rc) return en.rc;
 	if (pattern != PERSEUS_SYNTH_RANDOM && pattern != PERSEUS_SYNTH_RAMP) return fail(PERSEUS_GPU_ERRPARAM, "unknown pattern %d", pattern);
 	if (pattern == PERSEUS_SYNTH_RAMP && byte_offset % 6) return fail(PERSEUS_GPU_ERRPARAM, "RAMP byte_offset must be a multiple of 6");
 	if (nbytes && !dev_dst) return fail(PERSEUS_GPU_ERRPARAM, "null destination");
-	cudaError_t e = pg::launch_generate(dev_dst, nbytes, pattern, seed, byte_offset, h->streams[0]);
+	cudaError_t e = pg::launch_generate(dev_dst, nbytes, pattern, seed, byte_offset, h->sm_count, h->streams[0]);
 	if (e != cudaSuccess) return fail(PERSEUS_GPU_CUDAERR, "generate launch failed: %s", cudaGetErrorString(e));
 	h->stats.kernel_launches += nbytes ? 1 : 0;
 	CU(h, cudaStreamSynchronize(h->streams[0]));
 	return 0;
 }
 
-int perseus_synth_fill(void *host_dst, size_t nbytes, int pattern, uint64_t seed, uint64_t byte_offset)
-{
-	if (pattern != PERSEUS_SYNTH_RANDOM && pattern != PERSEUS_SYNTH_RAMP) return fail(PERSEUS_GPU_ERRPARAM, "unknown pattern %d", pattern);
-	if (pattern == PERSEUS_SYNTH_RAMP && byte_offset % 6) return fail(PERSEUS_GPU_ERRPARAM, "RAMP byte_offset must be a multiple of 6");
-	if (nbytes && !host_dst) return fail(PERSEUS_GPU_ERRPARAM, "null destination");
-	pg::host_generate(static_cast<uint8_t *>(host_dst), nbytes, pattern, seed, byte_offset);
-	return 0;
-}
-
 int perseus_gpu_checksum(perseus_gpu *h, const void *dev_words, size_t nwords, uint64_t first_index, uint64_t *sum)
 {
-	int rc = bind(h);
-	if (rc) return rc;
+	Entry en(h);
+	if (en.rc) return en.rc;
 	if (!sum || (nwords && !dev_words)) return fail(PERSEUS_GPU_ERRPARAM, "null argument");
 	if ((uintptr_t)dev_words & 3) return fail(PERSEUS_GPU_ERRPARAM, "words must be 4-byte aligned");
-	cudaError_t e = pg::launch_checksum(dev_words, nwords, first_index, h->d_scratch, h->streams[0]);
+	cudaError_t e = pg::launch_checksum(dev_words, nwords, first_index, h->d_scratch, h->sm_count, h->streams[0]);
 	if (e != cudaSuccess) return fail(PERSEUS_GPU_CUDAERR, "checksum launch failed: %s", cudaGetErrorString(e));
 	h->stats.kernel_launches += nwords ? 1 : 0;
 	CU(h, cudaMemcpyAsync(h->h_scratch, h->d_scratch, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->streams[0]));
@@ -1023,12 +1172,13 @@ int perseus_gpu_checksum(perseus_gpu *h, const void *dev_words, size_t nwords, u
 int perseus_gpu_verify(perseus_gpu *h, const void *dev_in, size_t nbytes, const void *dev_i32, const void *dev_f32, unsigned flags,
                        uint64_t *nmismatch, uint64_t *first_bad_word)
 {
-	int rc = bind(h);
+	Entry en(h);
+	int rc = en.rc;
 	if (rc) return rc;
 	unsigned fmt = 0;
 	rc = resolve_fmt(flags & ~PERSEUS_GPU_ASYNC, dev_i32, dev_f32, &fmt);
 	if (rc) return rc;
-	cudaError_t e = pg::launch_verify(dev_in, nbytes, dev_i32, dev_f32, fmt, h->d_scratch, h->streams[0]);
+	cudaError_t e = pg::launch_verify(dev_in, nbytes, dev_i32, dev_f32, fmt, h->d_scratch, h->sm_count, h->streams[0]);
 	if (e != cudaSuccess) return fail(PERSEUS_GPU_CUDAERR, "verify launch failed: %s", cudaGetErrorString(e));
 	h->stats.kernel_launches += nbytes / 6 ? 1 : 0;
 	CU(h, cudaMemcpyAsync(h->h_scratch, h->d_scratch, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->streams[0]));
@@ -1042,8 +1192,8 @@ int perseus_gpu_verify(perseus_gpu *h, const void *dev_in, size_t nbytes, const 
 
 int perseus_gpu_probe_hbm(perseus_gpu *h, int kind, size_t nbytes, int reps, double *gbs)
 {
-	int rc = bind(h);
-	if (rc) return rc;
+	Entry en(h);
+	if (en.rc) return en.rc;
 	if (kind < 0 || kind > 2 || !gbs || reps < 1 || nbytes < (1u << 20)) return fail(PERSEUS_GPU_ERRPARAM, "bad probe arguments");
 	nbytes -= nbytes % 16;
 	void *a = nullptr, *b = nullptr;
@@ -1057,7 +1207,7 @@ int perseus_gpu_probe_hbm(perseus_gpu *h, int kind, size_t nbytes, int reps, dou
 	cudaStream_t st = h->streams[0];
 	cudaMemsetAsync(a, 0x5A, nbytes, st);
 	double best = 0.0;
-	cudaEvent_t e0 = h->events[kEventSlots - 2], e1 = h->events[kEventSlots - 1];
+	cudaEvent_t e0 = h->tev[0], e1 = h->tev[1];
 	for (int ctas : {2, 4, 8, 16}) {
 		float ms = 0.f;
 		e = pg::launch_probe(kind, a, kind == 2 ? b : a, nbytes, h->sm_count, ctas, st);   // warm
@@ -1078,15 +1228,68 @@ int perseus_gpu_probe_hbm(perseus_gpu *h, int kind, size_t nbytes, int reps, dou
 	return 0;
 }
 
-int perseus_gpu_shard_range(uint64_t total, int nshards, int shard, uint64_t *first, uint64_t *count)
+int perseus_gpu_probe_pcie(perseus_gpu *h, int kind, size_t nbytes, size_t d2h_nbytes, int reps, double *h2d_gbs, double *d2h_gbs)
 {
-	if (nshards < 1 || shard < 0 || shard >= nshards || !first || !count) return fail(PERSEUS_GPU_ERRPARAM, "bad shard arguments");
-	// floor(shard*total/nshards) without overflowing 64 bits
-	const unsigned __int128 t = total;
-	const uint64_t a = (uint64_t)(t * (unsigned)shard / (unsigned)nshards);
-	const uint64_t b = (uint64_t)(t * (unsigned)(shard + 1) / (unsigned)nshards);
-	*first = a;
-	*count = b - a;
+	Entry en(h);
+	if (en.rc) return en.rc;
+	if (d2h_nbytes == 0) d2h_nbytes = nbytes;
+	if (kind < 0 || kind > 2 || reps < 1 || nbytes < (1u << 20) || d2h_nbytes < (1u << 20)) return fail(PERSEUS_GPU_ERRPARAM, "bad probe arguments");
+	int rc = sync_locked(h);
+	if (rc) return rc;
+	const bool up = kind != PERSEUS_GPU_PCIE_D2H, down = kind != PERSEUS_GPU_PCIE_H2D;
+	void *hu = nullptr, *du = nullptr, *hd = nullptr, *dd = nullptr;
+	cudaError_t e = cudaSuccess;
+	if (up) {
+		e = cudaHostAlloc(&hu, nbytes, cudaHostAllocDefault);
+		if (e == cudaSuccess) e = cudaMalloc(&du, nbytes);
+		if (e == cudaSuccess) memset(hu, 0x5A, nbytes);
+	}
+	if (down && e == cudaSuccess) {
+		e = cudaHostAlloc(&hd, d2h_nbytes, cudaHostAllocDefault);
+		if (e == cudaSuccess) e = cudaMalloc(&dd, d2h_nbytes);
+		if (e == cudaSuccess) memset(hd, 0, d2h_nbytes);   // touch the pages before timing
+	}
+	double best_up = 0.0, best_down = 0.0;
+	for (int r = 0; r <= reps && e == cudaSuccess; ++r) {   // r == 0 warms up
+		// both directions are queued before either is waited for, each on its own stream, so in DUPLEX mode they overlap
+		if (up) {
+			e = cudaEventRecord(h->tev[0], h->s_in);
+			if (e == cudaSuccess) e = cudaMemcpyAsync(du, hu, nbytes, cudaMemcpyHostToDevice, h->s_in);
+			if (e == cudaSuccess) e = cudaEventRecord(h->tev[1], h->s_in);
+		}
+		if (down && e == cudaSuccess) {
+			e = cudaEventRecord(h->tev[2], h->s_out);
+			if (e == cudaSuccess) e = cudaMemcpyAsync(hd, dd, d2h_nbytes, cudaMemcpyDeviceToHost, h->s_out);
+			if (e == cudaSuccess) e = cudaEventRecord(h->tev[3], h->s_out);
+		}
+		if (e == cudaSuccess) e = cudaStreamSynchronize(h->s_in);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(h->s_out);
+		float ms = 0.f;
+		if (up && e == cudaSuccess) {
+			e = cudaEventElapsedTime(&ms, h->tev[0], h->tev[1]);
+			const double g = (double)nbytes / (ms * 1e-3) / 1e9;
+			if (r && g > best_up) best_up = g;
+		}
+		if (down && e == cudaSuccess) {
+			e = cudaEventElapsedTime(&ms, h->tev[2], h->tev[3]);
+			const double g = (double)d2h_nbytes / (ms * 1e-3) / 1e9;
+			if (r && g > best_down) best_down = g;
+		}
+		if (e == cudaSuccess) {
+			if (up) h->stats.h2d_bytes += nbytes;
+			if (down) h->stats.d2h_bytes += d2h_nbytes;
+		}
+	}
+	if (hu) cudaFreeHost(hu);
+	if (hd) cudaFreeHost(hd);
+	if (du) cudaFree(du);
+	if (dd) cudaFree(dd);
+	if (e != cudaSuccess) {
+		cudaGetLastError();
+		return fail(PERSEUS_GPU_CUDAERR, "PCIe probe failed: %s", cudaGetErrorString(e));
+	}
+	if (h2d_gbs) *h2d_gbs = best_up;
+	if (d2h_gbs) *d2h_gbs = best_down;
 	return 0;
 }
 

@@ -5,25 +5,31 @@
 //   * a queue of 8 transfers over ONE contiguous pageable ring          perseus-sdr.c:683, perseus-in.c:68,83-91
 //   * per completed transfer: count bytes, deliver only if it is the expected slot AND full
 //     length, otherwise log-and-drop; then expect (idx+1)%8 and re-arm  perseus-in.c:199-216,260-263
+//   * the other completion statuses: TIMED_OUT is logged and the slot re-armed; ERROR / STALL /
+//     NO_DEVICE / OVERFLOW retire the slot for good WITHOUT advancing the expected index   perseus-in.c:218-257
 //   * stop: cancel, wait, report elapsed / kSamples / kS/s              perseus-sdr.c:694-734
 //   * nearest-rate selection over the ten bitstream rates               perseus-sdr.c:776-811
-// What replaces the USB device: the synthetic wire-data generator (kernels.h host_generate), so
+// What replaces the USB device: the synthetic wire-data generator (host_common.h host_generate), so
 // transfer number n of a stream carries bytes [n*size, (n+1)*size) of the synthetic recording.
+// Checked against the reference's own code (perseus-in.c and perseus-sdr.c compiled unmodified over a
+// fake libusb, oracle/_ref) by tests/test_refqueue_cpu.py and tests/test_reflib_cpu.py.
+//
+// No CUDA in this file: it builds with a plain C++ compiler (tools/sanitize.sh runs it under TSAN/ASAN).
 #include "../../include/perseus-gpu.h"
-#include "kernels.h"
+#include "host_common.h"
 
 #include <atomic>
 #include <chrono>
-#include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <initializer_list>
 #include <new>
 #include <thread>
 
 namespace {
 
-int vfail(int code, const char *fmt, ...);
+using pg::fail;
 
 // perseus-sdr.h:282-285 / generate_fpga_code.sh:71-97 — rates encoded in the bitstream file names
 const int kRates[] = {48000, 95000, 96000, 125000, 192000, 250000, 500000, 1000000, 1600000, 2000000};
@@ -41,64 +47,79 @@ struct perseus_vrx {
 	int rate = 0;
 	uint8_t *ring = nullptr;              // PERSEUS_VRX_QUEUE_SIZE * size bytes, pageable on purpose
 	uint32_t size = 0;
-	perseus_input_callback cb = nullptr;
+	perseus_gpu_input_fn cb = nullptr;
 	void *cb_extra = nullptr;
 	int idx_expected = 0;
-	int fifo[PERSEUS_VRX_QUEUE_SIZE] = {0, 1, 2, 3, 4, 5, 6, 7};   // slots in the order they were (re)submitted to the device
-	int fifo_head = 0;
-	uint64_t submitted = 0;               // transfers handed to the "device" so far == stream position
+	// slots in the order they were (re)submitted to the device; a retired slot never comes back (perseus-in.c:222-257)
+	int fifo[PERSEUS_VRX_QUEUE_SIZE] = {0, 1, 2, 3, 4, 5, 6, 7};
+	int fifo_head = 0, fifo_count = PERSEUS_VRX_QUEUE_SIZE;
+	uint64_t submitted = 0;               // transfers the "device" has filled so far == stream position
 	std::atomic<bool> cancelling{false};
 	bool started = false;
 	std::thread worker;
-	Clock::time_point t_start, t_stop;
-	perseus_vrx_stats stats{};
+	Clock::time_point t_start;
+	// written by the delivery thread, read by perseus_vrx_get_stats on the application thread
+	std::atomic<uint64_t> bytes_received{0}, delivered{0}, dropped_short{0}, dropped_sequence{0}, timed_out{0}, retired{0};
+	double elapsed_s = 0.0;               // frozen by stop / run
 };
-
-extern "C" const char *perseus_gpu_errorstr(void);
 
 namespace {
 
-// the message lands in the same thread-local string perseus_gpu_errorstr() returns
-int vfail(int code, const char *fmt, ...)
-{
-	va_list ap;
-	va_start(ap, fmt);
-	vsnprintf(const_cast<char *>(perseus_gpu_errorstr()), 512, fmt, ap);
-	va_end(ap);
-	return code;
-}
-
 int validate_size(const perseus_vrx *v, uint32_t buffersize)
 {
-	if (buffersize > PERSEUS_VRX_MAX_BUFFER) return vfail(PERSEUS_GPU_ERRPARAM, "max libusb bulk buffer size is 16320 bytes");
+	if (buffersize > PERSEUS_VRX_MAX_BUFFER) return fail(PERSEUS_GPU_ERRPARAM, "max libusb bulk buffer size is 16320 bytes");
 	const int maxps = v->cfg.ep_max_packet ? v->cfg.ep_max_packet : 512;
 	if (maxps == 512) {
-		if (buffersize % 6144) return vfail(PERSEUS_GPU_BUFFERSIZE, "buffer size should be an integer multiple of 6144 bytes (1024 I/Q samples)");
+		if (buffersize % 6144) return fail(PERSEUS_GPU_BUFFERSIZE, "buffer size should be an integer multiple of 6144 bytes (1024 I/Q samples)");
 	} else if (maxps == 510) {
-		if (buffersize % 510) return vfail(PERSEUS_GPU_BUFFERSIZE, "buffer size should be an integer multiple of 510 bytes (85 IQ samples)");
+		if (buffersize % 510) return fail(PERSEUS_GPU_BUFFERSIZE, "buffer size should be an integer multiple of 510 bytes (85 IQ samples)");
 	} else {
-		return vfail(PERSEUS_GPU_ERRPARAM, "Unexpected max packet size: %d", maxps);
+		return fail(PERSEUS_GPU_ERRPARAM, "Unexpected max packet size: %d", maxps);
 	}
-	if (buffersize == 0) return vfail(PERSEUS_GPU_BUFFERSIZE, "buffer size is zero");
+	// Deliberate difference: the reference lets 0 through (0 % 6144 == 0, perseus-sdr.c:671) and then spins on
+	// empty transfers; a zero-length stream is refused here.
+	if (buffersize == 0) return fail(PERSEUS_GPU_BUFFERSIZE, "buffer size is zero");
 	return 0;
 }
 
-// One completed transfer in slot `idx` with `actual` bytes: the body of the reference's
-// completion handler for LIBUSB_TRANSFER_COMPLETED.
-void complete_transfer(perseus_vrx *v, int idx, uint32_t actual)
+// What the device does with transfer number `seq` (1-based) of the stream.
+struct Outcome { int status; uint32_t actual; };
+
+Outcome outcome_of(const perseus_vrx *v, uint64_t seq)
 {
-	v->stats.bytes_received += actual;
-	if (idx == v->idx_expected) {
-		if (actual == v->size) {
-			if (v->cb) v->cb(v->ring + (size_t)idx * v->size, (int)v->size, v->cb_extra);
-			v->stats.delivered++;
+	if (v->cfg.fail_at && seq == v->cfg.fail_at) return {(int)v->cfg.fail_status, 0u};
+	if (v->cfg.timeout_every && seq % v->cfg.timeout_every == 0) return {PERSEUS_VRX_STATUS_TIMED_OUT, 0u};
+	if (v->cfg.drop_every && seq % v->cfg.drop_every == 0) return {PERSEUS_VRX_STATUS_COMPLETED, v->size - 6};
+	return {PERSEUS_VRX_STATUS_COMPLETED, v->size};
+}
+
+// The reference's completion handler (perseus-in.c:187-264) for slot `idx`.  Returns true when the slot is
+// re-armed (resubmitted), false when it is retired.
+bool complete_transfer(perseus_vrx *v, int idx, Outcome o)
+{
+	switch (o.status) {
+	case PERSEUS_VRX_STATUS_COMPLETED:
+		v->bytes_received.fetch_add(o.actual, std::memory_order_relaxed);
+		if (idx == v->idx_expected) {
+			if (o.actual == v->size) {
+				if (v->cb) v->cb(v->ring + (size_t)idx * v->size, (int)v->size, v->cb_extra);
+				v->delivered.fetch_add(1, std::memory_order_relaxed);
+			} else {
+				v->dropped_short.fetch_add(1, std::memory_order_relaxed);
+			}
 		} else {
-			v->stats.dropped_short++;
+			v->dropped_sequence.fetch_add(1, std::memory_order_relaxed);
 		}
-	} else {
-		v->stats.dropped_sequence++;
+		break;
+	case PERSEUS_VRX_STATUS_TIMED_OUT:   // logged only; falls out of the switch to the index update and the resubmit
+		v->timed_out.fetch_add(1, std::memory_order_relaxed);
+		break;
+	default:                            // ERROR, STALL, NO_DEVICE, OVERFLOW: slot marked cancelled, early return
+		v->retired.fetch_add(1, std::memory_order_relaxed);
+		return false;
 	}
 	v->idx_expected = (idx + 1) % PERSEUS_VRX_QUEUE_SIZE;
+	return true;
 }
 
 // "Device side": fill slot idx with the next `size` bytes of the synthetic stream.
@@ -127,21 +148,22 @@ int fifo_pop(perseus_vrx *v)
 {
 	const int idx = v->fifo[v->fifo_head];
 	v->fifo_head = (v->fifo_head + 1) % PERSEUS_VRX_QUEUE_SIZE;
+	v->fifo_count--;
 	return idx;
 }
-void fifo_push(perseus_vrx *v, int idx, int free_slots_before)
+void fifo_push(perseus_vrx *v, int idx)
 {
-	// the FIFO always holds QUEUE_SIZE - free_slots_before entries starting at fifo_head
-	v->fifo[(v->fifo_head + PERSEUS_VRX_QUEUE_SIZE - free_slots_before) % PERSEUS_VRX_QUEUE_SIZE] = idx;
+	v->fifo[(v->fifo_head + v->fifo_count) % PERSEUS_VRX_QUEUE_SIZE] = idx;
+	v->fifo_count++;
 }
 
-// Delivers `limit` completions (UINT64_MAX: until cancelled).
+// Delivers `limit` completions (UINT64_MAX: until cancelled, or until every slot has been retired).
 void deliver(perseus_vrx *v, uint64_t limit)
 {
 	uint64_t n = 0;            // completions so far in this run
-	while (n < limit && !v->cancelling.load(std::memory_order_acquire)) {
+	while (n < limit && v->fifo_count > 0 && !v->cancelling.load(std::memory_order_acquire)) {
 		const uint64_t seq = v->submitted + 1;   // 1-based number of the transfer about to complete
-		const bool swap = v->cfg.swap_every && seq % v->cfg.swap_every == 0 && n + 1 < limit;
+		const bool swap = v->cfg.swap_every && seq % v->cfg.swap_every == 0 && n + 1 < limit && v->fifo_count >= 2;
 		const int a = fifo_pop(v);
 		if (swap) {
 			// the two oldest submissions complete in the wrong order; each carries the data of its own stream position
@@ -149,37 +171,25 @@ void deliver(perseus_vrx *v, uint64_t limit)
 			arm_transfer(v, a);
 			arm_transfer(v, b);
 			pace(v, n + 2);
-			const bool a_short = v->cfg.drop_every && seq % v->cfg.drop_every == 0;
-			const bool b_short = v->cfg.drop_every && (seq + 1) % v->cfg.drop_every == 0;
-			complete_transfer(v, b, b_short ? v->size - 6 : v->size);
-			fifo_push(v, b, 2);
-			complete_transfer(v, a, a_short ? v->size - 6 : v->size);
-			fifo_push(v, a, 1);
+			if (complete_transfer(v, b, outcome_of(v, seq + 1))) fifo_push(v, b);
+			if (complete_transfer(v, a, outcome_of(v, seq))) fifo_push(v, a);
 			n += 2;
 			continue;
 		}
 		arm_transfer(v, a);
 		pace(v, n + 1);
-		const bool is_short = v->cfg.drop_every && seq % v->cfg.drop_every == 0;
-		complete_transfer(v, a, is_short ? v->size - 6 : v->size);
-		fifo_push(v, a, 1);
+		if (complete_transfer(v, a, outcome_of(v, seq))) fifo_push(v, a);
 		++n;
 	}
 }
 
-void finish_stats(perseus_vrx *v)
+int setup(perseus_vrx *v, uint32_t buffersize, perseus_gpu_input_fn cb, void *extra)
 {
-	v->stats.elapsed_s = std::chrono::duration<double>(v->t_stop - v->t_start).count();
-	v->stats.ksamples_per_s = v->stats.elapsed_s > 0 ? 1.0 * (double)v->stats.bytes_received / v->stats.elapsed_s / 6000.0 : 0.0;
-}
-
-int setup(perseus_vrx *v, uint32_t buffersize, perseus_input_callback cb, void *extra)
-{
-	if (v->started) return vfail(PERSEUS_GPU_ASYNCSTARTED, "async input already started");
+	if (v->started) return fail(PERSEUS_GPU_ASYNCSTARTED, "async input already started");
 	int rc = validate_size(v, buffersize);
 	if (rc) return rc;
 	uint8_t *ring = static_cast<uint8_t *>(malloc((size_t)PERSEUS_VRX_QUEUE_SIZE * buffersize));
-	if (!ring) return vfail(PERSEUS_GPU_NOMEM, "can't allocate datain buffer");
+	if (!ring) return fail(PERSEUS_GPU_NOMEM, "can't allocate datain buffer");
 	free(v->ring);
 	v->ring = ring;
 	v->size = buffersize;
@@ -189,10 +199,25 @@ int setup(perseus_vrx *v, uint32_t buffersize, perseus_input_callback cb, void *
 	v->submitted = 0;                                                  // every start is a new stream
 	for (int k = 0; k < PERSEUS_VRX_QUEUE_SIZE; ++k) v->fifo[k] = k;   // perseus-in.c:95-96 submits slots 0..7 in order
 	v->fifo_head = 0;
+	v->fifo_count = PERSEUS_VRX_QUEUE_SIZE;
 	v->cancelling.store(false);
-	v->stats = perseus_vrx_stats{};
+	for (std::atomic<uint64_t> *c : {&v->bytes_received, &v->delivered, &v->dropped_short, &v->dropped_sequence, &v->timed_out, &v->retired})
+		c->store(0, std::memory_order_relaxed);
+	v->elapsed_s = 0.0;
 	v->t_start = Clock::now();
 	return 0;
+}
+
+void fill_stats(const perseus_vrx *v, double elapsed_s, perseus_vrx_stats *out)
+{
+	out->bytes_received = v->bytes_received.load(std::memory_order_relaxed);
+	out->delivered = v->delivered.load(std::memory_order_relaxed);
+	out->dropped_short = v->dropped_short.load(std::memory_order_relaxed);
+	out->dropped_sequence = v->dropped_sequence.load(std::memory_order_relaxed);
+	out->timed_out = v->timed_out.load(std::memory_order_relaxed);
+	out->retired = v->retired.load(std::memory_order_relaxed);
+	out->elapsed_s = elapsed_s;
+	out->ksamples_per_s = elapsed_s > 0 ? 1.0 * (double)out->bytes_received / elapsed_s / 6000.0 : 0.0;   // perseus-sdr.c:721-722
 }
 
 }  // namespace
@@ -201,11 +226,11 @@ extern "C" {
 
 int perseus_vrx_get_sampling_rates(int *buf, unsigned int size)
 {
-	if (size == 0 || !buf) return vfail(PERSEUS_GPU_ERRPARAM, "Zero lenght buffer");
+	if (size == 0 || !buf) return fail(PERSEUS_GPU_ERRPARAM, "Zero lenght buffer");
 	for (unsigned i = 0; i < size; ++i) buf[i] = 0;
 	if (size < (unsigned)kNumRates) {
 		for (unsigned i = 0; i < size; ++i) buf[i] = kRates[i];
-		return vfail(PERSEUS_GPU_BUFFERSIZE, "Insufficient buffer size");
+		return fail(PERSEUS_GPU_BUFFERSIZE, "Insufficient buffer size");
 	}
 	for (int i = 0; i < kNumRates; ++i) buf[i] = kRates[i];
 	return 0;
@@ -232,18 +257,23 @@ int perseus_vrx_nearest_rate(int requested)
 
 int perseus_vrx_open(perseus_vrx **out, const perseus_vrx_config *ucfg)
 {
-	if (!out) return vfail(PERSEUS_GPU_ERRPARAM, "null handle pointer");
+	if (!out) return fail(PERSEUS_GPU_ERRPARAM, "null handle pointer");
 	*out = nullptr;
 	perseus_vrx_config cfg{};
 	if (ucfg) {
-		if (ucfg->struct_size < 8 || ucfg->struct_size > sizeof(cfg)) return vfail(PERSEUS_GPU_ERRPARAM, "perseus_vrx_config.struct_size %u not understood", ucfg->struct_size);
+		if (ucfg->struct_size < 8 || ucfg->struct_size > sizeof(cfg)) return fail(PERSEUS_GPU_ERRPARAM, "perseus_vrx_config.struct_size %u not understood", ucfg->struct_size);
 		memcpy(&cfg, ucfg, ucfg->struct_size);
 	}
-	if (cfg.pattern != PERSEUS_SYNTH_RANDOM && cfg.pattern != PERSEUS_SYNTH_RAMP) return vfail(PERSEUS_GPU_ERRPARAM, "unknown pattern %d", cfg.pattern);
+	if (cfg.pattern != PERSEUS_SYNTH_RANDOM && cfg.pattern != PERSEUS_SYNTH_RAMP) return fail(PERSEUS_GPU_ERRPARAM, "unknown pattern %d", cfg.pattern);
 	if (cfg.ep_max_packet != 0 && cfg.ep_max_packet != 512 && cfg.ep_max_packet != 510)
-		return vfail(PERSEUS_GPU_ERRPARAM, "Unexpected max packet size: %d", cfg.ep_max_packet);
+		return fail(PERSEUS_GPU_ERRPARAM, "Unexpected max packet size: %d", cfg.ep_max_packet);
+	if (cfg.fail_at) {
+		const uint32_t st = cfg.fail_status;
+		if (st != PERSEUS_VRX_STATUS_ERROR && st != PERSEUS_VRX_STATUS_STALL && st != PERSEUS_VRX_STATUS_NO_DEVICE && st != PERSEUS_VRX_STATUS_OVERFLOW)
+			return fail(PERSEUS_GPU_ERRPARAM, "fail_status %u is not ERROR, STALL, NO_DEVICE or OVERFLOW", st);
+	}
 	perseus_vrx *v = new (std::nothrow) perseus_vrx();
-	if (!v) return vfail(PERSEUS_GPU_NOMEM, "out of memory");
+	if (!v) return fail(PERSEUS_GPU_NOMEM, "out of memory");
 	v->cfg = cfg;
 	v->rate = perseus_vrx_nearest_rate(cfg.sample_rate ? cfg.sample_rate : 95000);   // perseustest.c:100 default
 	*out = v;
@@ -252,7 +282,7 @@ int perseus_vrx_open(perseus_vrx **out, const perseus_vrx_config *ucfg)
 
 int perseus_vrx_close(perseus_vrx *v)
 {
-	if (!v) return vfail(PERSEUS_GPU_NULLHANDLE, "null descriptor");
+	if (!v) return fail(PERSEUS_GPU_NULLHANDLE, "null descriptor");
 	if (v->started) perseus_vrx_stop_async_input(v);
 	free(v->ring);
 	delete v;
@@ -261,13 +291,13 @@ int perseus_vrx_close(perseus_vrx *v)
 
 int perseus_vrx_get_sampling_rate(perseus_vrx *v)
 {
-	if (!v) return vfail(PERSEUS_GPU_NULLHANDLE, "null descriptor");
+	if (!v) return fail(PERSEUS_GPU_NULLHANDLE, "null descriptor");
 	return v->rate;
 }
 
-int perseus_vrx_start_async_input(perseus_vrx *v, uint32_t buffersize, perseus_input_callback callback, void *cb_extra)
+int perseus_vrx_start_async_input(perseus_vrx *v, uint32_t buffersize, perseus_gpu_input_fn callback, void *cb_extra)
 {
-	if (!v) return vfail(PERSEUS_GPU_NULLHANDLE, "null descriptor");
+	if (!v) return fail(PERSEUS_GPU_NULLHANDLE, "null descriptor");
 	int rc = setup(v, buffersize, callback, cb_extra);
 	if (rc) return rc;
 	v->started = true;
@@ -275,48 +305,40 @@ int perseus_vrx_start_async_input(perseus_vrx *v, uint32_t buffersize, perseus_i
 		v->worker = std::thread([v] { deliver(v, UINT64_MAX); });
 	} catch (...) {
 		v->started = false;
-		return vfail(PERSEUS_GPU_NOMEM, "can't create delivery thread");
+		return fail(PERSEUS_GPU_NOMEM, "can't create delivery thread");
 	}
 	return 0;
 }
 
 int perseus_vrx_stop_async_input(perseus_vrx *v)
 {
-	if (!v) return vfail(PERSEUS_GPU_NULLHANDLE, "null descriptor");
-	if (!v->started) return vfail(PERSEUS_GPU_ASYNCSTARTED, "async input not started");
+	if (!v) return fail(PERSEUS_GPU_NULLHANDLE, "null descriptor");
+	if (!v->started) return fail(PERSEUS_GPU_ASYNCSTARTED, "async input not started");
 	v->cancelling.store(true, std::memory_order_release);
 	if (v->worker.joinable()) v->worker.join();
-	v->t_stop = Clock::now();
+	v->elapsed_s = std::chrono::duration<double>(Clock::now() - v->t_start).count();
 	v->cb = nullptr;
 	v->started = false;
-	finish_stats(v);
 	return 0;
 }
 
-int perseus_vrx_run(perseus_vrx *v, uint32_t buffersize, perseus_input_callback callback, void *cb_extra, uint64_t ntransfers)
+int perseus_vrx_run(perseus_vrx *v, uint32_t buffersize, perseus_gpu_input_fn callback, void *cb_extra, uint64_t ntransfers)
 {
-	if (!v) return vfail(PERSEUS_GPU_NULLHANDLE, "null descriptor");
+	if (!v) return fail(PERSEUS_GPU_NULLHANDLE, "null descriptor");
 	int rc = setup(v, buffersize, callback, cb_extra);
 	if (rc) return rc;
 	deliver(v, ntransfers);
-	v->t_stop = Clock::now();
+	v->elapsed_s = std::chrono::duration<double>(Clock::now() - v->t_start).count();
 	v->cb = nullptr;
-	finish_stats(v);
 	return 0;
 }
 
 int perseus_vrx_get_stats(perseus_vrx *v, perseus_vrx_stats *out)
 {
-	if (!v) return vfail(PERSEUS_GPU_NULLHANDLE, "null descriptor");
-	if (!out) return vfail(PERSEUS_GPU_ERRPARAM, "null stats pointer");
-	if (v->started) {   // live view
-		perseus_vrx_stats s = v->stats;
-		s.elapsed_s = std::chrono::duration<double>(Clock::now() - v->t_start).count();
-		s.ksamples_per_s = s.elapsed_s > 0 ? (double)s.bytes_received / s.elapsed_s / 6000.0 : 0.0;
-		*out = s;
-	} else {
-		*out = v->stats;
-	}
+	if (!v) return fail(PERSEUS_GPU_NULLHANDLE, "null descriptor");
+	if (!out) return fail(PERSEUS_GPU_ERRPARAM, "null stats pointer");
+	// live view while streaming, frozen elapsed time afterwards
+	fill_stats(v, v->started ? std::chrono::duration<double>(Clock::now() - v->t_start).count() : v->elapsed_s, out);
 	return 0;
 }
 

@@ -20,7 +20,7 @@
 // No tensor cores: there is no multiply-accumulate structure to map onto tcgen05.
 #include "kernels.h"
 
-#include <cstring>
+#include <atomic>
 
 namespace pg {
 namespace {
@@ -369,14 +369,6 @@ __global__ void __launch_bounds__(256) unpack24_direct_batch_kernel(const __grid
 }
 
 // ------------------------------------------------------------------ generator / checksum / verify
-__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x)
-{
-	x += 0x9E3779B97F4A7C15ull;
-	x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
-	x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
-	return x ^ (x >> 31);
-}
-
 // Stream word w (8 bytes, little endian) = splitmix64(seed + w); dst[i] is stream byte byte_offset + i.
 __global__ void __launch_bounds__(256) generate_random_kernel(uint8_t *dst, uint64_t nbytes, uint64_t seed, uint64_t byte_offset)
 {
@@ -396,15 +388,6 @@ __global__ void __launch_bounds__(256) generate_random_kernel(uint8_t *dst, uint
 			}
 		}
 	}
-}
-
-__host__ __device__ __forceinline__ void ramp_sample(uint64_t v64, uint8_t *p)
-{
-	const uint32_t v = (uint32_t)v64;
-	const uint32_t i24 = v & 0xFFFFFFu;
-	const uint32_t q24 = (uint32_t)(v * 2654435761u) >> 8;
-	p[0] = (uint8_t)i24; p[1] = (uint8_t)(i24 >> 8); p[2] = (uint8_t)(i24 >> 16);
-	p[3] = (uint8_t)q24; p[4] = (uint8_t)(q24 >> 8); p[5] = (uint8_t)(q24 >> 16);
 }
 
 __global__ void __launch_bounds__(256) generate_ramp_kernel(uint8_t *dst, uint64_t nsamples, uint64_t first_sample)
@@ -496,18 +479,30 @@ cudaError_t launch_stream_inst(const StreamParams &p, int grid, cudaStream_t str
 {
 	auto kern = unpack24_stream_kernel<FMT, TILE, ST, BATCHED>;
 	const size_t smem = (size_t)p.stages * (TILE + kStagePad);
-	static bool configured[64] = {};                      // per instantiation: devices whose smem limit is raised
+	if (smem > 201 * 1024) return cudaErrorInvalidValue;
+	// per instantiation: devices whose dynamic shared-memory limit has been raised.  Handles on different threads
+	// race here only to do the same idempotent call; the flags are atomic so the race is defined.
+	static std::atomic<bool> configured[64];
+	constexpr int kMaxSmem = kMaxStages * (TILE + kStagePad) > 201 * 1024 ? 201 * 1024 : kMaxStages * (TILE + kStagePad);
 	int dev = 0;
 	cudaGetDevice(&dev);
-	if (dev < 0 || dev >= 64 || !configured[dev]) {
-		constexpr int kMaxSmem = kMaxStages * (TILE + kStagePad) > 201 * 1024 ? 201 * 1024 : kMaxStages * (TILE + kStagePad);
-		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-		if (e != cudaSuccess) return e;
-		if (dev >= 0 && dev < 64) configured[dev] = true;
+	const bool tracked = dev >= 0 && dev < 64;
+	for (int attempt = 0; attempt < 2; ++attempt) {
+		if (!tracked || !configured[dev].load(std::memory_order_acquire)) {
+			cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+			if (e != cudaSuccess) return e;
+			if (tracked) configured[dev].store(true, std::memory_order_release);
+		}
+		kern<<<grid, kConsumerThreads + kProducerThreads, smem, stream>>>(p);
+		const cudaError_t e = cudaGetLastError();
+		// cudaDeviceReset() by the host application drops the raised limit behind our back: set it again, once
+		if (e == cudaErrorInvalidValue && attempt == 0 && tracked && smem > 48 * 1024) {
+			configured[dev].store(false, std::memory_order_release);
+			continue;
+		}
+		return e;
 	}
-	if (smem > 201 * 1024) return cudaErrorInvalidValue;
-	kern<<<grid, kConsumerThreads + kProducerThreads, smem, stream>>>(p);
-	return cudaGetLastError();
+	return cudaErrorInvalidValue;
 }
 
 template <unsigned FMT, int TILE, bool BATCHED>
@@ -633,47 +628,54 @@ cudaError_t launch_unpack(const void *in, size_t nbytes, void *out_i32, void *ou
 	return e;
 }
 
-cudaError_t launch_unpack_batch(const SegDesc *d_segs, const TileRef *d_tiles, uint64_t ntiles, int tile_bytes, unsigned fmt,
-                                bool all_aligned, const Tuning &t, int sm_count, cudaStream_t stream, int *launches)
+cudaError_t launch_unpack_batch(const SegDesc *d_segs, const TileRef *d_tiles_stream, uint64_t ntiles_stream,
+                                const TileRef *d_tiles_direct, uint64_t ntiles_direct, int tile_bytes, unsigned fmt,
+                                const Tuning &t, int sm_count, cudaStream_t stream, int *launches)
 {
 	*launches = 0;
-	if (ntiles == 0) return cudaSuccess;
-	cudaError_t e;
 	const Geometry g = resolve_geometry(t, fmt);
-	if (all_aligned && t.variant != 2) {
+	if (t.variant == 2) {   // A/B: everything through the register-only kernel (the caller put every tile in the direct list)
+		if (ntiles_stream) return cudaErrorInvalidValue;
+	}
+	if (ntiles_stream) {
 		StreamParams p{};
 		p.segs = d_segs;
-		p.tiles = d_tiles;
-		p.ntiles = ntiles;
+		p.tiles = d_tiles_stream;
+		p.ntiles = ntiles_stream;
 		p.stages = g.stages;
 		if ((size_t)g.stages * tile_bytes > 200 * 1024) p.stages = (int)(200 * 1024 / tile_bytes);
-		e = launch_stream_fmt<true>(p, fmt, tile_bytes, t.store_mode, persistent_grid(ntiles, sm_count, g.ctas_per_sm), stream);
-	} else {
+		cudaError_t e = launch_stream_fmt<true>(p, fmt, tile_bytes, t.store_mode, persistent_grid(ntiles_stream, sm_count, g.ctas_per_sm), stream);
+		if (e != cudaSuccess) return e;
+		++*launches;
+	}
+	if (ntiles_direct) {
 		DirectParams p{};
 		p.segs = d_segs;
-		p.tiles = d_tiles;
-		p.ntiles = ntiles;
+		p.tiles = d_tiles_direct;
+		p.ntiles = ntiles_direct;
 		p.tile_bytes = tile_bytes;
-		e = launch_direct_batch_fmt(p, fmt, persistent_grid(ntiles, sm_count, 16), stream);
+		cudaError_t e = launch_direct_batch_fmt(p, fmt, persistent_grid(ntiles_direct, sm_count, 16), stream);
+		if (e != cudaSuccess) return e;
+		++*launches;
 	}
-	if (e == cudaSuccess) *launches = 1;
-	return e;
+	return cudaSuccess;
 }
 
-cudaError_t launch_generate(void *dst, size_t nbytes, int pattern, uint64_t seed, uint64_t byte_offset, cudaStream_t stream)
+cudaError_t launch_generate(void *dst, size_t nbytes, int pattern, uint64_t seed, uint64_t byte_offset, int sm_count, cudaStream_t stream)
 {
 	if (nbytes == 0) return cudaSuccess;
+	const uint64_t max_blocks = (uint64_t)sm_count * 32;
 	if (pattern == 0) {
 		const uint64_t nwords = (nbytes + 15) / 8;
 		uint64_t blocks = (nwords + 255) / 256;
-		if (blocks > 148 * 32) blocks = 148 * 32;
+		if (blocks > max_blocks) blocks = max_blocks;
 		generate_random_kernel<<<(int)blocks, 256, 0, stream>>>(static_cast<uint8_t *>(dst), nbytes, seed, byte_offset);
 	} else if (pattern == 1) {
 		if (byte_offset % 6) return cudaErrorInvalidValue;
 		const uint64_t ns = nbytes / 6;
 		if (ns) {
 			uint64_t blocks = (ns + 255) / 256;
-			if (blocks > 148 * 32) blocks = 148 * 32;
+			if (blocks > max_blocks) blocks = max_blocks;
 			generate_ramp_kernel<<<(int)blocks, 256, 0, stream>>>(static_cast<uint8_t *>(dst), ns, byte_offset / 6);
 		}
 		if (nbytes % 6) {
@@ -686,26 +688,26 @@ cudaError_t launch_generate(void *dst, size_t nbytes, int pattern, uint64_t seed
 	return cudaGetLastError();
 }
 
-cudaError_t launch_checksum(const void *words, size_t nwords, uint64_t first_index, unsigned long long *d_sum, cudaStream_t stream,
-                            bool accumulate)
+cudaError_t launch_checksum(const void *words, size_t nwords, uint64_t first_index, unsigned long long *d_sum, int sm_count,
+                            cudaStream_t stream, bool accumulate)
 {
 	cudaError_t e = accumulate ? cudaSuccess : cudaMemsetAsync(d_sum, 0, sizeof(unsigned long long), stream);
 	if (e != cudaSuccess || nwords == 0) return e;
 	uint64_t blocks = (nwords + 256 * 8 - 1) / (256 * 8);
-	if (blocks > 148 * 16) blocks = 148 * 16;
+	if (blocks > (uint64_t)sm_count * 16) blocks = (uint64_t)sm_count * 16;
 	checksum32_kernel<<<(int)blocks, 256, 0, stream>>>(static_cast<const uint32_t *>(words), nwords, first_index, d_sum);
 	return cudaGetLastError();
 }
 
 cudaError_t launch_verify(const void *in, size_t nbytes, const void *out_i32, const void *out_f32, unsigned fmt,
-                          unsigned long long *d_result, cudaStream_t stream)
+                          unsigned long long *d_result, int sm_count, cudaStream_t stream)
 {
 	const unsigned long long init[2] = {0ull, ~0ull};
 	cudaError_t e = cudaMemcpyAsync(d_result, init, sizeof(init), cudaMemcpyHostToDevice, stream);
 	const uint64_t ns = nbytes / 6;
 	if (e != cudaSuccess || ns == 0) return e;
 	uint64_t blocks = (ns + 255) / 256;
-	if (blocks > 148 * 32) blocks = 148 * 32;
+	if (blocks > (uint64_t)sm_count * 32) blocks = (uint64_t)sm_count * 32;
 	verify_kernel<<<(int)blocks, 256, 0, stream>>>(static_cast<const uint8_t *>(in), ns, static_cast<const uint32_t *>(out_i32),
 	                                               static_cast<const uint32_t *>(out_f32), fmt, d_result);
 	return cudaGetLastError();
@@ -722,30 +724,6 @@ cudaError_t launch_probe(int kind, const void *src, void *dst, size_t nbytes, in
 	default: return cudaErrorInvalidValue;
 	}
 	return cudaGetLastError();
-}
-
-void host_generate(uint8_t *dst, size_t nbytes, int pattern, uint64_t seed, uint64_t byte_offset)
-{
-	if (pattern == 1) {
-		const size_t ns = nbytes / 6;
-		for (size_t k = 0; k < ns; ++k) ramp_sample(byte_offset / 6 + k, dst + 6 * k);
-		memset(dst + ns * 6, 0, nbytes - ns * 6);
-		return;
-	}
-	size_t i = 0;
-	// head: up to the next 8-byte stream-word boundary
-	while (i < nbytes && ((byte_offset + i) & 7)) {
-		const uint64_t pos = byte_offset + i;
-		dst[i++] = (uint8_t)(splitmix64(seed + (pos >> 3)) >> (8 * (pos & 7)));
-	}
-	for (; i + 8 <= nbytes; i += 8) {
-		const uint64_t word = splitmix64(seed + ((byte_offset + i) >> 3));   // little-endian host
-		memcpy(dst + i, &word, 8);
-	}
-	for (; i < nbytes; ++i) {
-		const uint64_t pos = byte_offset + i;
-		dst[i] = (uint8_t)(splitmix64(seed + (pos >> 3)) >> (8 * (pos & 7)));
-	}
 }
 
 }  // namespace pg

@@ -32,23 +32,28 @@ def test_header_is_plain_c_and_cites_reference():
         src = f"{td}/t.c"
         open(src, "w").write('#include "perseus-gpu.h"\n'
                              "static int cb(void *b, int n, void *e) { (void)b; (void)n; (void)e; return 0; }\n"
-                             "int main(void) { perseus_input_callback f = cb; perseus_input_callback g = perseus_gpu_input_callback;"
+                             "int main(void) { perseus_gpu_input_fn f = cb; perseus_gpu_input_fn g = perseus_gpu_input_callback;"
                              " return f == g; }\n")
         subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", str(ROOT / "include"), "-c", src, "-o", f"{td}/t.o"],
                        check=True)
 
 
-def test_header_coexists_with_the_reference_header():
-    """INTEGRATION.md step 1 compiles: the reference's real perseus-sdr.h (libusb stubbed), then perseus-gpu.h, and
-    perseus_gpu_input_callback handed to perseus_start_async_input's own prototype (perseus-sdr.h:247-248)."""
+@pytest.mark.parametrize("order", [("perseus-sdr.h", "perseus-gpu.h"), ("perseus-gpu.h", "perseus-sdr.h")])
+def test_header_coexists_with_the_reference_header(order):
+    """INTEGRATION.md step 1 compiles with the two headers in EITHER order: the reference's real perseus-sdr.h (libusb
+    stubbed) and perseus-gpu.h, perseus_gpu_input_callback handed to perseus_start_async_input's own prototype
+    (perseus-sdr.h:247-248), and a perseus_input_callback handed to the virtual receiver's prototype.  -pedantic
+    -Werror: a re-declared typedef would be an error in C99."""
     import os
     if not os.path.exists("/root/reference/perseus-sdr.h"):
         pytest.skip("/root/reference not mounted")
     with tempfile.TemporaryDirectory() as td:
-        open(f"{td}/t.c", "w").write('#include "perseus-sdr.h"\n#include "perseus-gpu.h"\n'
+        open(f"{td}/t.c", "w").write(f'#include "{order[0]}"\n#include "{order[1]}"\n'
                                      "int start(perseus_descr *d, perseus_gpu *g)\n"
-                                     "{ return perseus_start_async_input(d, 6144, perseus_gpu_input_callback, g); }\n")
-        subprocess.run(["gcc", "-std=gnu99", "-Wall", "-Werror=incompatible-pointer-types", "-I", str(ROOT / "oracle" / "stub"),
+                                     "{ return perseus_start_async_input(d, 6144, perseus_gpu_input_callback, g); }\n"
+                                     "int vstart(perseus_vrx *v, perseus_input_callback cb)\n"
+                                     "{ perseus_gpu_input_fn same = cb; return perseus_vrx_start_async_input(v, 6144, same, 0); }\n")
+        subprocess.run(["gcc", "-std=gnu99", "-pedantic", "-Wall", "-Werror", "-Wno-variadic-macros", "-I", str(ROOT / "oracle" / "stub"),
                         "-I", "/root/reference", "-I", str(ROOT / "include"), "-c", f"{td}/t.c", "-o", f"{td}/t.o"], check=True)
 
 

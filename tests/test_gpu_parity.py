@@ -316,6 +316,80 @@ def test_overlapped_checksum_flag(pg, coracle):
         h.dev_free(d_in)
 
 
+def test_checksum_totals_restart_even_for_an_empty_call(pg, coracle):
+    """perseus_gpu_get_checksums reports the most recent CHECKSUM call -- also when that call held no whole sample."""
+    wire = coracle.synth_random(6144 * 3, seed=5)
+    with pg.PerseusGpu(device=0) as h, DevBuf(h, wire.size) as din, DevBuf(h, wire.size // 6 * 8) as di:
+        h.memcpy(din.p, wire.ctypes.data, wire.size)
+        h.unpack(din.p, wire.size, di.p, None, pg.OUT_INT32 | pg.CHECKSUM)
+        assert h.get_checksums() == (coracle.checksum32(coracle.unpack(wire, O.MODE_I32)), 0)
+        assert h.unpack(din.p, 5, di.p, None, pg.OUT_INT32 | pg.CHECKSUM) == 0
+        assert h.get_checksums() == (0, 0)
+
+
+def test_event_slots_belong_to_the_caller(pg, coracle):
+    """All 32 timing slots are the caller's: autotune and the probes time with private events."""
+    with pg.PerseusGpu(device=0) as h, DevBuf(h, 6144 * 64) as din, DevBuf(h, 8192 * 64) as di:
+        h.event_record(30)
+        h.unpack(din.p, din.n, di.p, None, pg.OUT_INT32)
+        h.event_record(31)
+        before = h.event_elapsed_ms(30, 31)
+        h.probe_hbm(0, 64 << 20, 2)
+        h.autotune()
+        h.probe_pcie(pg.PCIE_DUPLEX, 8 << 20, 0, 1)
+        assert h.event_elapsed_ms(30, 31) == before > 0
+
+
+def test_pcie_probe_reports_both_directions(pg):
+    with pg.PerseusGpu(device=0) as h:
+        up, none = h.probe_pcie(pg.PCIE_H2D, 64 << 20)
+        none2, down = h.probe_pcie(pg.PCIE_D2H, 64 << 20)
+        dup_up, dup_down = h.probe_pcie(pg.PCIE_DUPLEX, 48 << 20, 128 << 20)
+        assert none == none2 == 0.0 and 5 < up < 70 and 5 < down < 70, (up, down)       # PCIe Gen4/5 x16 territory
+        assert 0.3 * up < dup_up <= 1.05 * up and 0.3 * down < dup_down <= 1.05 * down, (up, down, dup_up, dup_down)
+        with pytest.raises(pg.PerseusGpuError):
+            h.probe_pcie(7, 64 << 20)
+
+
+@pytest.mark.parametrize("slots,chunk", [(2, 48 * 500), (3, 48 * 1000), (5, 48 * 333), (8, 6144 * 7)])
+def test_host_pointer_pipeline_rotates_its_slots(pg, coracle, slots, chunk):
+    """perseus_gpu_unpack with host pointers is a three-stream pipeline over `stage_slots` staging slots; with small chunks
+    every slot is reused many times, across back-to-back ASYNC calls too.  Every pointer-kind combination stays exact."""
+    wire = coracle.synth_random(chunk * 23 + 510 + 4, seed=slots)
+    ns = wire.size // 6
+    want_i = coracle.unpack(wire, O.MODE_I32).view(np.uint32).reshape(-1)
+    want_f = coracle.unpack(wire, O.MODE_F32).view(np.uint32).reshape(-1)
+    with pg.PerseusGpu(device=0, stage_slots=slots, chunk_bytes=chunk) as h:
+        pin = h.host_alloc(wire.size)
+        C.memmove(pin, wire.ctypes.data, wire.size)
+        po_i, po_f = h.host_alloc(ns * 8), h.host_alloc(ns * 8)
+        d_in = h.to_device(wire)
+        d_i, d_f = h.dev_alloc(ns * 8), h.dev_alloc(ns * 8)
+        page_i, page_f = np.zeros(ns * 2, np.uint32), np.zeros(ns * 2, np.uint32)
+        host = lambda p: np.ctypeslib.as_array((C.c_uint32 * (ns * 2)).from_address(p))
+        F = pg.OUT_INT32 | pg.OUT_FLOAT
+        # pinned in -> pinned out, twice back to back without a sync in between (slot events carry over)
+        h.unpack(pin, wire.size, po_i, po_f, F | pg.ASYNC)
+        h.unpack(pin, wire.size, po_i, po_f, F | pg.ASYNC)
+        h.sync()
+        assert np.array_equal(host(po_i), want_i) and np.array_equal(host(po_f), want_f)
+        # pageable in -> device out;  device in -> pageable out;  pinned in -> (device int32, pinned float)
+        h.unpack(wire.ctypes.data, wire.size, d_i, d_f, F)
+        assert np.array_equal(h.to_host(d_i, ns * 8, np.uint32), want_i) and np.array_equal(h.to_host(d_f, ns * 8, np.uint32), want_f)
+        h.unpack(d_in, wire.size, page_i.ctypes.data, page_f.ctypes.data, F)
+        assert np.array_equal(page_i, want_i) and np.array_equal(page_f, want_f)
+        h.memset(d_i, 0, ns * 8); C.memset(po_f, 0, ns * 8)
+        h.unpack(pin, wire.size, d_i, po_f, F | pg.CHECKSUM)
+        assert np.array_equal(h.to_host(d_i, ns * 8, np.uint32), want_i) and np.array_equal(host(po_f), want_f)
+        assert h.get_checksums() == (coracle.checksum32(want_i), coracle.checksum32(want_f))
+        st = h.stats()
+        assert st["h2d_bytes"] == 4 * (wire.size // 6 * 6) + wire.size and st["d2h_bytes"] >= 2 * 2 * ns * 8 + 2 * ns * 8 + ns * 8
+        for p_ in (pin, po_i, po_f):
+            h.host_free(p_)
+        for p_ in (d_in, d_i, d_f):
+            h.dev_free(p_)
+
+
 def test_autotune_measures_and_keeps_a_geometry(pg, coracle):
     with pg.PerseusGpu(device=0) as h:
         assert h.get_geometry(pg.OUT_FLOAT) == {"tile_bytes": 12288, "stages": 4, "ctas_per_sm": 1}              # B200 defaults
@@ -459,6 +533,38 @@ def test_batch_plan_edge_cases(pg, gpu, coracle):
     with pytest.raises(pg.PerseusGpuError) as e:
         gpu.unpack_batch([(devs[0][0], 6144, None, None)], pg.OUT_INT32)          # output missing
     assert e.value.code == pg.ERR["ERRPARAM"]
+
+
+def test_batch_with_misaligned_receivers_splits_by_alignment(pg, gpu, coracle):
+    """Outputs that are only 4-byte aligned cannot take 16-byte stores.  Only THOSE receivers' tiles go to the
+    register-only kernel (a second launch); everyone else stays on the bulk-copy pipeline."""
+    sizes = [6144 * (20 + 7 * r) + (510 if r == 3 else 0) for r in range(12)]
+    odd = {5: 4, 7: 8, 9: 12}                          # receiver -> byte offset of its outputs
+    wires = [coracle.synth_random(n, seed=7000 + r) for r, n in enumerate(sizes)]
+    flags = pg.OUT_INT32 | pg.OUT_FLOAT
+    bufs, segs = [], []
+    for r, w in enumerate(wires):
+        din = DevBuf(gpu, w.size + 64); di = DevBuf(gpu, w.size // 6 * 8 + 64); df = DevBuf(gpu, w.size // 6 * 8 + 64)
+        gpu.memcpy(din.p + (r % 3), w.ctypes.data, w.size)          # wire pointers at any alignment, as always
+        gpu.memset(di.p, 0x5A, di.n); gpu.memset(df.p, 0x5A, df.n)
+        bufs.append((din, di, df))
+        segs.append((din.p + (r % 3), w.size, di.p + odd.get(r, 0), df.p + odd.get(r, 0)))
+    l0 = gpu.stats()["kernel_launches"]
+    assert gpu.unpack_batch(segs, flags) == sum(n // 6 for n in sizes)
+    assert gpu.stats()["kernel_launches"] == l0 + 2                  # pipeline launch + direct launch
+    for r, (w, (din, di, df)) in enumerate(zip(wires, bufs)):
+        ns, o = w.size // 6, odd.get(r, 0)
+        for d, m in ((di, O.MODE_I32), (df, O.MODE_F32)):
+            raw = gpu.to_host(d.p, d.n, np.uint8)
+            assert np.array_equal(raw[o:o + ns * 8].copy().view(np.uint32), coracle.unpack(w, m).view(np.uint32).reshape(-1)), r
+            assert (raw[:o] == 0x5A).all() and (raw[o + ns * 8:] == 0x5A).all(), r
+    # all receivers misaligned -> one (direct) launch; none -> one (pipeline) launch
+    l0 = gpu.stats()["kernel_launches"]
+    gpu.unpack_batch([(a, n, oi + 4, of + 4) for (a, n, oi, of) in segs if oi % 16 == 0 and n > 64], flags)
+    assert gpu.stats()["kernel_launches"] == l0 + 1
+    for t in bufs:
+        for b in t:
+            gpu.dev_free(b.p)
 
 
 def test_cfg3_full_size_1024_receivers_one_launch(pg, gpu, coracle):
@@ -623,7 +729,7 @@ def test_streaming_latency_bound_submits_partial_slabs(pg, coracle):
     """A real receiver delivers a 6144-byte transfer every 10.8 ms at 95 kS/s: slabs must go out on time, not when full."""
     import time
     wire = coracle.synth_random(6144 * 6, seed=17).reshape(6, 6144)
-    with pg.PerseusGpu(device=0, stream_flags=pg.OUT_FLOAT, slab_bytes=8 << 20, max_latency_us=2000) as h:
+    with pg.PerseusGpu(device=0, stream_flags=pg.OUT_FLOAT, slab_bytes=8 << 20, max_latency_us=2000, options=pg.OPT_NO_WATCHDOG) as h:
         blocks = []
         h.set_sink(lambda blk, extra: blocks.append((blk.contents.first_sample, blk.contents.nsamples, blk.contents.dev_f32)))
         for k in range(6):
@@ -643,6 +749,75 @@ def test_streaming_latency_bound_submits_partial_slabs(pg, coracle):
         assert blocks == []
         h.flush()
         assert blocks == [3 * 1024]
+
+
+def test_latency_bound_holds_without_a_following_callback(pg, coracle):
+    """The stream stalls after three transfers (USB error, or the tail before perseus_stop_async_input): the partial slab
+    must still reach the device within max_latency_us -- by the handle's watchdog thread, or by perseus_gpu_poll when the
+    application disabled the watchdog."""
+    import time
+    wire = coracle.synth_random(6144 * 3, seed=23).reshape(3, 6144)
+    want = coracle.unpack(wire.reshape(-1), O.MODE_F32).view(np.uint32).reshape(-1)
+    bound = 0.020
+    with pg.PerseusGpu(device=0, stream_flags=pg.OUT_FLOAT, slab_bytes=8 << 20, max_latency_us=int(bound * 1e6)) as h:
+        blocks = []
+        h.set_sink(lambda blk, extra: blocks.append((time.perf_counter(), blk.contents.first_sample, blk.contents.nsamples, blk.contents.dev_f32)))
+        t0 = time.perf_counter()
+        for k in range(3):
+            h.input_callback(wire[k].ctypes.data, 6144)
+        assert blocks == []                               # not full, not over age: nothing submitted yet
+        while not blocks and time.perf_counter() - t0 < 1.0:
+            time.sleep(0.001)                             # NO further callback, no flush
+        assert len(blocks) == 1, "the watchdog did not submit the partial slab"
+        t, first, n, dev = blocks[0]
+        assert (first, n) == (0, 3 * 1024) and bound * 0.9 <= t - t0 < bound + 0.015, t - t0
+        h.sync()
+        assert np.array_equal(h.to_host(dev, n * 8, np.uint32), want)
+        st = h.stats()
+        assert st["watchdog_submits"] == 1 and st["slabs"] == 1
+        # the stream resumes: sample numbering continues, the watchdog goes back to sleep
+        h.input_callback(wire[0].ctypes.data, 6144)
+        h.flush()
+        assert [(b[1], b[2]) for b in blocks] == [(0, 3072), (3072, 1024)]
+    with pg.PerseusGpu(device=0, stream_flags=pg.OUT_FLOAT, slab_bytes=8 << 20, max_latency_us=int(bound * 1e6),
+                       options=pg.OPT_NO_WATCHDOG) as h:
+        blocks = []
+        h.set_sink(lambda blk, extra: blocks.append((blk.contents.first_sample, blk.contents.nsamples, blk.contents.dev_f32)))
+        for k in range(3):
+            h.input_callback(wire[k].ctypes.data, 6144)
+        assert h.poll() == 0                              # not over age yet
+        time.sleep(bound * 3)
+        assert blocks == []                               # nobody is watching: that is what the option asks for
+        assert h.poll() == 1 and len(blocks) == 1 and h.poll() == 0
+        h.sync()
+        assert np.array_equal(h.to_host(blocks[0][2], 3072 * 8, np.uint32), want)
+        assert h.stats()["watchdog_submits"] == 1
+
+
+@pytest.mark.skipif(not O.Ref.available(), reason="oracle/_ref not built")
+def test_cfg1_95k_paced_float_file_equals_reference(pg, coracle, tmp_path):
+    """BASELINE config 1 on the GPU as specified: perseus95k24v31 (95 000 S/s), NBUF=6 x 1024-byte buffers = 6144-byte
+    transfers (perseustest.c:100-102,349), float output (-p), paced in real time, the handle's DEFAULT configuration
+    (8 MiB slabs, 50 ms latency bound, watchdog).  A transfer arrives every 10.8 ms, so slabs are cut by time, not by
+    size.  The file must equal what the reference's own float callback writes for the delivered transfers."""
+    import time
+    path = tmp_path / "perseusdata"
+    with pg.PerseusGpu(device=0, stream_flags=pg.OUT_FLOAT) as h:
+        h.stream_to_file(str(path))
+        v = pg.VirtualReceiver(sample_rate=95000, realtime=True, seed=95)
+        assert v.sample_rate == 95000 and pg.bitstream_name(v.sample_rate) == "perseus95k24v31"
+        v.start_async_input(6 * 1024, *h.callback)
+        time.sleep(0.6)
+        st = v.stop_async_input()
+        mid = h.stats()
+        h.flush()
+        h.stream_to_file(None)
+        v.close()
+        n = st["delivered"]
+        assert 45 <= n <= 65 and 80 < st["ksamples_per_s"] < 110, st       # 0.6 s at 92.8 transfers/s
+        assert mid["slabs"] >= 8 and mid["callbacks"] == n, mid            # ~one slab per 50 ms, long before any flush
+    wire = coracle.synth_random(n * 6144, seed=95)
+    assert path.read_bytes() == O.Ref().unpack(wire, O.MODE_F32, chunk=6144).tobytes()
 
 
 def test_two_handles_on_two_threads(pg, coracle):
@@ -707,7 +882,10 @@ def test_callback_errors_are_latched_and_surface_at_flush(pg, coracle):
     h = pg.PerseusGpu(device=0, slab_bytes=1 << 44, nslabs=2)            # 16 TiB pinned slabs cannot be allocated
     buf = coracle.synth_random(6144, seed=1)
     assert h.input_callback(buf.ctypes.data, 6144) == 0
-    assert h.input_callback(buf.ctypes.data, 6144) == 0                  # further transfers are dropped quietly
+    assert h.input_callback(buf.ctypes.data, 6144) == 0                  # further transfers are dropped, and counted
+    assert h.input_callback(buf.ctypes.data, 6000 + 5) == 0
+    st = h.stats()
+    assert (st["callbacks"], st["dropped_callbacks"], st["dropped_bytes"]) == (1, 2, 6144 + 6000)
     with pytest.raises(pg.PerseusGpuError) as e:
         h.flush()
     assert e.value.code == pg.ERR["CUDAERR"] and "cudaHostAlloc" in e.value.msg
