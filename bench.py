@@ -383,20 +383,24 @@ def workload_cfg3(cx, steps, warmup):
     ms = cx.timed(lambda: h.plan_run(plan, pg.ASYNC), steps, warmup, sampler)
     launches = h.stats()["kernel_launches"] - l0 - warmup
     h.plan_destroy(plan)
-    # the same batch with ONE receiver's outputs only 4-byte aligned (the last 2 MS/s receiver, moved 4 bytes up):
-    # its tiles alone take the register-only kernel, as a second launch
+    # the same batch with ONE receiver's outputs off 16-byte alignment (the last 2 MS/s receiver, its segment shortened by
+    # one transfer and its outputs moved up inside their own range): by 8 bytes -- the natural alignment of an {I,Q}
+    # array; still the pipeline, pre-rolled by one sample -- and by 4 bytes, which only the register-only kernel can
+    # serve: that receiver's tiles alone go to it, as a second launch
     odd = max(r for r in range(len(nbufs)) if nbufs[r] == max(nbufs))
-    segs2 = list(segs)
-    if odd == len(segs) - 1:
+    misaligned = {}
+    for shift in (8, 4):
+        segs2 = list(segs)
         a, n, oi, of = segs[odd]
-        segs2[odd] = (a, n, oi + 4, of + 4)
-    else:                                                               # not the last segment: shift it inside its own range
-        a, n, oi, of = segs[odd]
-        segs2[odd] = (a, n - BUF, oi + 4, of + 4)
-    plan2 = h.plan_create(segs2, flags)
-    ms_odd = cx.timed(lambda: h.plan_run(plan2, pg.ASYNC), steps, warmup)
-    h.plan_destroy(plan2)
-    ns2 = sum(n // 6 for _, n, _, _ in segs2)
+        segs2[odd] = (a, n - BUF, oi + shift, of + shift)
+        plan2 = h.plan_create(segs2, flags)
+        l0 = h.stats()["kernel_launches"]
+        ms_odd = cx.timed(lambda: h.plan_run(plan2, pg.ASYNC), steps, warmup)
+        per_step = (h.stats()["kernel_launches"] - l0) // (steps + warmup)
+        h.plan_destroy(plan2)
+        ns2 = ns - BUF // 6
+        misaligned[f"outputs_plus_{shift}_bytes"] = {"ms_per_step": round(ms_odd, 4), "launches_per_step": int(per_step),
+                                                     "time_per_sample_vs_all_aligned": round((ms_odd / ns2) / (ms / ns), 4)}
     for p_ in (d_in, d_i, d_f):
         h.dev_free(p_)
     achieved = BYTES_PER_SAMPLE_FUSED * ns / (ms * 1e-3) / 1e9
@@ -407,10 +411,8 @@ def workload_cfg3(cx, steps, warmup):
             "roofline": {"bound": "hbm", "kernel": "unpack24_stream_kernel<I32|F32, batched>", "achieved": round(achieved, 1), "peak": cx.peak,
                          "unit": "GB/s", "frac": round(achieved / cx.peak, 4), "bytes_per_sample": BYTES_PER_SAMPLE_FUSED},
             "gpu_launches": int(launches), "clocks": sampler.summary(),
-            "one_misaligned_receiver": {"ms_per_step": round(ms_odd, 4), "vs_all_aligned": round((ms_odd / ns2) / (ms / ns), 4),
-                                        "what": f"receiver {odd} ({nbufs[odd]} transfers) writes to outputs that are only 4-byte aligned: its tiles go to "
-                                                "the register-only kernel in a second launch, the other 1023 receivers stay on the pipeline; ratio of "
-                                                "time per sample"}}
+            "one_misaligned_receiver": dict(misaligned, what=f"receiver {odd} ({nbufs[odd]} transfers) writes to outputs that are not 16-byte "
+                                            "aligned; the other 1023 receivers are unaffected either way")}
 
 
 def workload_cfg4(cx, steps, warmup):
@@ -573,9 +575,10 @@ def ours(args):
         po_i, po_f = h.host_alloc(ns * 8), h.host_alloc(ns * 8)
         rt_steps = max(2, min(e2e_steps, 5))
         (_, d2h_gbs), d2h_conc = pcie(pg.PCIE_D2H)
-        # plain copies of the round trip's own traffic mix, both directions at once: 6 B up per 16 B (fused) / 8 B (one format) down
-        (dup16_up, dup16_down), dup16_conc = pcie(pg.PCIE_DUPLEX, 96 << 20, 256 << 20)
-        (dup8_up, dup8_down), _ = pcie(pg.PCIE_DUPLEX, 192 << 20, 256 << 20)
+        # plain copies of the round trip's own traffic, both directions at once: the whole recording up (6 B/sample) while the
+        # whole output comes down (16 B/sample fused, 8 B/sample one format), each as ONE cudaMemcpyAsync on its own stream
+        (dup16_up, dup16_down), dup16_conc = pcie(pg.PCIE_DUPLEX, nbytes, ns * 16)
+        (dup8_up, dup8_down), _ = pcie(pg.PCIE_DUPLEX, nbytes, ns * 8)
 
         def copy_bound_ms(up_gbs, down_gbs, down_bytes_per_sample):
             return max(6 * ns / (up_gbs * 1e9), down_bytes_per_sample * ns / (down_gbs * 1e9)) * 1e3
@@ -595,7 +598,7 @@ def ours(args):
                   "d2h_gbs_per_gpu": round(d2h_rate, 2), "pcie_d2h_gbs_measured": round(d2h_gbs, 2),
                   "frac_of_d2h_peak": round(d2h_rate / d2h_gbs, 4),
                   "duplex_plain_copies_gbs": {"h2d": round(dup16_up, 2), "d2h": round(dup16_down, 2),
-                                              "what": "plain pinned copies, 6 B up per 16 B down, both directions at once (perseus_gpu_probe_pcie)"},
+                                              "what": "the same bytes as two plain pinned copies queued at once: the recording up, both outputs' worth down (perseus_gpu_probe_pcie)"},
                   "frac_of_duplex_copy_bound": round(copy_bound_ms(dup16_up, dup16_down, 16) / ms_rt, 4),
                   "single_format": {"value": round(total_samples / (ms_rt1 * 1e-3) / 1e6, 1), "ms_per_step": round(ms_rt1, 3),
                                     "d2h_gbs_per_gpu": round(8 * ns / (ms_rt1 * 1e-3) / 1e9, 2),

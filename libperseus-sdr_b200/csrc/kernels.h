@@ -41,8 +41,12 @@ inline bool valid_tile(int tile) { return tile == 6144 || tile == 9216 || tile =
 
 // One tile of a batched launch: which segment, which tile of it.
 struct TileRef { uint32_t seg, tile; };
-// Device-side copy of a perseus_gpu_seg.
-struct SegDesc { const uint8_t *in; uint64_t nbytes; void *out_i32; void *out_f32; };
+// Device-side copy of a perseus_gpu_seg.  For a segment that takes the pipeline with a pre-roll (stream_preroll() == 6)
+// the pointers and the size are the virtual ones: moved back by 6 wire bytes / 8 output bytes, 6 bytes longer.
+struct SegDesc { const uint8_t *in; uint64_t nbytes; void *out_i32; void *out_f32; uint32_t preroll, pad; };
+
+// 0 / 6: the pipeline can serve these output pointers (with that pre-roll); -1: only the register-only kernel can.
+int stream_preroll(const void *out_i32, const void *out_f32);
 
 // Flat unpack of nbytes/6 samples.  Picks the kernel from `t.variant` and the pointers'
 // alignment; returns the number of kernels it launched through *launches.

@@ -466,6 +466,10 @@ int flush_locked(perseus_gpu *h)
 			rc = submit_slab(h);
 			if (rc) latch(h, rc);
 		}
+		// The slab events are BlockingSync (a back-pressure wait must sleep, see ensure_streaming), and a sleeping wait
+		// costs ~0.2 ms of wake-up latency.  flush is called by the application and wants the result now: spin on the
+		// streams first, after which every slab event is already complete and draining never sleeps.
+		for (int s = 0; s < h->nstreams; ++s) cudaStreamSynchronize(h->streams[s]);
 		rc = drain_file(h, h->nslabs);   // oldest first, so the file keeps stream order
 		if (rc) latch(h, rc);
 		h->next_to_write = h->cur;       // nothing in flight: the next slab submitted is the oldest
@@ -495,8 +499,9 @@ int plan_create_locked(perseus_gpu *h, const perseus_gpu_seg *segs, int nseg, un
 	const int tile = pg::resolve_geometry(h->tune, fmt).tile_bytes;
 	std::vector<pg::SegDesc> hs((size_t)nseg);
 	// Tiles are split by the alignment of their segment's OUTPUT pointers: 16-byte aligned ones (any cudaMalloc'd
-	// buffer) go to the bulk-copy pipeline, the rest to the register-only kernel -- per segment, so one odd
-	// receiver does not drag the whole batch onto the slow kernel.  Wire pointers may have any alignment.
+	// buffer) and 8-byte aligned ones (an {I,Q} array at its natural alignment) go to the bulk-copy pipeline, the
+	// rest to the register-only kernel -- per segment, so one odd receiver does not drag the whole batch onto the
+	// slow kernel.  Wire pointers may have any alignment.
 	std::vector<pg::TileRef> fast, slow;
 	uint64_t nsamples = 0, nbytes = 0;
 	for (int i = 0; i < nseg; ++i) {
@@ -507,12 +512,22 @@ int plan_create_locked(perseus_gpu *h, const perseus_gpu_seg *segs, int nseg, un
 		if (used && (fmt & (PERSEUS_GPU_OUT_FLOAT | PERSEUS_GPU_OUT_FLOAT_POW2)) && !s.out_f32)
 			return fail(PERSEUS_GPU_ERRPARAM, "segment %d: out_f32 is NULL", i);
 		if (((uintptr_t)s.out_i32 & 3) || ((uintptr_t)s.out_f32 & 3)) return fail(PERSEUS_GPU_ERRPARAM, "segment %d: outputs must be 4-byte aligned", i);
-		hs[(size_t)i] = pg::SegDesc{static_cast<const uint8_t *>(s.in), s.nbytes, (fmt & PERSEUS_GPU_OUT_INT32) ? s.out_i32 : nullptr,
-		                            (fmt & (PERSEUS_GPU_OUT_FLOAT | PERSEUS_GPU_OUT_FLOAT_POW2)) ? s.out_f32 : nullptr};
-		const bool out16 = ((((uintptr_t)hs[(size_t)i].out_i32 | (uintptr_t)hs[(size_t)i].out_f32) & 15) == 0) && h->tune.variant != PERSEUS_GPU_VARIANT_DIRECT;
-		const uint64_t nt = (used + (uint64_t)tile - 1) / (uint64_t)tile;
+		pg::SegDesc &d = hs[(size_t)i];
+		d = pg::SegDesc{static_cast<const uint8_t *>(s.in), s.nbytes, (fmt & PERSEUS_GPU_OUT_INT32) ? s.out_i32 : nullptr,
+		                (fmt & (PERSEUS_GPU_OUT_FLOAT | PERSEUS_GPU_OUT_FLOAT_POW2)) ? s.out_f32 : nullptr, 0u, 0u};
+		const int pre = h->tune.variant == PERSEUS_GPU_VARIANT_DIRECT ? -1 : pg::stream_preroll(d.out_i32, d.out_f32);
+		uint64_t span = used;                  // wire bytes the segment's tiles cover
+		if (pre > 0 && used) {                 // outputs 8 bytes past a 16-byte boundary: the segment starts one sample early (kernels.h)
+			d.in -= pre;
+			d.nbytes = used + (uint64_t)pre;
+			if (d.out_i32) d.out_i32 = static_cast<uint8_t *>(d.out_i32) - 8;
+			if (d.out_f32) d.out_f32 = static_cast<uint8_t *>(d.out_f32) - 8;
+			d.preroll = (uint32_t)pre;
+			span = d.nbytes;
+		}
+		const uint64_t nt = (span + (uint64_t)tile - 1) / (uint64_t)tile;
 		if (nt > 0xFFFFFFFFull) return fail(PERSEUS_GPU_BUFFERSIZE, "segment %d too large", i);
-		std::vector<pg::TileRef> &dst = out16 ? fast : slow;
+		std::vector<pg::TileRef> &dst = pre >= 0 ? fast : slow;
 		for (uint64_t t = 0; t < nt; ++t) dst.push_back(pg::TileRef{(uint32_t)i, (uint32_t)t});
 		nsamples += used / 6;
 		nbytes += used;

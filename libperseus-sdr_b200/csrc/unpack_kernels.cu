@@ -100,6 +100,23 @@ __device__ __forceinline__ uint4 unit_to_i32(uint32_t w0, uint32_t w1, uint32_t 
 	return o;
 }
 
+template <int ST>
+__device__ __forceinline__ void store8(void *p, uint2 v)
+{
+	if (ST == 2) *reinterpret_cast<uint2 *>(p) = v;
+	else __stcs(reinterpret_cast<uint2 *>(p), v);
+}
+
+// Second sample of a unit only (the first one is the pre-roll of a segment whose outputs are 8- but not 16-byte aligned).
+template <unsigned FMT, int ST>
+__device__ __forceinline__ void emit_unit_hi(uint32_t w0, uint32_t w1, uint32_t w2, uint8_t *o_i32, uint8_t *o_f32, size_t unit)
+{
+	const uint4 v = unit_to_i32(w0, w1, w2);
+	if (FMT & FMT_I32) store8<ST>(o_i32 + unit * 16 + 8, make_uint2(v.z, v.w));
+	if (FMT & (FMT_F32 | FMT_POW2))
+		store8<ST>(o_f32 + unit * 16 + 8, make_uint2(__float_as_uint(to_float<FMT>(v.z)), __float_as_uint(to_float<FMT>(v.w))));
+}
+
 template <unsigned FMT, int ST>
 __device__ __forceinline__ void emit_unit(uint32_t w0, uint32_t w1, uint32_t w2, uint8_t *o_i32, uint8_t *o_f32, size_t unit)
 {
@@ -133,11 +150,17 @@ __device__ __forceinline__ void emit_sample_bytes(const uint8_t *src, uint8_t *o
 }
 
 // ------------------------------------------------------------------ stream kernel
+// Outputs that are 8- but not 16-byte aligned (an {I,Q} array at its natural alignment: packed per-receiver outputs,
+// legacy 510-byte transfers of 85 samples) still take the pipeline: the buffer is treated as if it began one sample
+// earlier -- `preroll` = 6 wire bytes, 8 output bytes -- which makes every 16-byte store aligned again; the pre-roll
+// sample itself is never loaded from before the caller's buffer and never stored.  All pointers and sizes below are
+// the VIRTUAL ones (already moved back by the pre-roll).
 struct StreamParams {
-	const uint8_t *in;        // flat: wire bytes (any alignment; the outputs are 16-byte aligned)
-	uint8_t *out_i32, *out_f32;
-	uint64_t in_bytes;        // flat: 6 * nsamples
+	const uint8_t *in;        // flat: wire bytes (any alignment)
+	uint8_t *out_i32, *out_f32;   // 16-byte aligned
+	uint64_t in_bytes;        // flat: 6 * nsamples (+ preroll)
 	uint64_t ntiles;
+	uint32_t preroll;         // flat: 0 or 6
 	const SegDesc *segs;      // batched
 	const TileRef *tiles;
 	int stages;
@@ -147,7 +170,8 @@ struct TileHdr {              // written by the producer lane, read by the consu
 	const uint8_t *src;       // first wire byte of the tile (any alignment)
 	uint8_t *o_i32, *o_f32;
 	uint32_t valid;           // wire bytes of this tile that hold whole samples (<= TILE)
-	uint32_t bulk;            // bytes the bulk copy brought in, starting at the 16-byte boundary at or below src
+	uint32_t bulk;            // bytes the bulk copy covers, counted from the 16-byte boundary at or below src
+	uint32_t skip_first;      // first tile of a pre-rolled buffer: sample 0 is the pre-roll, do not store it
 };
 
 constexpr int kStagePad = 16;   // a misaligned tile spills into one more 16-byte granule
@@ -185,9 +209,11 @@ unpack24_stream_kernel(const __grid_constant__ StreamParams p)
 			for (uint64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
 				TileHdr h;
 				uint64_t left;                                     // whole-sample bytes from this tile's start to the end of its buffer
+				uint32_t pre;                                      // pre-roll of this tile's buffer (0 or 6)
 				if (BATCHED) {
 					const TileRef r = p.tiles[tile];
 					const SegDesc sd = p.segs[r.seg];
+					pre = r.tile == 0 ? sd.preroll : 0;
 					const uint8_t *seg_in = sd.in;
 					const uint64_t used = sd.nbytes / 6 * 6;
 					uint8_t *oi = static_cast<uint8_t *>(sd.out_i32);
@@ -199,6 +225,7 @@ unpack24_stream_kernel(const __grid_constant__ StreamParams p)
 					h.o_f32 = of + off / 6 * 8;
 					h.valid = left < (uint64_t)TILE ? (uint32_t)left : (uint32_t)TILE;
 				} else {
+					pre = tile == 0 ? p.preroll : 0;
 					const uint64_t off = tile * TILE;
 					left = p.in_bytes - off;
 					h.src = p.in + off;
@@ -213,11 +240,16 @@ unpack24_stream_kernel(const __grid_constant__ StreamParams p)
 				const uint64_t reach = (delta + left) & ~(uint64_t)15;                 // readable without passing the end
 				const uint32_t want = (delta + h.valid + 15u) & ~15u;
 				h.bulk = reach < (uint64_t)want ? (uint32_t)reach : want;
+				h.skip_first = pre ? 1u : 0u;
+				// The pre-roll bytes lie BEFORE the caller's buffer.  When they fall into an earlier granule than the buffer's
+				// first byte, the copy starts one granule later (same shared-memory image for every real byte).
+				const uint32_t skip = (pre && delta + pre >= 16u) ? 16u : 0u;
+				const uint32_t nb = h.bulk > skip ? h.bulk - skip : 0u;
 				mbar_wait(smem_u32(&empty_bar[s]), phase ^ 1);   // consumers released this stage
 				hdr[s] = h;
-				if (h.bulk) {
-					mbar_arrive_expect_tx(smem_u32(&full_bar[s]), h.bulk);
-					bulk_g2s(smem_u32(ring + (size_t)s * (TILE + kStagePad)), h.src - delta, h.bulk, smem_u32(&full_bar[s]), pol);
+				if (nb) {
+					mbar_arrive_expect_tx(smem_u32(&full_bar[s]), nb);
+					bulk_g2s(smem_u32(ring + (size_t)s * (TILE + kStagePad) + skip), h.src - delta + skip, nb, smem_u32(&full_bar[s]), pol);
 				} else {
 					mbar_arrive(smem_u32(&full_bar[s]));
 				}
@@ -237,7 +269,7 @@ unpack24_stream_kernel(const __grid_constant__ StreamParams p)
 		const uint32_t delta = (uint32_t)(reinterpret_cast<uintptr_t>(h.src) & 15u);
 		const uint32_t *w = reinterpret_cast<const uint32_t *>(ring + (size_t)s * (TILE + kStagePad)) + (delta >> 2);
 		const uint32_t sh = (delta & 3u) * 8u;
-		if (h.valid == (uint32_t)TILE && h.bulk >= delta + (uint32_t)TILE) {
+		if (h.valid == (uint32_t)TILE && h.bulk >= delta + (uint32_t)TILE && !h.skip_first) {
 			uint32_t r[kPasses][3];
 			if (sh == 0) {
 #pragma unroll
@@ -266,17 +298,17 @@ unpack24_stream_kernel(const __grid_constant__ StreamParams p)
 			const uint32_t nunits = h.bulk > delta ? (h.bulk - delta) / 12 : 0;
 			const uint32_t full_units = h.valid / 12 < nunits ? h.valid / 12 : nunits;
 			for (uint32_t u = tid; u < full_units; u += kConsumerThreads) {
-				const uint32_t a0 = w[3 * u], a1 = w[3 * u + 1], a2 = w[3 * u + 2];
-				if (sh == 0) {
-					emit_unit<FMT, ST>(a0, a1, a2, h.o_i32, h.o_f32, u);
-				} else {
+				uint32_t a0 = w[3 * u], a1 = w[3 * u + 1], a2 = w[3 * u + 2];
+				if (sh != 0) {
 					const uint32_t a3 = w[3 * u + 3];
-					emit_unit<FMT, ST>(__funnelshift_r(a0, a1, sh), __funnelshift_r(a1, a2, sh), __funnelshift_r(a2, a3, sh), h.o_i32, h.o_f32, u);
+					a0 = __funnelshift_r(a0, a1, sh); a1 = __funnelshift_r(a1, a2, sh); a2 = __funnelshift_r(a2, a3, sh);
 				}
+				if (u == 0 && h.skip_first) emit_unit_hi<FMT, ST>(a0, a1, a2, h.o_i32, h.o_f32, u);   // sample 0 is the pre-roll
+				else emit_unit<FMT, ST>(a0, a1, a2, h.o_i32, h.o_f32, u);
 			}
 			const uint32_t ns = h.valid / 6;
 			for (uint32_t k = 2 * full_units + tid; k < ns; k += kConsumerThreads)
-				emit_sample_bytes<FMT>(h.src, h.o_i32, h.o_f32, k);
+				if (k || !h.skip_first) emit_sample_bytes<FMT>(h.src, h.o_i32, h.o_f32, k);
 		}
 		// every consumer thread releases the stage itself: its own shared-memory reads are ordered before its own
 		// arrive (release), and the producer's wait (acquire) orders them before the next bulk copy into this stage
@@ -576,6 +608,26 @@ cudaError_t launch_direct_batch_fmt(const DirectParams &p, unsigned fmt, int gri
 
 inline bool aligned_to(const void *p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
+}  // namespace
+
+// Pre-roll (wire bytes) that makes the 16-byte stores of the pipeline legal for these outputs: 0 when every output
+// that is produced is 16-byte aligned, 6 when every one sits 8 bytes past a 16-byte boundary, -1 when neither.
+int stream_preroll(const void *out_i32, const void *out_f32)
+{
+	const void *o[2] = {out_i32, out_f32};
+	int phase = -1;
+	for (const void *q : o) {
+		if (!q) continue;
+		const int ph = (int)(reinterpret_cast<uintptr_t>(q) & 15);
+		if (ph != 0 && ph != 8) return -1;
+		if (phase >= 0 && ph != phase) return -1;
+		phase = ph;
+	}
+	return phase == 8 ? 6 : 0;
+}
+
+namespace {
+
 inline int persistent_grid(uint64_t ntiles, int sm_count, int ctas_per_sm)
 {
 	const uint64_t want = (uint64_t)sm_count * (uint64_t)ctas_per_sm;
@@ -594,16 +646,17 @@ cudaError_t launch_unpack(const void *in, size_t nbytes, void *out_i32, void *ou
 	if (!(fmt & FMT_I32)) out_i32 = nullptr;
 	if (!(fmt & (FMT_F32 | FMT_POW2))) out_f32 = nullptr;
 	const bool out16 = aligned_to(out_i32, 16) && aligned_to(out_f32, 16);
-	const bool can_stream = out16;   // the wire pointer may have any alignment (see the producer), the STG.128 targets may not
-	const bool use_stream = t.variant == 2 ? false : can_stream;   // variant 1 (STREAM) degrades to direct when unaligned
+	const int pre = stream_preroll(out_i32, out_f32);   // the wire pointer may have any alignment (see the producer), the STG.128 targets may not
+	const bool use_stream = t.variant == 2 ? false : pre >= 0;   // variant 1 (STREAM) degrades to direct when it cannot align them
 
 	const Geometry g = resolve_geometry(t, fmt);
 	if (use_stream) {
 		StreamParams p{};
-		p.in = static_cast<const uint8_t *>(in);
-		p.out_i32 = static_cast<uint8_t *>(out_i32);
-		p.out_f32 = static_cast<uint8_t *>(out_f32);
-		p.in_bytes = nsamples * 6;
+		p.preroll = (uint32_t)pre;
+		p.in = static_cast<const uint8_t *>(in) - pre;
+		p.out_i32 = out_i32 ? static_cast<uint8_t *>(out_i32) - pre / 6 * 8 : nullptr;
+		p.out_f32 = out_f32 ? static_cast<uint8_t *>(out_f32) - pre / 6 * 8 : nullptr;
+		p.in_bytes = nsamples * 6 + (uint64_t)pre;
 		p.ntiles = (p.in_bytes + (uint64_t)g.tile_bytes - 1) / (uint64_t)g.tile_bytes;
 		p.stages = g.stages;
 		const int grid = persistent_grid(p.ntiles, sm_count, g.ctas_per_sm);

@@ -30,7 +30,8 @@ import numpy as np
 HERE = Path(__file__).resolve().parent
 LIB_ORACLE = HERE / "liboracle.so"
 LIB_REF = HERE / "_ref" / "libperseus_ref.so"
-LIB_REFQUEUE = HERE / "_ref" / "libperseus_refqueue.so"
+LIB_REFLIB = HERE / "_ref" / "libperseus_sdr_ref.so"
+LIB_REFQUEUE = LIB_REFLIB   # the queue code is part of the whole reference library
 
 MODE_I32, MODE_F32, MODE_F32_POW2 = 0, 1, 2
 #: (float)(INT_MAX - 256), perseustest.c:496 — exactly representable in binary32.
@@ -162,12 +163,16 @@ class RefQueue:
     def available() -> bool:
         return LIB_REFQUEUE.exists()
 
-    def __init__(self, seed: int = SYNTH_SEED, drop_every: int = 0, swap_every: int = 0) -> None:
+    def __init__(self, seed: int = SYNTH_SEED, drop_every: int = 0, swap_every: int = 0, timeout_every: int = 0,
+                 fail_at: int = 0, fail_status: int = 0) -> None:
         if not self.available():
             raise FileNotFoundError(f"{LIB_REFQUEUE} not built (needs /root/reference at build time)")
         L = C.CDLL(str(LIB_REFQUEUE))
         vp, u64, u32 = C.c_void_p, C.c_uint64, C.c_uint32
         L.fakeusb_open.restype, L.fakeusb_open.argtypes = vp, [u64, u32, u32]
+        L.fakeusb_set_faults.restype, L.fakeusb_set_faults.argtypes = None, [vp, u32, u32, u32]
+        L.fakeusb_pending.restype, L.fakeusb_pending.argtypes = u64, [vp]
+        L.refq_completed.restype, L.refq_completed.argtypes = C.c_int, [vp]
         L.fakeusb_close.restype, L.fakeusb_close.argtypes = None, [vp]
         L.fakeusb_pump.restype, L.fakeusb_pump.argtypes = u64, [vp, u64]
         L.refq_start.restype, L.refq_start.argtypes = vp, [vp, C.c_int, vp, vp]
@@ -177,8 +182,14 @@ class RefQueue:
         L.refq_idx_expected.restype, L.refq_idx_expected.argtypes = C.c_int, [vp]
         self.L = L
         self.dev = L.fakeusb_open(seed, drop_every, swap_every)
+        L.fakeusb_set_faults(self.dev, timeout_every, fail_at, fail_status)
         self.q = None
         self._keep = None
+
+    @property
+    def pending(self) -> int:
+        """Transfers currently submitted to the device (8 minus the retired slots)."""
+        return int(self.L.fakeusb_pending(self.dev))
 
     def start(self, buffersize: int, callback, extra=None) -> None:
         """callback: a C function pointer (int/c_void_p) or a Python callable (buf, size, extra) -> int."""
@@ -211,6 +222,159 @@ class RefQueue:
         if self.dev:
             self.L.fakeusb_close(self.dev)
             self.dev = None
+
+
+class FakeUsbConfig(C.Structure):
+    """oracle/fakeusb.h fakeusb_config"""
+    _fields_ = [("struct_size", C.c_uint32), ("blank_eeprom", C.c_uint32), ("ep_max_packet", C.c_uint32), ("realtime", C.c_uint32),
+                ("seed", C.c_uint64), ("limit", C.c_uint64), ("drop_every", C.c_uint32), ("swap_every", C.c_uint32),
+                ("timeout_every", C.c_uint32), ("fail_at", C.c_uint32), ("fail_status", C.c_uint32), ("preserie", C.c_uint32),
+                ("serial", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class FakeUsbState(C.Structure):
+    """oracle/fakeusb.h fakeusb_state"""
+    _fields_ = [("inits", C.c_uint64), ("exits", C.c_uint64), ("opens", C.c_uint64), ("closes", C.c_uint64), ("device_refs", C.c_int64),
+                ("claimed", C.c_int32), ("firmware_loaded", C.c_int32),
+                ("cpu_resets", C.c_uint64), ("fw_records", C.c_uint64), ("fw_bytes", C.c_uint64), ("fw_hash", C.c_uint64),
+                ("fpga_resets", C.c_uint64), ("fpga_bytes", C.c_uint64), ("fpga_hash", C.c_uint64),
+                ("fpga_rate", C.c_int32), ("fifo_enabled", C.c_int32), ("sio_freg", C.c_uint32), ("sio_ctl", C.c_uint8), ("porte", C.c_uint8),
+                ("pad", C.c_uint8 * 2), ("sio_writes", C.c_uint64), ("porte_writes", C.c_uint64), ("eeprom_reads", C.c_uint64),
+                ("shutdowns", C.c_uint64), ("commands", C.c_uint64),
+                ("submits", C.c_uint64), ("stream_pos", C.c_uint64), ("completed_ok", C.c_uint64), ("cancelled", C.c_uint64),
+                ("timed_out", C.c_uint64), ("failed", C.c_uint64), ("events_calls", C.c_uint64),
+                ("events_thread_policy", C.c_int32), ("events_thread_priority", C.c_int32), ("events_thread_is_fifo", C.c_int32),
+                ("pad2", C.c_int32)]
+
+    def asdict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_ if not n.startswith("pad")}
+
+
+class EepromProdId(C.Structure):
+    """perseus-sdr.h:66-74 eeprom_prodid (packed)"""
+    _pack_ = 1
+    _fields_ = [("sn", C.c_uint16), ("prodcode", C.c_uint16), ("hwrel", C.c_uint8), ("hwver", C.c_uint8), ("signature", C.c_uint8 * 6)]
+
+
+# perseus-sdr.h:317-343
+PERSEUS_ERR = {"NOERROR": 0, "INVALIDDEV": -1, "NULLDESCR": -2, "ALREADYOPEN": -3, "LIBUSBERR": -4, "DEVNOTOPEN": -5, "FNNOTAVAIL": -9,
+               "DEVNOTFOUND": -10, "EEPROMREAD": -11, "IOERROR": -13, "FWNOTLOADED": -16, "FPGACFGERROR": -17, "FPGANOTCFGD": -18,
+               "ASYNCSTARTED": -19, "NOMEM": -20, "CANTCREAT": -21, "ERRPARAM": -22, "BUFFERSIZE": -24, "ATTERROR": -25, "SNNOTAVAILABLE": -26}
+
+
+class RefLib:
+    """The reference's WHOLE library (/root/reference/perseus-sdr.c, perseusfx2.c, perseus-in.c, perseuserr.c, unmodified)
+    over the synthetic receiver of oracle/fakeusb.c.  Methods are the reference's public API (perseus-sdr.h), called
+    through ctypes exactly as a C application would; `plug()` / `state()` talk to the fake device.
+
+    The library keeps global state (descriptor list, one poll thread: perseus-sdr.c:45-61), so there is one instance
+    per process and sessions must not overlap: use `with reflib.session(...) as descr:`."""
+
+    _inst = None
+
+    @staticmethod
+    def available() -> bool:
+        return LIB_REFLIB.exists()
+
+    def __new__(cls):
+        if cls._inst is None:
+            cls._inst = super().__new__(cls)
+            cls._inst._load()
+        return cls._inst
+
+    def _load(self) -> None:
+        if not self.available():
+            raise FileNotFoundError(f"{LIB_REFLIB} not built (needs /root/reference at build time)")
+        L = C.CDLL(str(LIB_REFLIB))
+        vp, ci, u32 = C.c_void_p, C.c_int, C.c_uint32
+        sig = {
+            "perseus_init": (ci, []), "perseus_exit": (ci, []), "perseus_open": (vp, [ci]), "perseus_close": (ci, [vp]),
+            "perseus_set_debug": (None, [ci]), "perseus_errorstr": (C.c_char_p, []),
+            "perseus_firmware_download": (ci, [vp, C.c_char_p]), "perseus_get_product_id": (ci, [vp, C.POINTER(EepromProdId)]),
+            "perseus_is_preserie": (ci, [vp, C.POINTER(ci)]),
+            "perseus_set_sampling_rate": (ci, [vp, ci]), "perseus_set_sampling_rate_n": (ci, [vp, C.c_uint]),
+            "perseus_get_sampling_rates": (ci, [vp, C.POINTER(ci), C.c_uint]),
+            "perseus_set_attenuator_n": (ci, [vp, ci]), "perseus_set_attenuator_in_db": (ci, [vp, ci]),
+            "perseus_set_adc": (ci, [vp, ci, ci]), "perseus_set_ddc_center_freq": (ci, [vp, C.c_double, ci]),
+            "perseus_start_async_input": (ci, [vp, u32, vp, vp]), "perseus_stop_async_input": (ci, [vp]),
+            "fakeusb_plug": (ci, [C.POINTER(FakeUsbConfig)]), "fakeusb_unplug": (None, []), "fakeusb_get_state": (None, [C.POINTER(FakeUsbState)]),
+            "reflib_descr_firmware_downloaded": (ci, [vp]), "reflib_descr_fpga_configured": (ci, [vp]), "reflib_descr_is_preserie": (ci, [vp]),
+            "reflib_descr_ring": (vp, [vp]), "reflib_descr_bytes_received": (C.c_uint64, [vp]), "reflib_descr_queue_active": (ci, [vp]),
+        }
+        for name, (res, args) in sig.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        self.L = L
+        self._keep = None
+
+    # -- fake device
+    def plug(self, **kw) -> None:
+        cfg = FakeUsbConfig()
+        cfg.struct_size = C.sizeof(FakeUsbConfig)
+        cfg.seed = SYNTH_SEED
+        for k, v in kw.items():
+            setattr(cfg, k, v)
+        if self.L.fakeusb_plug(C.byref(cfg)) != 0:
+            raise RuntimeError("fake receiver still has pending transfers")
+
+    def unplug(self) -> None:
+        self.L.fakeusb_unplug()
+
+    def state(self) -> dict:
+        st = FakeUsbState()
+        self.L.fakeusb_get_state(C.byref(st))
+        return st.asdict()
+
+    def errorstr(self) -> str:
+        return self.L.perseus_errorstr().decode(errors="replace")
+
+    def wait_stream_pos(self, n: int, timeout_s: float = 20.0) -> dict:
+        """Polls the fake device until it has completed `n` stream transfers."""
+        import time
+        t_end = time.monotonic() + timeout_s
+        while time.monotonic() < t_end:
+            st = self.state()
+            if st["stream_pos"] >= n:
+                return st
+            time.sleep(0.001)
+        raise TimeoutError(f"fake receiver stuck at {self.state()['stream_pos']} of {n} transfers")
+
+    def callback_pointer(self, callback):
+        """C pointer for `callback`: an int / c_void_p is passed through, a Python callable is wrapped (and kept alive)."""
+        if callable(callback) and not isinstance(callback, (int, C.c_void_p)):
+            self._keep = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p)(callback)
+            return C.cast(self._keep, C.c_void_p)
+        return callback
+
+    class _Session:
+        def __init__(self, lib, bring_up, rate, plug):
+            self.lib, self.bring_up, self.rate, self.plug_kw = lib, bring_up, rate, plug
+            self.descr = None
+
+        def __enter__(self):
+            lib, L = self.lib, self.lib.L
+            lib.plug(**self.plug_kw)
+            n = L.perseus_init()                                        # perseustest.c:188
+            assert n == 1, (n, lib.errorstr())
+            self.descr = L.perseus_open(0)                              # :205
+            assert self.descr, lib.errorstr()
+            if self.bring_up:
+                assert L.perseus_firmware_download(self.descr, None) == 0, lib.errorstr()      # :213
+                if self.rate:
+                    assert L.perseus_set_sampling_rate(self.descr, self.rate) == 0, lib.errorstr()   # :266
+            return self.descr
+
+        def __exit__(self, *exc):
+            L = self.lib.L
+            if self.descr and L.reflib_descr_queue_active(self.descr):
+                L.perseus_stop_async_input(self.descr)
+            L.perseus_exit()                                            # joins the poll thread, closes the device
+            self.lib.unplug()
+            return False
+
+    def session(self, bring_up: bool = True, rate: int = 95000, **plug):
+        """plug -> perseus_init -> perseus_open(0) [-> firmware_download -> set_sampling_rate]; perseus_exit on the way out."""
+        return RefLib._Session(self, bring_up, rate, plug)
 
 
 # --------------------------------------------------------------------------- numpy

@@ -1,0 +1,194 @@
+// TEST INFRASTRUCTURE ONLY: drives the host layer of libperseus_gpu (perseus_gpu.cu's host code, perseus_vrx.cpp,
+// perseus_host.cpp) from several threads at once so ThreadSanitizer / AddressSanitizer can see it.  Built by
+// tools/sanitize.sh against tests/sanitize/fake_cuda (no GPU involved); results are also checked against the CPU oracle.
+#include "../../include/perseus-gpu.h"
+
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+extern "C" size_t perseus_oracle_unpack(int mode, const uint8_t *in, size_t nbytes, void *out);
+
+#define CHECK(c)                                                                          \
+	do {                                                                                  \
+		if (!(c)) { fprintf(stderr, "FAILED %s:%d: %s  [%s]\n", __FILE__, __LINE__, #c, perseus_gpu_errorstr()); exit(1); } \
+	} while (0)
+
+static void sleep_ms(int ms) { std::this_thread::sleep_for(std::chrono::milliseconds(ms)); }
+
+struct Collected {
+	std::mutex mu;
+	std::vector<uint8_t> bytes;
+	perseus_gpu *h = nullptr;
+};
+
+static void sink(const perseus_gpu_block *b, void *extra)
+{
+	Collected *c = static_cast<Collected *>(extra);
+	std::lock_guard<std::mutex> lk(c->mu);
+	const size_t n = b->nsamples * 8, at = c->bytes.size();
+	CHECK(at == b->first_sample * 8);
+	c->bytes.resize(at + n);
+	CHECK(perseus_gpu_memcpy(c->h, c->bytes.data() + at, b->dev_i32, n) == 0);   // re-enters the handle from its own sink
+}
+
+// A: the virtual receiver's delivery thread against a stats reader
+static void scenario_vrx_stats()
+{
+	perseus_vrx_config cfg;
+	memset(&cfg, 0, sizeof cfg);
+	cfg.struct_size = sizeof cfg;
+	cfg.sample_rate = 2000000;
+	cfg.drop_every = 7; cfg.swap_every = 11; cfg.timeout_every = 13;
+	perseus_vrx *v = nullptr;
+	CHECK(perseus_vrx_open(&v, &cfg) == 0);
+	std::atomic<uint64_t> calls{0};
+	auto cb = [](void *, int, void *extra) -> int { static_cast<std::atomic<uint64_t> *>(extra)->fetch_add(1); return 0; };
+	CHECK(perseus_vrx_start_async_input(v, 6144, cb, &calls) == 0);
+	CHECK(perseus_vrx_start_async_input(v, 6144, cb, &calls) == PERSEUS_GPU_ASYNCSTARTED);
+	uint64_t last = 0;
+	for (int k = 0; k < 2000 || last < 200; ++k) {
+		perseus_vrx_stats s;
+		CHECK(perseus_vrx_get_stats(v, &s) == 0);
+		CHECK(s.delivered >= last);
+		last = s.delivered;
+	}
+	CHECK(perseus_vrx_stop_async_input(v) == 0);
+	perseus_vrx_stats s;
+	CHECK(perseus_vrx_get_stats(v, &s) == 0 && s.delivered == calls.load() && s.timed_out > 0 && s.dropped_short > 0);
+	CHECK(perseus_vrx_close(v) == 0);
+}
+
+// B: callbacks from the receiver's thread, watchdog inside the handle, and an application thread that polls, reads
+//    statistics and syncs -- all on ONE handle
+static void scenario_trampoline()
+{
+	perseus_gpu_config cfg;
+	memset(&cfg, 0, sizeof cfg);
+	cfg.struct_size = sizeof cfg;
+	cfg.stream_flags = PERSEUS_GPU_OUT_INT32;
+	cfg.slab_bytes = 6144 * 5;
+	cfg.nslabs = 3;
+	cfg.max_latency_us = 300;
+	perseus_gpu *h = nullptr;
+	CHECK(perseus_gpu_open(&h, &cfg) == 0);
+	Collected col;
+	col.h = h;
+	CHECK(perseus_gpu_set_sink(h, sink, &col) == 0);
+
+	perseus_vrx_config vc;
+	memset(&vc, 0, sizeof vc);
+	vc.struct_size = sizeof vc;
+	vc.sample_rate = 2000000;
+	vc.realtime = 1;
+	vc.seed = 42;
+	perseus_vrx *v = nullptr;
+	CHECK(perseus_vrx_open(&v, &vc) == 0);
+	CHECK(perseus_vrx_start_async_input(v, 6144, perseus_gpu_input_callback, h) == 0);
+	std::atomic<bool> stop{false};
+	std::thread app([&] {
+		while (!stop.load()) {
+			perseus_gpu_stats s;
+			CHECK(perseus_gpu_get_stats(h, &s) == 0);
+			CHECK(perseus_gpu_poll(h) >= 0);
+			if (s.callbacks % 7 == 0) CHECK(perseus_gpu_sync(h) == 0);
+			int t, st, c;
+			CHECK(perseus_gpu_get_geometry(h, PERSEUS_GPU_OUT_INT32, &t, &st, &c) == 0);
+		}
+	});
+	sleep_ms(300);
+	CHECK(perseus_vrx_stop_async_input(v) == 0);
+	sleep_ms(5);                       // the stream has stopped: the watchdog submits the tail on its own
+	stop.store(true);
+	app.join();
+	perseus_vrx_stats vs;
+	perseus_gpu_stats gs;
+	CHECK(perseus_vrx_get_stats(v, &vs) == 0);
+	CHECK(perseus_gpu_flush(h) == 0);
+	CHECK(perseus_gpu_get_stats(h, &gs) == 0);
+	CHECK(gs.callbacks == vs.delivered && gs.samples == vs.delivered * 1024 && gs.watchdog_submits > 0);
+	// the stream the sink collected == the oracle's unpack of the synthetic stream
+	std::vector<uint8_t> wire(vs.delivered * 6144), want(vs.delivered * 8192);
+	CHECK(perseus_synth_fill(wire.data(), wire.size(), PERSEUS_SYNTH_RANDOM, 42, 0) == 0);
+	perseus_oracle_unpack(0, wire.data(), wire.size(), want.data());
+	CHECK(col.bytes.size() == want.size() && memcmp(col.bytes.data(), want.data(), want.size()) == 0);
+	CHECK(perseus_vrx_close(v) == 0);
+	CHECK(perseus_gpu_close(h) == 0);
+}
+
+// C: two handles on two threads through the host-pointer pipeline (slot rotation, events, statistics)
+static void scenario_two_handles()
+{
+	auto work = [](int k) {
+		perseus_gpu_config cfg;
+		memset(&cfg, 0, sizeof cfg);
+		cfg.struct_size = sizeof cfg;
+		cfg.chunk_bytes = 48 * 100;
+		cfg.stage_slots = 2 + k;
+		perseus_gpu *h = nullptr;
+		CHECK(perseus_gpu_open(&h, &cfg) == 0);
+		std::vector<uint8_t> wire(6144 * 9 + 30), oi(wire.size() / 6 * 8), of(wire.size() / 6 * 8), want(oi.size());
+		CHECK(perseus_synth_fill(wire.data(), wire.size(), PERSEUS_SYNTH_RANDOM, 7 + k, 0) == 0);
+		for (int r = 0; r < 20; ++r) {
+			CHECK(perseus_gpu_unpack(h, wire.data(), wire.size(), oi.data(), of.data(), PERSEUS_GPU_CHECKSUM) == (int64_t)(wire.size() / 6));
+			uint64_t a, b;
+			CHECK(perseus_gpu_get_checksums(h, &a, &b) == 0);
+		}
+		perseus_oracle_unpack(0, wire.data(), wire.size(), want.data());
+		CHECK(memcmp(oi.data(), want.data(), want.size()) == 0);
+		perseus_oracle_unpack(1, wire.data(), wire.size(), want.data());
+		CHECK(memcmp(of.data(), want.data(), want.size()) == 0);
+		perseus_gpu_seg seg = {wire.data(), wire.size(), oi.data(), nullptr};
+		CHECK(perseus_gpu_unpack_batch(h, &seg, 1, PERSEUS_GPU_OUT_INT32) == (int64_t)(wire.size() / 6));
+		CHECK(perseus_gpu_close(h) == 0);
+	};
+	std::thread a(work, 0), b(work, 1);
+	a.join();
+	b.join();
+}
+
+// D: close while the watchdog sleeps on a partial slab; error latching with its counters; the file sink
+static void scenario_edges()
+{
+	perseus_gpu_config cfg;
+	memset(&cfg, 0, sizeof cfg);
+	cfg.struct_size = sizeof cfg;
+	cfg.max_latency_us = 200000;
+	perseus_gpu *h = nullptr;
+	CHECK(perseus_gpu_open(&h, &cfg) == 0);
+	std::vector<uint8_t> t(6144, 0x55);
+	CHECK(perseus_gpu_stream_to_file(h, "/tmp/perseus_sanitize.bin") == 0);
+	for (int k = 0; k < 3; ++k) perseus_gpu_input_callback(t.data(), 6144, h);
+	CHECK(perseus_gpu_close(h) == 0);                    // flushes the partial slab, joins the sleeping watchdog
+	FILE *f = fopen("/tmp/perseus_sanitize.bin", "rb");
+	CHECK(f != nullptr);
+	fseek(f, 0, SEEK_END);
+	CHECK(ftell(f) == 3 * 8192);
+	fclose(f);
+	remove("/tmp/perseus_sanitize.bin");
+
+	cfg.slab_bytes = 1ull << 44;                         // cannot be allocated: the callback latches the failure
+	CHECK(perseus_gpu_open(&h, &cfg) == 0);
+	for (int k = 0; k < 4; ++k) CHECK(perseus_gpu_input_callback(t.data(), 6144, h) == 0);
+	perseus_gpu_stats s;
+	CHECK(perseus_gpu_get_stats(h, &s) == 0 && s.callbacks == 1 && s.dropped_callbacks == 3 && s.dropped_bytes == 3 * 6144);
+	CHECK(perseus_gpu_flush(h) == PERSEUS_GPU_CUDAERR);
+	CHECK(perseus_gpu_flush(h) == 0);
+	CHECK(perseus_gpu_close(h) == 0);
+	CHECK(perseus_gpu_close(nullptr) == PERSEUS_GPU_NULLHANDLE);
+}
+
+int main()
+{
+	scenario_vrx_stats();
+	scenario_trampoline();
+	scenario_two_handles();
+	scenario_edges();
+	printf("host_stress: all scenarios passed\n");
+	return 0;
+}

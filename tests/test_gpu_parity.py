@@ -198,6 +198,29 @@ def test_stream_kernel_any_wire_alignment(pg, gpu, coracle, tile):
     gpu.set_tuning()
 
 
+@pytest.mark.parametrize("tile", [6144, 12288])
+def test_stream_kernel_outputs_at_natural_8_byte_alignment(pg, gpu, coracle, tile):
+    """An {I,Q} array is naturally 8-byte aligned (packed per-receiver outputs, 85-sample legacy transfers).  Such outputs
+    still take the pipeline: the buffer is treated as if it began one sample earlier, which re-aligns every 16-byte store;
+    that pre-roll sample is neither read from before the caller's wire buffer (in_off 0..5 puts it before the allocation:
+    memcheck) nor written before the caller's output (guard bytes in run_unpack)."""
+    gpu.set_tuning(variant=pg.VARIANT_STREAM, tile_bytes=tile, stages=3, ctas_per_sm=2)
+    big = coracle.synth_random(tile * 5 + 4000, seed=tile + 1)
+    for delta in range(16):
+        for n in (tile * 3, tile * 3 + 6, tile * 2 + 4000, tile - 6, tile, tile + 6, 6, 12, 18, 30, 510):
+            check_against_oracle(pg, gpu, coracle, big[:n], in_off=delta, out_off=8, tail_pad=0,
+                                 cases=[c for c in fmt_cases(pg) if c[0] in ("i32+f32", "f32")])
+    gpu.set_tuning()
+    # the two outputs at different phases (0 and 8): no single pre-roll serves both -> register-only kernel, still exact
+    wire = big[:tile * 2 + 30]
+    ns = wire.size // 6
+    with DevBuf(gpu, wire.size) as din, DevBuf(gpu, ns * 8 + 32) as di, DevBuf(gpu, ns * 8 + 32) as df:
+        gpu.memcpy(din.p, wire.ctypes.data, wire.size)
+        gpu.unpack(din.p, wire.size, di.p, df.p + 8, pg.OUT_INT32 | pg.OUT_FLOAT)
+        assert np.array_equal(gpu.to_host(di.p, ns * 8, np.uint32), coracle.unpack(wire, O.MODE_I32).view(np.uint32).reshape(-1))
+        assert np.array_equal(gpu.to_host(df.p + 8, ns * 8, np.uint32), coracle.unpack(wire, O.MODE_F32).view(np.uint32).reshape(-1))
+
+
 @pytest.mark.parametrize("tile", [6144, 9216, 12288, 18432, 24576])
 @pytest.mark.parametrize("stages", [2, 3, 8])
 def test_every_pipeline_geometry(pg, gpu, coracle, tile, stages):
@@ -383,7 +406,7 @@ def test_host_pointer_pipeline_rotates_its_slots(pg, coracle, slots, chunk):
         assert np.array_equal(h.to_host(d_i, ns * 8, np.uint32), want_i) and np.array_equal(host(po_f), want_f)
         assert h.get_checksums() == (coracle.checksum32(want_i), coracle.checksum32(want_f))
         st = h.stats()
-        assert st["h2d_bytes"] == 4 * (wire.size // 6 * 6) + wire.size and st["d2h_bytes"] >= 2 * 2 * ns * 8 + 2 * ns * 8 + ns * 8
+        assert st["h2d_bytes"] == 4 * (wire.size // 6 * 6) and st["d2h_bytes"] == (2 * 2 + 2 + 1) * ns * 8 + 16   # + the checksum read-back
         for p_ in (pin, po_i, po_f):
             h.host_free(p_)
         for p_ in (d_in, d_i, d_f):
@@ -539,7 +562,7 @@ def test_batch_with_misaligned_receivers_splits_by_alignment(pg, gpu, coracle):
     """Outputs that are only 4-byte aligned cannot take 16-byte stores.  Only THOSE receivers' tiles go to the
     register-only kernel (a second launch); everyone else stays on the bulk-copy pipeline."""
     sizes = [6144 * (20 + 7 * r) + (510 if r == 3 else 0) for r in range(12)]
-    odd = {5: 4, 7: 8, 9: 12}                          # receiver -> byte offset of its outputs
+    odd = {5: 4, 7: 8, 9: 12, 2: 8}                    # receiver -> byte offset of its outputs (8: still the pipeline, pre-rolled)
     wires = [coracle.synth_random(n, seed=7000 + r) for r, n in enumerate(sizes)]
     flags = pg.OUT_INT32 | pg.OUT_FLOAT
     bufs, segs = [], []

@@ -34,8 +34,11 @@ def record_vrx(pg, buffersize, n, ep=0, **faults):
 
 
 @pytest.mark.parametrize("buffersize,ep", [(6144, 512), (12288, 512), (510 * 3, 510)])
-@pytest.mark.parametrize("faults", [{}, {"drop_every": 5}, {"swap_every": 7}, {"drop_every": 4, "swap_every": 9}])
+@pytest.mark.parametrize("faults", [{}, {"drop_every": 5}, {"swap_every": 7}, {"drop_every": 4, "swap_every": 9},
+                                    {"timeout_every": 5}, {"fail_at": 10, "fail_status": 1}, {"fail_at": 2, "fail_status": 6, "swap_every": 6}],
+                         ids=lambda f: "-".join(f"{k}{v}" for k, v in f.items()) or "clean")
 def test_virtual_receiver_equals_reference_queue(pg, buffersize, ep, faults):
+    """Statuses other than COMPLETED included (perseus-in.c:218-257): TIMED_OUT re-arms the slot, ERROR / OVERFLOW retire it."""
     n = 61
     ref_calls, ref_received, ref_stopped = record_reference(buffersize, n, **faults)
     calls, st = record_vrx(pg, buffersize, n, ep=ep, **faults)
@@ -44,7 +47,22 @@ def test_virtual_receiver_equals_reference_queue(pg, buffersize, ep, faults):
     assert [(a - vbase, s, b) for a, s, b in calls] == ref_calls
     assert st["delivered"] == len(ref_calls)
     assert st["bytes_received"] == ref_received == ref_stopped       # cancelled transfers add nothing (perseus-in.c:191-196)
-    assert st["dropped_short"] + st["dropped_sequence"] == n - len(ref_calls)
+    assert st["dropped_short"] + st["dropped_sequence"] + st["timed_out"] + st["retired"] == n - len(ref_calls)
+    assert st["timed_out"] == (n // faults["timeout_every"] if "timeout_every" in faults else 0)
+    assert st["retired"] == (1 if "fail_at" in faults else 0)
+
+
+def test_retired_slot_leaves_seven_transfers_in_flight_and_stop_still_completes():
+    """ERROR / STALL / NO_DEVICE / OVERFLOW: the handler marks the slot cancelled and does not resubmit (perseus-in.c:222-257),
+    so 7 transfers stay in flight; perseus_stop_async_input's completion check (perseus-in.c:143-158) still terminates."""
+    rq = O.RefQueue(fail_at=4, fail_status=5)            # LIBUSB_TRANSFER_NO_DEVICE
+    got = []
+    rq.start(6144, lambda b, s, e: got.append(s) or 0)
+    assert rq.pending == 8
+    rq.pump(20)
+    assert rq.pending == 7 and 0 < len(got) < 19
+    rq.stop()
+    rq.close()
 
 
 def test_reference_queue_cancel_handshake():
