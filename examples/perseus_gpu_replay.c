@@ -6,7 +6,7 @@
  * Everything else reads like perseustest.c:93-409: parse -s -n -b -t -o -p, start the async input with
  * nb*bs-byte buffers, let it run, stop, print the kS/s line perseus_stop_async_input prints
  * (perseus-sdr.c:719-722).  The output file is byte-identical to what `perseustest -o file [-p]` writes for
- * the same wire stream (tests/test_examples_gpu.py checks that against the reference's own callbacks).
+ * the same wire stream (tests/test_examples.py checks that against the reference's own callbacks).
  *
  * Plain C99; links only against libperseus_gpu.so:
  *   gcc -std=c99 -I include examples/perseus_gpu_replay.c -L libperseus-sdr_b200/lib -lperseus_gpu -o perseus_gpu_replay

@@ -24,10 +24,13 @@
  * There is NO CPU fallback: every entry point that computes fails with
  * PERSEUS_GPU_NODEVICE / PERSEUS_GPU_BADARCH when no sm_100 device is usable.
  *
- * Threads: a handle is a monitor -- every entry point takes the handle's lock, so the callback
- * thread, the application thread and the library's own latency watchdog may touch the same
- * handle; they serialise.  The lock is recursive: a sink may call the synchronous plumbing
- * (sync, memcpy, get_stats) of its own handle, but not flush/close/unpack.  Every entry
+ * Threads: a handle is a monitor -- the callback thread (ONE per handle: the reference calls
+ * back strictly serially, perseus-sdr.c:736-770), application threads and the library's own
+ * latency watchdog may all touch the same handle; they serialise.  Ownership is recursive: a
+ * sink may call the synchronous plumbing (sync, memcpy, get_stats) of its own handle, but not
+ * flush/close/unpack.  perseus_gpu_input_callback itself takes no lock in the common case
+ * (the hand-off uses sys_membarrier, csrc/perseus_gpu.cu), so it costs nothing next to its
+ * copy; entry points called while a handle is streaming pay one membarrier (~us).  Every entry
  * point that takes a handle leaves the CALLING thread's current CUDA device set to the
  * handle's device (cudaSetDevice, not restored).
  *
@@ -85,9 +88,9 @@ typedef struct perseus_vrx perseus_vrx;               /* synthetic receiver (sta
 /* flags == 0 means: produce whatever non-NULL output pointers were passed (float = reference scale). */
 
 /* kernel selection (perseus_gpu_tuning.variant) */
-#define PERSEUS_GPU_VARIANT_AUTO    0  /* bulk-copy pipeline when the outputs are 16-byte aligned, else direct */
-#define PERSEUS_GPU_VARIANT_STREAM  1  /* TMA bulk copy -> shared-memory ring -> coalesced 16-byte stores */
-#define PERSEUS_GPU_VARIANT_DIRECT  2  /* register-only kernel, any alignment */
+#define PERSEUS_GPU_VARIANT_AUTO    0  /* = STREAM */
+#define PERSEUS_GPU_VARIANT_STREAM  1  /* TMA bulk copy -> shared-memory ring -> coalesced stores; any pointer alignment */
+#define PERSEUS_GPU_VARIANT_DIRECT  2  /* register-only kernel, any alignment: kept as the A/B comparison */
 
 typedef struct perseus_gpu_tuning {
 	int variant;       /* PERSEUS_GPU_VARIANT_*                                      (0 = auto)   */
@@ -142,8 +145,9 @@ int perseus_gpu_close(perseus_gpu *h);
  *   flags    PERSEUS_GPU_OUT_* | PERSEUS_GPU_ASYNC, or 0.
  * Returns the number of complex samples produced (>= 0) or a negative error.
  * The wire pointer may have ANY alignment and never matters for speed.  Output pointers must be 4-byte aligned
- * (PERSEUS_GPU_ERRPARAM otherwise; they hold int32 / float); those that are 16-byte aligned (any cudaMalloc'd
- * buffer) take the fast path, others a slower register-only kernel. */
+ * (PERSEUS_GPU_ERRPARAM otherwise; they hold int32 / float).  16-byte aligned outputs (any cudaMalloc'd buffer) and
+ * 8-byte aligned ones (an {I,Q} array at its natural alignment) run at full speed; outputs that are only 4-byte
+ * aligned are written with 32-bit stores by the same kernel. */
 int64_t perseus_gpu_unpack(perseus_gpu *h, const void *buf, size_t nbytes,
                            void *out_i32, void *out_f32, unsigned flags);
 

@@ -43,9 +43,10 @@ inline bool valid_tile(int tile) { return tile == 6144 || tile == 9216 || tile =
 struct TileRef { uint32_t seg, tile; };
 // Device-side copy of a perseus_gpu_seg.  For a segment that takes the pipeline with a pre-roll (stream_preroll() == 6)
 // the pointers and the size are the virtual ones: moved back by 6 wire bytes / 8 output bytes, 6 bytes longer.
-struct SegDesc { const uint8_t *in; uint64_t nbytes; void *out_i32; void *out_f32; uint32_t preroll, pad; };
+// word_stores: the outputs are only 4-byte aligned, the pipeline writes them with 32-bit stores.
+struct SegDesc { const uint8_t *in; uint64_t nbytes; void *out_i32; void *out_f32; uint32_t preroll, word_stores; };
 
-// 0 / 6: the pipeline can serve these output pointers (with that pre-roll); -1: only the register-only kernel can.
+// 0 / 6: 128-bit stores are legal for these output pointers (after that pre-roll); -1: only 32-bit stores are.
 int stream_preroll(const void *out_i32, const void *out_f32);
 
 // Flat unpack of nbytes/6 samples.  Picks the kernel from `t.variant` and the pointers'
@@ -54,10 +55,10 @@ cudaError_t launch_unpack(const void *in, size_t nbytes, void *out_i32, void *ou
                           const Tuning &t, int sm_count, cudaStream_t stream, int *launches);
 
 // Batched unpack over segments described on the device; the caller built two tile maps with tile size
-// `tile_bytes`: `d_tiles_stream` lists the tiles of segments whose OUTPUT pointers are 16-byte aligned (wire
-// pointers may have any alignment) -- they go through the bulk-copy pipeline -- and `d_tiles_direct` the tiles of
-// the others, which take the register-only kernel.  One misaligned receiver therefore costs only its own tiles.
-// The two launches go back to back on `stream`.
+// `tile_bytes`: `d_tiles_stream` lists the tiles that go through the bulk-copy pipeline (every segment, whatever the
+// alignment of its pointers: SegDesc.preroll / word_stores say how its stores are made, so one odd receiver costs only
+// its own tiles) and `d_tiles_direct` the tiles for the register-only kernel (PERSEUS_GPU_VARIANT_DIRECT, the A/B
+// variant).  The two launches, when both lists are non-empty, go back to back on `stream`.
 cudaError_t launch_unpack_batch(const SegDesc *d_segs, const TileRef *d_tiles_stream, uint64_t ntiles_stream,
                                 const TileRef *d_tiles_direct, uint64_t ntiles_direct, int tile_bytes, unsigned fmt,
                                 const Tuning &t, int sm_count, cudaStream_t stream, int *launches);

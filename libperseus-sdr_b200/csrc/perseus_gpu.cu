@@ -8,6 +8,7 @@
 #include "../../include/perseus-gpu.h"
 #include "kernels.h"
 
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <cstdarg>
@@ -19,7 +20,14 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include <pthread.h>
+#include <sched.h>
 #include <time.h>
+#include <unistd.h>
+#if defined(__linux__)
+#include <linux/membarrier.h>
+#include <sys/syscall.h>
+#endif
 #if defined(__SSE2__)
 #include <emmintrin.h>
 #endif
@@ -49,9 +57,23 @@ struct Slab {
 }  // namespace
 
 struct perseus_gpu {
-	// Monitor lock: every C-ABI entry point that takes a handle holds it, so the callback thread, the application
-	// thread and the watchdog serialise on the handle's state.
-	std::recursive_mutex mu;   // recursive: a sink runs under it and may call the plumbing (sync, memcpy) of its own handle
+	// Ownership of the handle's state.  Every C-ABI entry point takes `mu` (recursive: a sink runs under it and may call the
+	// plumbing of its own handle) -- EXCEPT perseus_gpu_input_callback, whose fast path must not execute a single locked
+	// instruction: the slab copy uses non-temporal stores, and a locked instruction (mutex, atomic read-modify-write, mfence)
+	// stalls until the write-combining buffers have drained, ~0.25 us per 6144-byte transfer, a quarter of the path's
+	// throughput.  The callback thread and everybody else therefore meet in an ASYMMETRIC Dekker handshake:
+	//   callback:  cb_active = 1;  <compiler barrier>;  if (others_want) -> slow path (take mu like everybody else)
+	//   others:    lock mu;  others_want++;  membarrier(PRIVATE_EXPEDITED);  wait until cb_active == 0
+	// sys_membarrier makes every running thread of the process execute a full barrier at that instant, which supplies the
+	// store-load ordering the callback side leaves out (and drains that core's write-combining buffers).  Where the system call
+	// is not available both sides fall back to a real fence.
+	std::recursive_mutex mu;
+	int lock_depth = 0;                          // under mu: nested entries of the owning thread
+	std::atomic<uint32_t> cb_active{0};          // 1 while the callback thread is inside its lock-free fast path
+	std::atomic<uint32_t> others_want{0};        // threads that hold or wait for `mu`
+	std::atomic<unsigned long> cb_thread{0};     // the thread that set cb_active (a sink called from it already owns the handle)
+	std::atomic<uint64_t> partial_since_ns{0};   // published by the owner for the watchdog: age stamp of the partial slab, 0 = none
+	bool asym = false;                           // membarrier available: the callback side needs no fence
 	int device = 0;
 	int sm_count = 0;
 	perseus_gpu_config cfg{};
@@ -89,7 +111,8 @@ struct perseus_gpu {
 	FILE *fout = nullptr;
 	// latency watchdog (started with the first callback unless PERSEUS_GPU_OPT_NO_WATCHDOG)
 	std::thread watchdog;
-	std::condition_variable_any wd_cv;
+	std::mutex wd_mu;                            // only for wd_cv / wd_stop
+	std::condition_variable wd_cv;
 	bool wd_started = false, wd_stop = false;
 	// bookkeeping
 	perseus_gpu_stats stats{};
@@ -320,6 +343,7 @@ int submit_slab(perseus_gpu *h)
 	h->samples_submitted += ns;
 	h->stats.slabs++;
 	h->fill = 0;
+	h->partial_since_ns.store(0, std::memory_order_relaxed);
 	h->cur = (h->cur + 1) % h->nslabs;
 	// the slab we are about to fill must be free: back-pressure only when the ring is full
 	Slab &next = h->slabs[h->cur];
@@ -374,23 +398,100 @@ int submit_if_over_age(perseus_gpu *h, uint64_t now)
 	return rc ? rc : 1;
 }
 
+// ---- ownership hand-off between the callback thread and everybody else (see struct perseus_gpu) ----------------------
+
+bool membarrier_available()
+{
+#if defined(__linux__) && defined(__NR_membarrier)
+	static const bool ok = [] {
+		const char *off = getenv("PERSEUS_GPU_NO_MEMBARRIER");          // tests: force the fence fallback
+		if (off && *off && *off != '0') return false;
+		const long cmds = syscall(__NR_membarrier, MEMBARRIER_CMD_QUERY, 0, 0);
+		if (cmds < 0 || !(cmds & MEMBARRIER_CMD_PRIVATE_EXPEDITED)) return false;
+		return syscall(__NR_membarrier, MEMBARRIER_CMD_REGISTER_PRIVATE_EXPEDITED, 0, 0) == 0;
+	}();
+	return ok;
+#else
+	return false;
+#endif
+}
+
+inline void light_barrier(const perseus_gpu *h)      // callback side
+{
+	if (h->asym) asm volatile("" ::: "memory");
+	else std::atomic_thread_fence(std::memory_order_seq_cst);
+}
+
+void heavy_barrier(const perseus_gpu *h)             // everybody else
+{
+#if defined(__linux__) && defined(__NR_membarrier)
+	if (h->asym) {
+		if (syscall(__NR_membarrier, MEMBARRIER_CMD_PRIVATE_EXPEDITED, 0, 0) != 0) {
+			// cannot happen after a successful registration; without the barrier the hand-off would be unsound
+			fprintf(stderr, "perseus-gpu: membarrier(PRIVATE_EXPEDITED) failed\n");
+			abort();
+		}
+		return;
+	}
+#endif
+	std::atomic_thread_fence(std::memory_order_seq_cst);
+}
+
+// Exclusive ownership for any thread but the callback's fast path.  Also binds the device (bind = true).
+struct Entry {
+	perseus_gpu *h = nullptr;
+	bool locked = false;
+	int rc = 0;
+	explicit Entry(perseus_gpu *hh, bool bind_device = true)
+	{
+		if (!hh) { rc = fail(PERSEUS_GPU_NULLHANDLE, "null handle"); return; }
+		h = hh;
+		const bool inside_fast_path = h->cb_active.load(std::memory_order_relaxed) &&
+		                              h->cb_thread.load(std::memory_order_relaxed) == (unsigned long)pthread_self();
+		if (!inside_fast_path) {                 // otherwise: a sink called from the callback -- this thread owns the handle already
+			h->mu.lock();
+			locked = true;
+			if (h->lock_depth++ == 0) {
+				h->others_want.fetch_add(1, std::memory_order_seq_cst);
+				heavy_barrier(h);
+				while (h->cb_active.load(std::memory_order_acquire)) sched_yield();   // a callback that was already running finishes first
+			}
+		}
+		if (bind_device) rc = bind(h);
+	}
+	~Entry()
+	{
+		if (!locked) return;
+		if (--h->lock_depth == 0) h->others_want.fetch_sub(1, std::memory_order_release);
+		h->mu.unlock();
+	}
+	Entry(const Entry &) = delete;
+	Entry &operator=(const Entry &) = delete;
+};
+
 // The latency bound must hold when no further callback comes (a stalled stream, the tail before
-// perseus_stop_async_input): this thread sleeps until the current partial slab's deadline and submits it.
+// perseus_stop_async_input): this thread sleeps until the partial slab's deadline and submits it.
 void watchdog_main(perseus_gpu *h)
 {
-	std::unique_lock<std::recursive_mutex> lk(h->mu);
+	std::unique_lock<std::mutex> lk(h->wd_mu);
 	while (!h->wd_stop) {
+		const uint64_t since = h->partial_since_ns.load(std::memory_order_relaxed), now = monotonic_ns();
 		uint64_t wait_ns = h->max_latency_ns;
-		if (h->fill) {
-			const uint64_t now = monotonic_ns(), due = h->fill_started_ns + h->max_latency_ns;
-			wait_ns = due > now ? due - now : 0;
+		if (since) wait_ns = since + h->max_latency_ns > now ? since + h->max_latency_ns - now : 0;
+		if (wait_ns) {
+			h->wd_cv.wait_for(lk, std::chrono::nanoseconds(wait_ns));
+			continue;                                                   // look again: the slab may have gone out meanwhile
 		}
-		if (wait_ns) h->wd_cv.wait_for(lk, std::chrono::nanoseconds(wait_ns));
-		if (h->wd_stop) break;
-		const int rc = submit_if_over_age(h, monotonic_ns());
-		if (rc < 0) latch(h, rc);
-		else if (rc > 0) h->stats.watchdog_submits++;
-		else if (!wait_ns) h->wd_cv.wait_for(lk, std::chrono::milliseconds(1));   // latched error: nothing to do, do not spin
+		lk.unlock();
+		int rc;
+		{
+			Entry en(h);                                                // takes the handle away from the callback thread
+			rc = en.rc ? en.rc : submit_if_over_age(h, monotonic_ns());
+			if (rc < 0) latch(h, rc);
+			else if (rc > 0) h->stats.watchdog_submits++;
+		}
+		lk.lock();
+		if (rc <= 0 && !h->wd_stop) h->wd_cv.wait_for(lk, std::chrono::milliseconds(1));   // latched error / raced with a callback: do not spin
 	}
 }
 
@@ -405,10 +506,10 @@ void start_watchdog(perseus_gpu *h)
 	}
 }
 
-void stop_watchdog(perseus_gpu *h)   // called WITHOUT h->mu
+void stop_watchdog(perseus_gpu *h)   // called without owning the handle
 {
 	{
-		std::lock_guard<std::recursive_mutex> lk(h->mu);
+		std::lock_guard<std::mutex> lk(h->wd_mu);
 		h->wd_stop = true;
 	}
 	h->wd_cv.notify_all();
@@ -421,7 +522,10 @@ int stream_push(perseus_gpu *h, const uint8_t *buf, size_t nbytes)
 	if (rc) return rc;
 	start_watchdog(h);
 	const uint64_t now = h->max_latency_ns ? monotonic_ns() : 0;
-	if (h->fill == 0) h->fill_started_ns = now;
+	if (h->fill == 0) {
+		h->fill_started_ns = now;
+		h->partial_since_ns.store(now, std::memory_order_relaxed);
+	}
 	while (nbytes) {
 		size_t room = h->slab_bytes - h->fill;
 		size_t n = nbytes < room ? nbytes : room;
@@ -433,6 +537,7 @@ int stream_push(perseus_gpu *h, const uint8_t *buf, size_t nbytes)
 			rc = submit_slab(h);
 			if (rc) return rc;
 			h->fill_started_ns = now;
+			if (nbytes) h->partial_since_ns.store(now, std::memory_order_relaxed);
 		}
 	}
 	// latency bound: on a real receiver transfers trickle in (10.8 ms apart at 95 kS/s); do not sit on them
@@ -498,10 +603,11 @@ int plan_create_locked(perseus_gpu *h, const perseus_gpu_seg *segs, int nseg, un
 
 	const int tile = pg::resolve_geometry(h->tune, fmt).tile_bytes;
 	std::vector<pg::SegDesc> hs((size_t)nseg);
-	// Tiles are split by the alignment of their segment's OUTPUT pointers: 16-byte aligned ones (any cudaMalloc'd
-	// buffer) and 8-byte aligned ones (an {I,Q} array at its natural alignment) go to the bulk-copy pipeline, the
-	// rest to the register-only kernel -- per segment, so one odd receiver does not drag the whole batch onto the
-	// slow kernel.  Wire pointers may have any alignment.
+	// Every segment takes the bulk-copy pipeline; the alignment of ITS output pointers decides how its tiles are
+	// stored: 16-byte aligned (any cudaMalloc'd buffer) -> 128-bit stores; 8-byte aligned (an {I,Q} array at its natural
+	// alignment) -> the same after a one-sample pre-roll; 4-byte aligned -> 32-bit stores.  Per segment, so one odd
+	// receiver does not slow the batch down.  Wire pointers may have any alignment.  (`slow`: the register-only
+	// kernel, only when the handle is tuned to PERSEUS_GPU_VARIANT_DIRECT.)
 	std::vector<pg::TileRef> fast, slow;
 	uint64_t nsamples = 0, nbytes = 0;
 	for (int i = 0; i < nseg; ++i) {
@@ -515,7 +621,9 @@ int plan_create_locked(perseus_gpu *h, const perseus_gpu_seg *segs, int nseg, un
 		pg::SegDesc &d = hs[(size_t)i];
 		d = pg::SegDesc{static_cast<const uint8_t *>(s.in), s.nbytes, (fmt & PERSEUS_GPU_OUT_INT32) ? s.out_i32 : nullptr,
 		                (fmt & (PERSEUS_GPU_OUT_FLOAT | PERSEUS_GPU_OUT_FLOAT_POW2)) ? s.out_f32 : nullptr, 0u, 0u};
-		const int pre = h->tune.variant == PERSEUS_GPU_VARIANT_DIRECT ? -1 : pg::stream_preroll(d.out_i32, d.out_f32);
+		const bool direct = h->tune.variant == PERSEUS_GPU_VARIANT_DIRECT;
+		const int pre = direct ? 0 : pg::stream_preroll(d.out_i32, d.out_f32);
+		if (pre < 0) d.word_stores = 1u;       // outputs only 4-byte aligned: same kernel, 32-bit stores for this segment's tiles
 		uint64_t span = used;                  // wire bytes the segment's tiles cover
 		if (pre > 0 && used) {                 // outputs 8 bytes past a 16-byte boundary: the segment starts one sample early (kernels.h)
 			d.in -= pre;
@@ -527,7 +635,7 @@ int plan_create_locked(perseus_gpu *h, const perseus_gpu_seg *segs, int nseg, un
 		}
 		const uint64_t nt = (span + (uint64_t)tile - 1) / (uint64_t)tile;
 		if (nt > 0xFFFFFFFFull) return fail(PERSEUS_GPU_BUFFERSIZE, "segment %d too large", i);
-		std::vector<pg::TileRef> &dst = pre >= 0 ? fast : slow;
+		std::vector<pg::TileRef> &dst = direct ? slow : fast;
 		for (uint64_t t = 0; t < nt; ++t) dst.push_back(pg::TileRef{(uint32_t)i, (uint32_t)t});
 		nsamples += used / 6;
 		nbytes += used;
@@ -573,18 +681,6 @@ int64_t plan_run_locked(perseus_gpu *h, perseus_gpu_plan *p, unsigned flags)
 	}
 	return (int64_t)p->nsamples;
 }
-
-// Locks the handle and makes its device current on the calling thread.
-struct Entry {
-	std::unique_lock<std::recursive_mutex> lk;
-	int rc = 0;
-	explicit Entry(perseus_gpu *h)
-	{
-		if (!h) { rc = fail(PERSEUS_GPU_NULLHANDLE, "null handle"); return; }
-		lk = std::unique_lock<std::recursive_mutex>(h->mu);
-		rc = bind(h);
-	}
-};
 
 }  // namespace
 
@@ -674,6 +770,7 @@ int perseus_gpu_open(perseus_gpu **out, const perseus_gpu_config *ucfg)
 	h->slab_bytes = (size_t)slab;
 	h->max_latency_ns = cfg.max_latency_us == 0xFFFFFFFFu ? 0 : (uint64_t)(cfg.max_latency_us ? cfg.max_latency_us : 50000u) * 1000ull;
 	h->chunk_bytes = (size_t)chunk;
+	h->asym = membarrier_available();
 	auto bail = [&](int code) {   // free what exists, keep the message of the original failure
 		const std::string keep = pg::last_error();
 		perseus_gpu_close(h);
@@ -707,7 +804,7 @@ int perseus_gpu_close(perseus_gpu *h)
 	stop_watchdog(h);
 	int rc = 0;
 	{
-		std::lock_guard<std::recursive_mutex> lk(h->mu);
+		Entry en(h, false);
 		if (cudaSetDevice(h->device) == cudaSuccess) {
 			rc = flush_locked(h);
 			for (int k = 0; k < kMaxSlabs; ++k) {
@@ -896,21 +993,43 @@ int64_t perseus_gpu_unpack_batch(perseus_gpu *h, const perseus_gpu_seg *segs, in
 
 // ---- streaming hand-off -----------------------------------------------------------------------------
 
+namespace {
+inline void callback_body(perseus_gpu *h, const uint8_t *buf, size_t n)
+{
+	if (h->latched) {                              // a previous failure is waiting to be reported: count what is lost
+		h->stats.dropped_callbacks++;
+		h->stats.dropped_bytes += n;
+		return;
+	}
+	h->stats.callbacks++;
+	int rc = stream_push(h, buf, n);
+	if (rc) latch(h, rc);
+}
+}  // namespace
+
 int perseus_gpu_input_callback(void *buf, int buf_size, void *extra)
 {
 	perseus_gpu *h = static_cast<perseus_gpu *>(extra);
 	if (!h || !buf || buf_size < 6) return 0;
 	// perseustest.c:443 — only whole samples of THIS transfer count
 	const size_t n = (size_t)buf_size / 6 * 6;
-	std::lock_guard<std::recursive_mutex> lk(h->mu);
-	if (h->latched) {                              // a previous failure is waiting to be reported: count what is lost
-		h->stats.dropped_callbacks++;
-		h->stats.dropped_bytes += n;
+	// fast path: announce, then look whether anybody else holds or wants the handle (no locked instruction, see struct perseus_gpu)
+	h->cb_thread.store((unsigned long)pthread_self(), std::memory_order_relaxed);
+	h->cb_active.store(1, std::memory_order_relaxed);
+	light_barrier(h);
+	if (h->others_want.load(std::memory_order_acquire) != 0) {
+		h->cb_active.store(0, std::memory_order_release);
+		Entry en(h, false);                         // slow path: queue up behind them like any other thread
+		callback_body(h, static_cast<const uint8_t *>(buf), n);
 		return 0;
 	}
-	h->stats.callbacks++;
-	int rc = stream_push(h, static_cast<const uint8_t *>(buf), n);
-	if (rc) latch(h, rc);
+	callback_body(h, static_cast<const uint8_t *>(buf), n);
+#if defined(__SSE2__)
+	// somebody arrived meanwhile and will take over when cb_active drops: the slab bytes written with non-temporal stores must
+	// be globally visible before that (a thread that arrives later than this check drains them with its membarrier)
+	if (h->others_want.load(std::memory_order_relaxed) != 0) _mm_sfence();
+#endif
+	h->cb_active.store(0, std::memory_order_release);
 	return 0;
 }
 
@@ -926,8 +1045,8 @@ int perseus_gpu_poll(perseus_gpu *h)
 
 int perseus_gpu_set_sink(perseus_gpu *h, perseus_gpu_sink sink, void *extra)
 {
-	if (!h) return fail(PERSEUS_GPU_NULLHANDLE, "null handle");
-	std::lock_guard<std::recursive_mutex> lk(h->mu);
+	Entry en(h, false);
+	if (en.rc) return en.rc;
 	h->sink = sink;
 	h->sink_extra = extra;
 	return 0;
@@ -962,9 +1081,9 @@ int perseus_gpu_flush(perseus_gpu *h)
 
 int perseus_gpu_get_stats(perseus_gpu *h, perseus_gpu_stats *out)
 {
-	if (!h) return fail(PERSEUS_GPU_NULLHANDLE, "null handle");
+	Entry en(h, false);
+	if (en.rc) return en.rc;
 	if (!out) return fail(PERSEUS_GPU_ERRPARAM, "null stats pointer");
-	std::lock_guard<std::recursive_mutex> lk(h->mu);
 	*out = h->stats;
 	return 0;
 }
@@ -975,7 +1094,7 @@ int perseus_gpu_set_tuning(perseus_gpu *h, const perseus_gpu_tuning *t)
 	pg::Tuning r = resolve_tuning(t);
 	int rc = check_tuning(r);
 	if (rc) return rc;
-	std::lock_guard<std::recursive_mutex> lk(h->mu);
+	Entry en(h, false);
 	memcpy(r.tuned, h->tune.tuned, sizeof(r.tuned));   // autotune results survive; explicit fields take precedence anyway
 	h->tune = r;
 	return 0;
@@ -984,7 +1103,7 @@ int perseus_gpu_set_tuning(perseus_gpu *h, const perseus_gpu_tuning *t)
 int perseus_gpu_get_geometry(perseus_gpu *h, unsigned flags, int *tile_bytes, int *stages, int *ctas_per_sm)
 {
 	if (!h) return fail(PERSEUS_GPU_NULLHANDLE, "null handle");
-	std::lock_guard<std::recursive_mutex> lk(h->mu);
+	Entry en(h, false);
 	const pg::Geometry g = pg::resolve_geometry(h->tune, flags & 7u);
 	if (tile_bytes) *tile_bytes = g.tile_bytes;
 	if (stages) *stages = g.stages;
@@ -1049,7 +1168,7 @@ int perseus_gpu_get_tuning(perseus_gpu *h, perseus_gpu_tuning *t)
 {
 	if (!h) return fail(PERSEUS_GPU_NULLHANDLE, "null handle");
 	if (!t) return fail(PERSEUS_GPU_ERRPARAM, "null tuning pointer");
-	std::lock_guard<std::recursive_mutex> lk(h->mu);
+	Entry en(h, false);
 	memset(t, 0, sizeof(*t));
 	t->variant = h->tune.variant;
 	t->tile_bytes = h->tune.tile_bytes;

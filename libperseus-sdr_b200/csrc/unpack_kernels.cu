@@ -132,6 +132,21 @@ __device__ __forceinline__ void emit_unit(uint32_t w0, uint32_t w1, uint32_t w2,
 	}
 }
 
+// One unit written with 32-bit stores: for outputs that are only 4-byte aligned.
+template <unsigned FMT>
+__device__ __forceinline__ void emit_unit_words(uint32_t w0, uint32_t w1, uint32_t w2, uint8_t *o_i32, uint8_t *o_f32, size_t unit)
+{
+	const uint4 v = unit_to_i32(w0, w1, w2);
+	if (FMT & FMT_I32) {
+		uint32_t *o = reinterpret_cast<uint32_t *>(o_i32) + 4 * unit;
+		o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+	}
+	if (FMT & (FMT_F32 | FMT_POW2)) {
+		float *o = reinterpret_cast<float *>(o_f32) + 4 * unit;
+		o[0] = to_float<FMT>(v.x); o[1] = to_float<FMT>(v.y); o[2] = to_float<FMT>(v.z); o[3] = to_float<FMT>(v.w);
+	}
+}
+
 // Scalar path for the few samples a vector path cannot cover (ragged ends, odd counts).
 template <unsigned FMT>
 __device__ __forceinline__ void emit_sample_bytes(const uint8_t *src, uint8_t *o_i32, uint8_t *o_f32, size_t k)
@@ -161,6 +176,7 @@ struct StreamParams {
 	uint64_t in_bytes;        // flat: 6 * nsamples (+ preroll)
 	uint64_t ntiles;
 	uint32_t preroll;         // flat: 0 or 6
+	uint32_t word_stores;     // flat: outputs only 4-byte aligned -> 32-bit stores (no pre-roll can align them)
 	const SegDesc *segs;      // batched
 	const TileRef *tiles;
 	int stages;
@@ -172,6 +188,7 @@ struct TileHdr {              // written by the producer lane, read by the consu
 	uint32_t valid;           // wire bytes of this tile that hold whole samples (<= TILE)
 	uint32_t bulk;            // bytes the bulk copy covers, counted from the 16-byte boundary at or below src
 	uint32_t skip_first;      // first tile of a pre-rolled buffer: sample 0 is the pre-roll, do not store it
+	uint32_t word_stores;     // this tile's outputs are only 4-byte aligned: 32-bit stores instead of 128-bit ones
 };
 
 constexpr int kStagePad = 16;   // a misaligned tile spills into one more 16-byte granule
@@ -214,6 +231,7 @@ unpack24_stream_kernel(const __grid_constant__ StreamParams p)
 					const TileRef r = p.tiles[tile];
 					const SegDesc sd = p.segs[r.seg];
 					pre = r.tile == 0 ? sd.preroll : 0;
+					h.word_stores = sd.word_stores;
 					const uint8_t *seg_in = sd.in;
 					const uint64_t used = sd.nbytes / 6 * 6;
 					uint8_t *oi = static_cast<uint8_t *>(sd.out_i32);
@@ -226,6 +244,7 @@ unpack24_stream_kernel(const __grid_constant__ StreamParams p)
 					h.valid = left < (uint64_t)TILE ? (uint32_t)left : (uint32_t)TILE;
 				} else {
 					pre = tile == 0 ? p.preroll : 0;
+					h.word_stores = p.word_stores;
 					const uint64_t off = tile * TILE;
 					left = p.in_bytes - off;
 					h.src = p.in + off;
@@ -269,7 +288,7 @@ unpack24_stream_kernel(const __grid_constant__ StreamParams p)
 		const uint32_t delta = (uint32_t)(reinterpret_cast<uintptr_t>(h.src) & 15u);
 		const uint32_t *w = reinterpret_cast<const uint32_t *>(ring + (size_t)s * (TILE + kStagePad)) + (delta >> 2);
 		const uint32_t sh = (delta & 3u) * 8u;
-		if (h.valid == (uint32_t)TILE && h.bulk >= delta + (uint32_t)TILE && !h.skip_first) {
+		if (h.valid == (uint32_t)TILE && h.bulk >= delta + (uint32_t)TILE && !(h.skip_first | h.word_stores)) {
 			uint32_t r[kPasses][3];
 			if (sh == 0) {
 #pragma unroll
@@ -303,7 +322,8 @@ unpack24_stream_kernel(const __grid_constant__ StreamParams p)
 					const uint32_t a3 = w[3 * u + 3];
 					a0 = __funnelshift_r(a0, a1, sh); a1 = __funnelshift_r(a1, a2, sh); a2 = __funnelshift_r(a2, a3, sh);
 				}
-				if (u == 0 && h.skip_first) emit_unit_hi<FMT, ST>(a0, a1, a2, h.o_i32, h.o_f32, u);   // sample 0 is the pre-roll
+				if (h.word_stores) emit_unit_words<FMT>(a0, a1, a2, h.o_i32, h.o_f32, u);             // outputs off 8-byte alignment
+				else if (u == 0 && h.skip_first) emit_unit_hi<FMT, ST>(a0, a1, a2, h.o_i32, h.o_f32, u);   // sample 0 is the pre-roll
 				else emit_unit<FMT, ST>(a0, a1, a2, h.o_i32, h.o_f32, u);
 			}
 			const uint32_t ns = h.valid / 6;
@@ -333,20 +353,6 @@ __device__ __forceinline__ void load_unit_bytes(const uint8_t *s, uint32_t &w0, 
 	w0 = s[0] | (s[1] << 8) | (s[2] << 16) | ((uint32_t)s[3] << 24);
 	w1 = s[4] | (s[5] << 8) | (s[6] << 16) | ((uint32_t)s[7] << 24);
 	w2 = s[8] | (s[9] << 8) | (s[10] << 16) | ((uint32_t)s[11] << 24);
-}
-
-template <unsigned FMT>
-__device__ __forceinline__ void emit_unit_words(uint32_t w0, uint32_t w1, uint32_t w2, uint8_t *o_i32, uint8_t *o_f32, size_t unit)
-{
-	const uint4 v = unit_to_i32(w0, w1, w2);
-	if (FMT & FMT_I32) {
-		uint32_t *o = reinterpret_cast<uint32_t *>(o_i32) + 4 * unit;
-		o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
-	}
-	if (FMT & (FMT_F32 | FMT_POW2)) {
-		float *o = reinterpret_cast<float *>(o_f32) + 4 * unit;
-		o[0] = to_float<FMT>(v.x); o[1] = to_float<FMT>(v.y); o[2] = to_float<FMT>(v.z); o[3] = to_float<FMT>(v.w);
-	}
 }
 
 // ALIGNED: in % 4 == 0 and outputs % 16 == 0 -> 3 LDG.32 (a warp reads 384 contiguous bytes)
@@ -646,12 +652,16 @@ cudaError_t launch_unpack(const void *in, size_t nbytes, void *out_i32, void *ou
 	if (!(fmt & FMT_I32)) out_i32 = nullptr;
 	if (!(fmt & (FMT_F32 | FMT_POW2))) out_f32 = nullptr;
 	const bool out16 = aligned_to(out_i32, 16) && aligned_to(out_f32, 16);
-	const int pre = stream_preroll(out_i32, out_f32);   // the wire pointer may have any alignment (see the producer), the STG.128 targets may not
-	const bool use_stream = t.variant == 2 ? false : pre >= 0;   // variant 1 (STREAM) degrades to direct when it cannot align them
+	// the wire pointer may have any alignment (see the producer); the outputs decide how the stores are made: 128-bit when
+	// 16-byte aligned, 128-bit after a one-sample pre-roll when 8-byte aligned, 32-bit otherwise -- all inside the pipeline
+	int pre = stream_preroll(out_i32, out_f32);
+	const bool use_stream = t.variant != 2;
 
 	const Geometry g = resolve_geometry(t, fmt);
 	if (use_stream) {
 		StreamParams p{};
+		p.word_stores = pre < 0 ? 1u : 0u;
+		if (pre < 0) pre = 0;
 		p.preroll = (uint32_t)pre;
 		p.in = static_cast<const uint8_t *>(in) - pre;
 		p.out_i32 = out_i32 ? static_cast<uint8_t *>(out_i32) - pre / 6 * 8 : nullptr;
@@ -687,9 +697,7 @@ cudaError_t launch_unpack_batch(const SegDesc *d_segs, const TileRef *d_tiles_st
 {
 	*launches = 0;
 	const Geometry g = resolve_geometry(t, fmt);
-	if (t.variant == 2) {   // A/B: everything through the register-only kernel (the caller put every tile in the direct list)
-		if (ntiles_stream) return cudaErrorInvalidValue;
-	}
+	// which tiles take which kernel was decided when the caller built the two lists (t.variant is honoured there)
 	if (ntiles_stream) {
 		StreamParams p{};
 		p.segs = d_segs;
