@@ -385,8 +385,7 @@ def workload_cfg3(cx, steps, warmup):
     h.plan_destroy(plan)
     # the same batch with ONE receiver's outputs off 16-byte alignment (the last 2 MS/s receiver, its segment shortened by
     # one transfer and its outputs moved up inside their own range): by 8 bytes -- the natural alignment of an {I,Q}
-    # array: 128-bit stores after a one-sample pre-roll -- and by 4 bytes: 32-bit stores for that receiver's tiles.
-    # Same kernel, same single launch either way
+    # array -- and by 4 bytes.  Same kernel, same single launch, 128-bit stores after a pre-roll of 2 / 1 output words
     odd = max(r for r in range(len(nbufs)) if nbufs[r] == max(nbufs))
     misaligned = {}
     for shift in (8, 4):

@@ -145,9 +145,8 @@ int perseus_gpu_close(perseus_gpu *h);
  *   flags    PERSEUS_GPU_OUT_* | PERSEUS_GPU_ASYNC, or 0.
  * Returns the number of complex samples produced (>= 0) or a negative error.
  * The wire pointer may have ANY alignment and never matters for speed.  Output pointers must be 4-byte aligned
- * (PERSEUS_GPU_ERRPARAM otherwise; they hold int32 / float).  16-byte aligned outputs (any cudaMalloc'd buffer) and
- * 8-byte aligned ones (an {I,Q} array at its natural alignment) run at full speed; outputs that are only 4-byte
- * aligned are written with 32-bit stores by the same kernel. */
+ * (PERSEUS_GPU_ERRPARAM otherwise; they hold int32 / float) and then run at full speed whatever their phase within 16
+ * bytes -- except when out_i32 and out_f32 sit at DIFFERENT phases, which the same kernel serves with 32-bit stores. */
 int64_t perseus_gpu_unpack(perseus_gpu *h, const void *buf, size_t nbytes,
                            void *out_i32, void *out_f32, unsigned flags);
 

@@ -41,12 +41,13 @@ inline bool valid_tile(int tile) { return tile == 6144 || tile == 9216 || tile =
 
 // One tile of a batched launch: which segment, which tile of it.
 struct TileRef { uint32_t seg, tile; };
-// Device-side copy of a perseus_gpu_seg.  For a segment that takes the pipeline with a pre-roll (stream_preroll() == 6)
-// the pointers and the size are the virtual ones: moved back by 6 wire bytes / 8 output bytes, 6 bytes longer.
-// word_stores: the outputs are only 4-byte aligned, the pipeline writes them with 32-bit stores.
+// Device-side copy of a perseus_gpu_seg; nbytes is rounded down to whole samples by the host.  For a segment that takes
+// the pipeline with a pre-roll (stream_preroll() = 3m > 0) the pointers and the size are the virtual ones: moved back by
+// 3m wire bytes / 4m output bytes, 3m bytes longer.  word_stores: the two outputs sit at different phases, the pipeline
+// writes this segment with 32-bit stores.
 struct SegDesc { const uint8_t *in; uint64_t nbytes; void *out_i32; void *out_f32; uint32_t preroll, word_stores; };
 
-// 0 / 6: 128-bit stores are legal for these output pointers (after that pre-roll); -1: only 32-bit stores are.
+// 0 / 3 / 6 / 9: 128-bit stores are legal for these output pointers after that pre-roll; -1: only 32-bit stores are.
 int stream_preroll(const void *out_i32, const void *out_f32);
 
 // Flat unpack of nbytes/6 samples.  Picks the kernel from `t.variant` and the pointers'

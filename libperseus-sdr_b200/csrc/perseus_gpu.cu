@@ -603,10 +603,9 @@ int plan_create_locked(perseus_gpu *h, const perseus_gpu_seg *segs, int nseg, un
 
 	const int tile = pg::resolve_geometry(h->tune, fmt).tile_bytes;
 	std::vector<pg::SegDesc> hs((size_t)nseg);
-	// Every segment takes the bulk-copy pipeline; the alignment of ITS output pointers decides how its tiles are
-	// stored: 16-byte aligned (any cudaMalloc'd buffer) -> 128-bit stores; 8-byte aligned (an {I,Q} array at its natural
-	// alignment) -> the same after a one-sample pre-roll; 4-byte aligned -> 32-bit stores.  Per segment, so one odd
-	// receiver does not slow the batch down.  Wire pointers may have any alignment.  (`slow`: the register-only
+	// Every segment takes the bulk-copy pipeline with 128-bit stores; outputs that are not 16-byte aligned (an {I,Q}
+	// array at its natural 8-byte alignment, or any multiple of 4) get them after a pre-roll of 1..3 output words.  Per
+	// segment, so one odd receiver does not slow the batch down.  Wire pointers may have any alignment.  (`slow`: the register-only
 	// kernel, only when the handle is tuned to PERSEUS_GPU_VARIANT_DIRECT.)
 	std::vector<pg::TileRef> fast, slow;
 	uint64_t nsamples = 0, nbytes = 0;
@@ -619,17 +618,17 @@ int plan_create_locked(perseus_gpu *h, const perseus_gpu_seg *segs, int nseg, un
 			return fail(PERSEUS_GPU_ERRPARAM, "segment %d: out_f32 is NULL", i);
 		if (((uintptr_t)s.out_i32 & 3) || ((uintptr_t)s.out_f32 & 3)) return fail(PERSEUS_GPU_ERRPARAM, "segment %d: outputs must be 4-byte aligned", i);
 		pg::SegDesc &d = hs[(size_t)i];
-		d = pg::SegDesc{static_cast<const uint8_t *>(s.in), s.nbytes, (fmt & PERSEUS_GPU_OUT_INT32) ? s.out_i32 : nullptr,
+		d = pg::SegDesc{static_cast<const uint8_t *>(s.in), used, (fmt & PERSEUS_GPU_OUT_INT32) ? s.out_i32 : nullptr,
 		                (fmt & (PERSEUS_GPU_OUT_FLOAT | PERSEUS_GPU_OUT_FLOAT_POW2)) ? s.out_f32 : nullptr, 0u, 0u};
 		const bool direct = h->tune.variant == PERSEUS_GPU_VARIANT_DIRECT;
 		const int pre = direct ? 0 : pg::stream_preroll(d.out_i32, d.out_f32);
-		if (pre < 0) d.word_stores = 1u;       // outputs only 4-byte aligned: same kernel, 32-bit stores for this segment's tiles
+		if (pre < 0) d.word_stores = 1u;       // the two outputs at different phases: same kernel, 32-bit stores for this segment's tiles
 		uint64_t span = used;                  // wire bytes the segment's tiles cover
-		if (pre > 0 && used) {                 // outputs 8 bytes past a 16-byte boundary: the segment starts one sample early (kernels.h)
+		if (pre > 0 && used) {                 // outputs 4m bytes past a 16-byte boundary: the segment starts m words early (kernels.h)
 			d.in -= pre;
 			d.nbytes = used + (uint64_t)pre;
-			if (d.out_i32) d.out_i32 = static_cast<uint8_t *>(d.out_i32) - 8;
-			if (d.out_f32) d.out_f32 = static_cast<uint8_t *>(d.out_f32) - 8;
+			if (d.out_i32) d.out_i32 = static_cast<uint8_t *>(d.out_i32) - pre / 3 * 4;
+			if (d.out_f32) d.out_f32 = static_cast<uint8_t *>(d.out_f32) - pre / 3 * 4;
 			d.preroll = (uint32_t)pre;
 			span = d.nbytes;
 		}

@@ -100,21 +100,18 @@ __device__ __forceinline__ uint4 unit_to_i32(uint32_t w0, uint32_t w1, uint32_t 
 	return o;
 }
 
-template <int ST>
-__device__ __forceinline__ void store8(void *p, uint2 v)
-{
-	if (ST == 2) *reinterpret_cast<uint2 *>(p) = v;
-	else __stcs(reinterpret_cast<uint2 *>(p), v);
-}
-
-// Second sample of a unit only (the first one is the pre-roll of a segment whose outputs are 8- but not 16-byte aligned).
-template <unsigned FMT, int ST>
-__device__ __forceinline__ void emit_unit_hi(uint32_t w0, uint32_t w1, uint32_t w2, uint8_t *o_i32, uint8_t *o_f32, size_t unit)
+// A unit whose first `skip` output words (1..3) are the pre-roll of its buffer: only the words from `skip` on are stored.
+template <unsigned FMT>
+__device__ __forceinline__ void emit_unit_from(uint32_t skip, uint32_t w0, uint32_t w1, uint32_t w2, uint8_t *o_i32, uint8_t *o_f32, size_t unit)
 {
 	const uint4 v = unit_to_i32(w0, w1, w2);
-	if (FMT & FMT_I32) store8<ST>(o_i32 + unit * 16 + 8, make_uint2(v.z, v.w));
-	if (FMT & (FMT_F32 | FMT_POW2))
-		store8<ST>(o_f32 + unit * 16 + 8, make_uint2(__float_as_uint(to_float<FMT>(v.z)), __float_as_uint(to_float<FMT>(v.w))));
+	const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+	for (uint32_t i = 1; i < 4; ++i) {
+		if (i < skip) continue;
+		if (FMT & FMT_I32) reinterpret_cast<uint32_t *>(o_i32)[4 * unit + i] = w[i];
+		if (FMT & (FMT_F32 | FMT_POW2)) reinterpret_cast<float *>(o_f32)[4 * unit + i] = to_float<FMT>(w[i]);
+	}
 }
 
 template <unsigned FMT, int ST>
@@ -164,19 +161,30 @@ __device__ __forceinline__ void emit_sample_bytes(const uint8_t *src, uint8_t *o
 	}
 }
 
+// One output word (I or Q of one sample) from its 3 wire bytes: tail of a buffer whose word count is not a multiple of 4.
+template <unsigned FMT>
+__device__ __forceinline__ void emit_word_bytes(const uint8_t *src, uint8_t *o_i32, uint8_t *o_f32, size_t k)
+{
+	const uint8_t *s = src + 3 * k;
+	const uint32_t w = ((uint32_t)s[0] << 8) | ((uint32_t)s[1] << 16) | ((uint32_t)s[2] << 24);
+	if (FMT & FMT_I32) reinterpret_cast<uint32_t *>(o_i32)[k] = w;
+	if (FMT & (FMT_F32 | FMT_POW2)) reinterpret_cast<float *>(o_f32)[k] = to_float<FMT>(w);
+}
+
 // ------------------------------------------------------------------ stream kernel
-// Outputs that are 8- but not 16-byte aligned (an {I,Q} array at its natural alignment: packed per-receiver outputs,
-// legacy 510-byte transfers of 85 samples) still take the pipeline: the buffer is treated as if it began one sample
-// earlier -- `preroll` = 6 wire bytes, 8 output bytes -- which makes every 16-byte store aligned again; the pre-roll
-// sample itself is never loaded from before the caller's buffer and never stored.  All pointers and sizes below are
-// the VIRTUAL ones (already moved back by the pre-roll).
+// Outputs that are not 16-byte aligned (an {I,Q} array at its natural 8-byte alignment: packed per-receiver outputs,
+// legacy 510-byte transfers of 85 samples; or any multiple of 4) still get 128-bit stores: every output word is made
+// of its own 3 wire bytes, so a buffer whose outputs sit m words (4m bytes) past a 16-byte boundary is treated as if it
+// began m words earlier -- `preroll` = 3m wire bytes -- which re-aligns every store.  The pre-roll words are never
+// loaded from before the caller's buffer and never stored.  All pointers and sizes below are the VIRTUAL ones
+// (already moved back by the pre-roll); sizes are multiples of 3 (whole output words), not necessarily of 6.
 struct StreamParams {
 	const uint8_t *in;        // flat: wire bytes (any alignment)
 	uint8_t *out_i32, *out_f32;   // 16-byte aligned
 	uint64_t in_bytes;        // flat: 6 * nsamples (+ preroll)
 	uint64_t ntiles;
-	uint32_t preroll;         // flat: 0 or 6
-	uint32_t word_stores;     // flat: outputs only 4-byte aligned -> 32-bit stores (no pre-roll can align them)
+	uint32_t preroll;         // flat: 0, 3, 6 or 9
+	uint32_t word_stores;     // flat: the two outputs sit at different phases, no pre-roll aligns both -> 32-bit stores
 	const SegDesc *segs;      // batched
 	const TileRef *tiles;
 	int stages;
@@ -185,10 +193,10 @@ struct StreamParams {
 struct TileHdr {              // written by the producer lane, read by the consumers of that stage
 	const uint8_t *src;       // first wire byte of the tile (any alignment)
 	uint8_t *o_i32, *o_f32;
-	uint32_t valid;           // wire bytes of this tile that hold whole samples (<= TILE)
+	uint32_t valid;           // wire bytes of this tile that hold whole output words (<= TILE, multiple of 3)
 	uint32_t bulk;            // bytes the bulk copy covers, counted from the 16-byte boundary at or below src
-	uint32_t skip_first;      // first tile of a pre-rolled buffer: sample 0 is the pre-roll, do not store it
-	uint32_t word_stores;     // this tile's outputs are only 4-byte aligned: 32-bit stores instead of 128-bit ones
+	uint32_t skip_words;      // first tile of a pre-rolled buffer: its first 1..3 output words are the pre-roll, do not store them
+	uint32_t word_stores;     // this tile's outputs cannot be aligned by a pre-roll: 32-bit stores instead of 128-bit ones
 };
 
 constexpr int kStagePad = 16;   // a misaligned tile spills into one more 16-byte granule
@@ -225,15 +233,15 @@ unpack24_stream_kernel(const __grid_constant__ StreamParams p)
 			uint32_t phase = 0;
 			for (uint64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
 				TileHdr h;
-				uint64_t left;                                     // whole-sample bytes from this tile's start to the end of its buffer
-				uint32_t pre;                                      // pre-roll of this tile's buffer (0 or 6)
+				uint64_t left;                                     // whole-word bytes from this tile's start to the end of its buffer
+				uint32_t pre;                                      // pre-roll bytes in this tile (first tile of a pre-rolled buffer only)
 				if (BATCHED) {
 					const TileRef r = p.tiles[tile];
 					const SegDesc sd = p.segs[r.seg];
 					pre = r.tile == 0 ? sd.preroll : 0;
 					h.word_stores = sd.word_stores;
 					const uint8_t *seg_in = sd.in;
-					const uint64_t used = sd.nbytes / 6 * 6;
+					const uint64_t used = sd.nbytes;                // the host rounded it to whole samples (+ pre-roll)
 					uint8_t *oi = static_cast<uint8_t *>(sd.out_i32);
 					uint8_t *of = static_cast<uint8_t *>(sd.out_f32);
 					const uint64_t off = (uint64_t)r.tile * TILE;
@@ -259,10 +267,10 @@ unpack24_stream_kernel(const __grid_constant__ StreamParams p)
 				const uint64_t reach = (delta + left) & ~(uint64_t)15;                 // readable without passing the end
 				const uint32_t want = (delta + h.valid + 15u) & ~15u;
 				h.bulk = reach < (uint64_t)want ? (uint32_t)reach : want;
-				h.skip_first = pre ? 1u : 0u;
+				h.skip_words = pre / 3u;
 				// The pre-roll bytes lie BEFORE the caller's buffer.  When they fall into an earlier granule than the buffer's
 				// first byte, the copy starts one granule later (same shared-memory image for every real byte).
-				const uint32_t skip = (pre && delta + pre >= 16u) ? 16u : 0u;
+				const uint32_t skip = (pre && delta + pre >= 16u) ? 16u : 0u;   // pre <= 9: at most one granule
 				const uint32_t nb = h.bulk > skip ? h.bulk - skip : 0u;
 				mbar_wait(smem_u32(&empty_bar[s]), phase ^ 1);   // consumers released this stage
 				hdr[s] = h;
@@ -288,7 +296,7 @@ unpack24_stream_kernel(const __grid_constant__ StreamParams p)
 		const uint32_t delta = (uint32_t)(reinterpret_cast<uintptr_t>(h.src) & 15u);
 		const uint32_t *w = reinterpret_cast<const uint32_t *>(ring + (size_t)s * (TILE + kStagePad)) + (delta >> 2);
 		const uint32_t sh = (delta & 3u) * 8u;
-		if (h.valid == (uint32_t)TILE && h.bulk >= delta + (uint32_t)TILE && !(h.skip_first | h.word_stores)) {
+		if (h.valid == (uint32_t)TILE && h.bulk >= delta + (uint32_t)TILE && !(h.skip_words | h.word_stores)) {
 			uint32_t r[kPasses][3];
 			if (sh == 0) {
 #pragma unroll
@@ -322,13 +330,13 @@ unpack24_stream_kernel(const __grid_constant__ StreamParams p)
 					const uint32_t a3 = w[3 * u + 3];
 					a0 = __funnelshift_r(a0, a1, sh); a1 = __funnelshift_r(a1, a2, sh); a2 = __funnelshift_r(a2, a3, sh);
 				}
-				if (h.word_stores) emit_unit_words<FMT>(a0, a1, a2, h.o_i32, h.o_f32, u);             // outputs off 8-byte alignment
-				else if (u == 0 && h.skip_first) emit_unit_hi<FMT, ST>(a0, a1, a2, h.o_i32, h.o_f32, u);   // sample 0 is the pre-roll
+				if (h.word_stores) emit_unit_words<FMT>(a0, a1, a2, h.o_i32, h.o_f32, u);                 // outputs at two different phases
+				else if (u == 0 && h.skip_words) emit_unit_from<FMT>(h.skip_words, a0, a1, a2, h.o_i32, h.o_f32, u);   // leading words are the pre-roll
 				else emit_unit<FMT, ST>(a0, a1, a2, h.o_i32, h.o_f32, u);
 			}
-			const uint32_t ns = h.valid / 6;
-			for (uint32_t k = 2 * full_units + tid; k < ns; k += kConsumerThreads)
-				if (k || !h.skip_first) emit_sample_bytes<FMT>(h.src, h.o_i32, h.o_f32, k);
+			const uint32_t nw = h.valid / 3;
+			for (uint32_t k = 4 * full_units + tid; k < nw; k += kConsumerThreads)
+				if (k >= h.skip_words) emit_word_bytes<FMT>(h.src, h.o_i32, h.o_f32, k);
 		}
 		// every consumer thread releases the stage itself: its own shared-memory reads are ordered before its own
 		// arrive (release), and the producer's wait (acquire) orders them before the next bulk copy into this stage
@@ -616,8 +624,8 @@ inline bool aligned_to(const void *p, uintptr_t a) { return (reinterpret_cast<ui
 
 }  // namespace
 
-// Pre-roll (wire bytes) that makes the 16-byte stores of the pipeline legal for these outputs: 0 when every output
-// that is produced is 16-byte aligned, 6 when every one sits 8 bytes past a 16-byte boundary, -1 when neither.
+// Pre-roll (wire bytes: 0, 3, 6 or 9) that makes the 16-byte stores of the pipeline legal for these outputs: every output
+// that is produced sits the same 4m bytes past a 16-byte boundary -> 3m.  -1 when the two outputs sit at different phases.
 int stream_preroll(const void *out_i32, const void *out_f32)
 {
 	const void *o[2] = {out_i32, out_f32};
@@ -625,11 +633,11 @@ int stream_preroll(const void *out_i32, const void *out_f32)
 	for (const void *q : o) {
 		if (!q) continue;
 		const int ph = (int)(reinterpret_cast<uintptr_t>(q) & 15);
-		if (ph != 0 && ph != 8) return -1;
+		if (ph & 3) return -1;
 		if (phase >= 0 && ph != phase) return -1;
 		phase = ph;
 	}
-	return phase == 8 ? 6 : 0;
+	return phase < 0 ? 0 : phase / 4 * 3;
 }
 
 namespace {
@@ -652,8 +660,8 @@ cudaError_t launch_unpack(const void *in, size_t nbytes, void *out_i32, void *ou
 	if (!(fmt & FMT_I32)) out_i32 = nullptr;
 	if (!(fmt & (FMT_F32 | FMT_POW2))) out_f32 = nullptr;
 	const bool out16 = aligned_to(out_i32, 16) && aligned_to(out_f32, 16);
-	// the wire pointer may have any alignment (see the producer); the outputs decide how the stores are made: 128-bit when
-	// 16-byte aligned, 128-bit after a one-sample pre-roll when 8-byte aligned, 32-bit otherwise -- all inside the pipeline
+	// the wire pointer may have any alignment (see the producer); the outputs decide how the stores are made: 128-bit, after a
+	// pre-roll of 0..3 output words when they are 4-, 8- or 12-byte off; 32-bit only when the two outputs disagree
 	int pre = stream_preroll(out_i32, out_f32);
 	const bool use_stream = t.variant != 2;
 
@@ -664,8 +672,8 @@ cudaError_t launch_unpack(const void *in, size_t nbytes, void *out_i32, void *ou
 		if (pre < 0) pre = 0;
 		p.preroll = (uint32_t)pre;
 		p.in = static_cast<const uint8_t *>(in) - pre;
-		p.out_i32 = out_i32 ? static_cast<uint8_t *>(out_i32) - pre / 6 * 8 : nullptr;
-		p.out_f32 = out_f32 ? static_cast<uint8_t *>(out_f32) - pre / 6 * 8 : nullptr;
+		p.out_i32 = out_i32 ? static_cast<uint8_t *>(out_i32) - pre / 3 * 4 : nullptr;
+		p.out_f32 = out_f32 ? static_cast<uint8_t *>(out_f32) - pre / 3 * 4 : nullptr;
 		p.in_bytes = nsamples * 6 + (uint64_t)pre;
 		p.ntiles = (p.in_bytes + (uint64_t)g.tile_bytes - 1) / (uint64_t)g.tile_bytes;
 		p.stages = g.stages;

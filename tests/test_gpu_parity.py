@@ -199,17 +199,19 @@ def test_stream_kernel_any_wire_alignment(pg, gpu, coracle, tile):
     gpu.set_tuning()
 
 
+@pytest.mark.parametrize("out_off", [4, 8, 12])
 @pytest.mark.parametrize("tile", [6144, 12288])
-def test_stream_kernel_outputs_at_natural_8_byte_alignment(pg, gpu, coracle, tile):
-    """An {I,Q} array is naturally 8-byte aligned (packed per-receiver outputs, 85-sample legacy transfers).  Such outputs
-    still take the pipeline: the buffer is treated as if it began one sample earlier, which re-aligns every 16-byte store;
-    that pre-roll sample is neither read from before the caller's wire buffer (in_off 0..5 puts it before the allocation:
-    memcheck) nor written before the caller's output (guard bytes in run_unpack)."""
+def test_stream_kernel_outputs_off_16_byte_alignment(pg, gpu, coracle, tile, out_off):
+    """An {I,Q} array is naturally 8-byte aligned (packed per-receiver outputs, 85-sample legacy transfers), and any multiple of
+    4 is legal.  Such outputs still get 128-bit stores: every output word is made of its own 3 wire bytes, so the buffer is
+    treated as if it began 1..3 words earlier, which re-aligns every store; those pre-roll words are neither read from before
+    the caller's wire buffer (small in_off puts them before the allocation: memcheck) nor written before the caller's output
+    (guard bytes in run_unpack).  Sizes include every tail length (words mod 4) and buffers smaller than the pre-roll unit."""
     gpu.set_tuning(variant=pg.VARIANT_STREAM, tile_bytes=tile, stages=3, ctas_per_sm=2)
-    big = coracle.synth_random(tile * 5 + 4000, seed=tile + 1)
+    big = coracle.synth_random(tile * 5 + 4000, seed=tile + out_off)
     for delta in range(16):
-        for n in (tile * 3, tile * 3 + 6, tile * 2 + 4000, tile - 6, tile, tile + 6, 6, 12, 18, 30, 510):
-            check_against_oracle(pg, gpu, coracle, big[:n], in_off=delta, out_off=8, tail_pad=0,
+        for n in (tile * 3, tile * 3 + 6, tile * 2 + 4000, tile - 6, tile, tile + 6, tile + 12, tile + 18, 6, 12, 18, 24, 30, 510):
+            check_against_oracle(pg, gpu, coracle, big[:n], in_off=delta, out_off=out_off, tail_pad=0,
                                  cases=[c for c in fmt_cases(pg) if c[0] in ("i32+f32", "f32")])
     gpu.set_tuning()
     # the two outputs at different phases (0 and 8): no single pre-roll serves both -> 32-bit stores, still exact
@@ -560,11 +562,11 @@ def test_batch_plan_edge_cases(pg, gpu, coracle):
 
 
 def test_batch_with_misaligned_receivers_stays_one_launch(pg, gpu, coracle):
-    """Outputs that are only 8- or 4-byte aligned cannot take 16-byte stores as they are.  Only THOSE receivers' tiles are
-    stored differently (pre-rolled by one sample / with 32-bit stores), inside the same launch of the same pipeline kernel;
-    everyone else is unaffected."""
+    """Outputs that are only 8- or 4-byte aligned cannot take 16-byte stores as they are.  Only THOSE receivers' segments are
+    treated differently (pre-rolled by 1..3 output words), inside the same launch of the same pipeline kernel; everyone else is
+    unaffected."""
     sizes = [6144 * (20 + 7 * r) + (510 if r == 3 else 0) for r in range(12)]
-    odd = {5: 4, 7: 8, 9: 12, 2: 8}                    # receiver -> byte offset of its outputs (8: still the pipeline, pre-rolled)
+    odd = {5: 4, 7: 8, 9: 12, 2: 8}                    # receiver -> byte offset of its outputs (pre-rolled by 1, 2, 3, 2 words)
     wires = [coracle.synth_random(n, seed=7000 + r) for r, n in enumerate(sizes)]
     flags = pg.OUT_INT32 | pg.OUT_FLOAT
     bufs, segs = [], []
