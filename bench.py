@@ -298,6 +298,17 @@ def reference_arm(args):
 
 # ----------------------------------------------------------------------------------------- our arm
 
+def spread_device(local: int, local_world: int, visible: int):
+    """Which GPU a rank uses.  The shards are independent and host-fed, so when fewer ranks than GPUs run, they are spread
+    over the box (stride visible // ranks: 4 ranks on an 8-GPU box use GPUs 0, 2, 4, 6) instead of packed onto GPUs 0..N-1:
+    on these hosts GPUs 0-3 share one path to host memory (115 GB/s of pinned reads for the four of them, measured by
+    tools/h2d_matrix.py, profiles/r2_h2d_matrix_8gpu.md), GPUs 4-7 another.  Kernel-only numbers do not depend on it."""
+    if os.environ.get("PERSEUS_BENCH_PACKED") or local_world >= visible or visible % local_world:
+        return local, "packed: rank r -> GPU r"
+    stride = visible // local_world
+    return local * stride, f"spread: rank r -> GPU r*{stride} of {visible}"
+
+
 class Ctx:
     """Per-rank plumbing shared by the legs: handle, distributed helpers, timing."""
 
@@ -312,10 +323,11 @@ class Ctx:
         self.local = int(os.environ.get("LOCAL_RANK", "0"))
         if self.world != args.gpus:
             log(f"[bench] WORLD_SIZE={self.world} but --gpus {args.gpus}; using {self.world}")
-        self.numa = bind_to_gpu_numa_node(self.local)
-        torch.cuda.set_device(self.local)
+        self.device, self.device_map = spread_device(self.local, int(os.environ.get("LOCAL_WORLD_SIZE", self.world)), torch.cuda.device_count())
+        self.numa = bind_to_gpu_numa_node(self.device)
+        torch.cuda.set_device(self.device)
         if self.world > 1:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.device))
         if self.local == 0:
             G.ensure_built()
         self.barrier()
@@ -323,7 +335,7 @@ class Ctx:
         self.sharding = importlib.import_module("libperseus_sdr_b200.sharding")
         self.allmax = self.sharding.allreduce_max
         self.peak, self.peak_src = measured_peak()
-        self.h = self.pg.PerseusGpu(device=self.local, chunk_bytes=args.chunk_mib << 20, stage_slots=args.slots)
+        self.h = self.pg.PerseusGpu(device=self.device, chunk_bytes=args.chunk_mib << 20, stage_slots=args.slots)
 
     def barrier(self):
         if self.world > 1:
@@ -346,7 +358,7 @@ class Ctx:
         return self.allmax(ms) / steps
 
     def free_bytes(self):
-        return self.torch.cuda.mem_get_info(self.local)[0]
+        return self.torch.cuda.mem_get_info(self.device)[0]
 
     def close(self):
         self.h.close()
@@ -378,7 +390,7 @@ def workload_cfg3(cx, steps, warmup):
     h.plan_run(plan)
     bad, _ = h.verify(d_in, total_in, d_i, d_f, flags)
     assert bad == 0, bad
-    sampler = ClockSampler(cx.local)
+    sampler = ClockSampler(cx.device)
     l0 = h.stats()["kernel_launches"]
     ms = cx.timed(lambda: h.plan_run(plan, pg.ASYNC), steps, warmup, sampler)
     launches = h.stats()["kernel_launches"] - l0 - warmup
@@ -434,7 +446,7 @@ def workload_cfg4(cx, steps, warmup):
     # position-weighted checksum of the whole recording's float output: shard sums add up (mod 2^64), so it must be
     # the same number whatever N is
     checksum = cx.sharding.allreduce_sum_u64(h.checksum(d_f, ns * 2, first_index=first * 2048))
-    sampler = ClockSampler(cx.local)
+    sampler = ClockSampler(cx.device)
     l0 = h.stats()["kernel_launches"]
     ms = cx.timed(lambda: h.unpack(d_in, nbytes, None, d_f, flags | pg.ASYNC), steps, warmup, sampler)
     launches = h.stats()["kernel_launches"] - l0 - warmup
@@ -452,7 +464,7 @@ def workload_cfg4(cx, steps, warmup):
 def ours(args):
     import numpy as np
     cx = Ctx(args)
-    pg, h, rank, world, local = cx.pg, cx.h, cx.rank, cx.world, cx.local
+    pg, h, rank, world, local = cx.pg, cx.h, cx.rank, cx.world, cx.device
     barrier, allmax, timed = cx.barrier, cx.allmax, cx.timed
     sharding = cx.sharding
     if args.tile or args.stages or args.ctas or args.variant or args.store:
@@ -531,16 +543,27 @@ def ours(args):
     h.memcpy(pin, d_in, nbytes)                                           # the synthetic recording, now in pinned host memory
 
     def pcie(kind, up=256 << 20, down=0):
-        """In-run PCIe roofline: plain pinned copies by the library's probe; with all ranks at once when N > 1 (max over ranks)."""
-        alone = h.probe_pcie(kind, up, down, 3)
-        if world == 1:
-            return alone, None
-        barrier()
-        together = h.probe_pcie(kind, up, down, 3)
-        barrier()
-        return alone, tuple(-allmax(-g) for g in together)                # the slowest rank's rate
+        """In-run PCIe roofline of THIS GPU alone: plain pinned copies by the library's probe (ranks take turns)."""
+        res = None
+        for r in range(world):
+            if r == rank:
+                res = h.probe_pcie(kind, up, down, 3)
+            barrier()
+        return res
 
-    (h2d_gbs, _), h2d_conc = pcie(pg.PCIE_H2D)
+    def all_ranks_at_once(dst, src, n):
+        """The same plain copy with every rank copying at the same time, between buffers that already exist: GB/s of the slowest rank."""
+        if world == 1:
+            return None
+        times = []
+        for _ in range(2):
+            barrier()
+            h.event_record(2); h.memcpy(dst, src, n); h.event_record(3)
+            times.append(allmax(h.event_elapsed_ms(2, 3)))
+        return n / (min(times) * 1e-3) / 1e9
+
+    h2d_gbs, _ = pcie(pg.PCIE_H2D)
+    h2d_conc = all_ranks_at_once(d_in, pin, nbytes)
     sums = []
 
     def e2e_step():
@@ -566,18 +589,19 @@ def ours(args):
            "frac_of_gen5_x16_theory": round(e2e_gbs / PCIE_GEN5_X16_GBS, 4),
            "pinned_memory": "write-combined" if args.pinned_wc else "default (cudaHostAlloc portable)"}
     if h2d_conc:
-        e2e["pcie_h2d_gbs_all_ranks_at_once"] = round(h2d_conc[0], 2)
-        e2e["frac_of_concurrent_pcie"] = round(e2e_gbs / h2d_conc[0], 4)
+        e2e["pcie_h2d_gbs_all_ranks_at_once"] = round(h2d_conc, 2)
+        e2e["frac_of_concurrent_pcie"] = round(e2e_gbs / h2d_conc, 4)
 
     e2e_rt = None
     if not args.no_roundtrip:
         po_i, po_f = h.host_alloc(ns * 8), h.host_alloc(ns * 8)
         rt_steps = max(2, min(e2e_steps, 5))
-        (_, d2h_gbs), d2h_conc = pcie(pg.PCIE_D2H)
+        _, d2h_gbs = pcie(pg.PCIE_D2H)
+        d2h_conc = all_ranks_at_once(po_f, d_f32, ns * 8)
         # plain copies of the round trip's own traffic, both directions at once: the whole recording up (6 B/sample) while the
         # whole output comes down (16 B/sample fused, 8 B/sample one format), each as ONE cudaMemcpyAsync on its own stream
-        (dup16_up, dup16_down), dup16_conc = pcie(pg.PCIE_DUPLEX, nbytes, ns * 16)
-        (dup8_up, dup8_down), _ = pcie(pg.PCIE_DUPLEX, nbytes, ns * 8)
+        dup16_up, dup16_down = pcie(pg.PCIE_DUPLEX, nbytes, ns * 16)
+        dup8_up, dup8_down = pcie(pg.PCIE_DUPLEX, nbytes, ns * 8)
 
         def copy_bound_ms(up_gbs, down_gbs, down_bytes_per_sample):
             return max(6 * ns / (up_gbs * 1e9), down_bytes_per_sample * ns / (down_gbs * 1e9)) * 1e3
@@ -605,10 +629,8 @@ def ours(args):
                                     "frac_of_duplex_copy_bound": round(copy_bound_ms(dup8_up, dup8_down, 8) / ms_rt1, 4),
                                     "what": "float only: 8 B/sample D2H against 6 B/sample H2D"}}
         if d2h_conc:
-            e2e_rt["pcie_d2h_gbs_all_ranks_at_once"] = round(d2h_conc[1], 2)
-            e2e_rt["frac_of_concurrent_d2h"] = round(d2h_rate / d2h_conc[1], 4)
-            e2e_rt["duplex_plain_copies_gbs_all_ranks_at_once"] = {"h2d": round(dup16_conc[0], 2), "d2h": round(dup16_conc[1], 2)}
-            e2e_rt["frac_of_concurrent_duplex_copy_bound"] = round(copy_bound_ms(dup16_conc[0], dup16_conc[1], 16) / ms_rt, 4)
+            e2e_rt["pcie_d2h_gbs_all_ranks_at_once"] = round(d2h_conc, 2)
+            e2e_rt["frac_of_concurrent_d2h"] = round(d2h_rate / d2h_conc, 4)
         h.host_free(po_i); h.host_free(po_f)
     if wc_rt is not None:
         wc_rt.cudaFreeHost(C.c_void_p(pin))
@@ -674,7 +696,7 @@ def ours(args):
                   "generated": "on the device (perseus_gpu_generate), rank r at byte offset r * shard size of the recording",
                   "pass": "int32 AND float written by one fused kernel launch per step",
                   "parallelism": f"{world} independent shard(s) (perseus_gpu_shard_range), no data-path collective", "tuning": tuning,
-                  "numa_node": cx.numa},
+                  "device_map": cx.device_map, "numa_node": cx.numa},
         "roofline": {"bound": "hbm", "kernel": "unpack24_stream_kernel<I32|F32>", "achieved": round(achieved, 1), "peak": peak,
                      "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": BYTES_PER_SAMPLE_FUSED * ns, "bytes_per_sample": BYTES_PER_SAMPLE_FUSED,
