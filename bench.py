@@ -551,19 +551,25 @@ def ours(args):
             barrier()
         return res
 
-    def all_ranks_at_once(dst, src, n):
-        """The same plain copy with every rank copying at the same time, between buffers that already exist: GB/s of the slowest rank."""
+    own_rate = {}
+
+    def all_ranks_at_once(dst, src, n, key=None):
+        """The same plain copy with every rank copying at the same time, between buffers that already exist: GB/s of the slowest
+        rank (this rank's own rate is kept in own_rate[key])."""
         if world == 1:
             return None
-        times = []
+        times, mine = [], []
         for _ in range(2):
             barrier()
             h.event_record(2); h.memcpy(dst, src, n); h.event_record(3)
-            times.append(allmax(h.event_elapsed_ms(2, 3)))
+            mine.append(h.event_elapsed_ms(2, 3))
+            times.append(allmax(mine[-1]))
+        if key:
+            own_rate[key] = n / (min(mine) * 1e-3) / 1e9
         return n / (min(times) * 1e-3) / 1e9
 
     h2d_gbs, _ = pcie(pg.PCIE_H2D)
-    h2d_conc = all_ranks_at_once(d_in, pin, nbytes)
+    h2d_conc = all_ranks_at_once(d_in, pin, nbytes, "h2d")
     sums = []
 
     def e2e_step():
@@ -591,6 +597,39 @@ def ours(args):
     if h2d_conc:
         e2e["pcie_h2d_gbs_all_ranks_at_once"] = round(h2d_conc, 2)
         e2e["frac_of_concurrent_pcie"] = round(e2e_gbs / h2d_conc, 4)
+
+    # -- the same N x cfg2 recording, host-fed, with shards proportional to each GPU's measured host-link rate: on a box whose
+    #    GPUs do not all reach host memory equally fast (profiles/r2_h2d_matrix_8gpu.md) equal shards wait for the slowest link
+    e2e_bal = None
+    if world > 1 and not args.no_balanced:
+        rates = sharding.allgather_float(own_rate["h2d"])
+        first_b, count_b = pg.shard_range_weighted(nbuf * world, rates, rank)
+        nb_b = count_b * BUF
+        ns_b = nb_b // 6
+        d_gen = h.dev_alloc(max(nb_b, 1))
+        h.generate(d_gen, nb_b, pg.SYNTH_RANDOM, pg.SYNTH_SEED, first_b * BUF)
+        pin_b = h.host_alloc(max(nb_b, 1))
+        h.memcpy(pin_b, d_gen, nb_b)
+        h.dev_free(d_gen)
+        d_ib, d_fb = h.dev_alloc(max(ns_b * 8, 1)), h.dev_alloc(max(ns_b * 8, 1))
+        sums_b = []
+
+        def bal_step():
+            h.unpack(pin_b, nb_b, d_ib, d_fb, FUSED | pg.ASYNC | pg.CHECKSUM)
+            sums_b.append(h.get_checksums())
+
+        ms_bal = timed(bal_step, e2e_steps, 2)
+        assert len(set(sums_b)) == 1 and sums_b[0] == (h.checksum(d_ib, ns_b * 2), h.checksum(d_fb, ns_b * 2))
+        # a different sharding of the SAME recording: the shard checksums must add up to the same whole-recording checksum
+        assert sharding.allreduce_sum_u64(h.checksum(d_fb, ns_b * 2, first_index=first_b * 2048)) == recording_checksum
+        shares = sharding.allgather_float(float(count_b))
+        e2e_bal = {"value": round(total_samples / (ms_bal * 1e-3) / 1e6, 1), "unit": UNIT, "ms_per_step": round(ms_bal, 3),
+                   "h2d_bytes_per_step_all_gpus": int(nbytes * world), "d2h_bytes_per_step": 16,
+                   "aggregate_h2d_gbs": round(nbytes * world / (ms_bal * 1e-3) / 1e9, 1),
+                   "link_gbs_per_rank": [round(r, 1) for r in rates], "transfers_per_rank": [int(c) for c in shares],
+                   "what": "the same call on the same N x cfg2 recording, sharded with perseus_gpu_shard_range_weighted by each rank's rate in the "
+                           "concurrent plain pinned copy measured just before; shard checksums add up to the equal-shard recording checksum"}
+        h.host_free(pin_b); h.dev_free(d_ib); h.dev_free(d_fb)
 
     e2e_rt = None
     if not args.no_roundtrip:
@@ -707,6 +746,8 @@ def ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
+    if e2e_bal:
+        line["e2e_link_weighted_shards"] = e2e_bal
     if e2e_rt:
         line["e2e_roundtrip"] = e2e_rt
     if e2e_cb:
@@ -752,6 +793,7 @@ def main():
     ap.add_argument("--slots", type=int, default=0, help="staging slots of the host-pointer pipeline (0 = library default, 3)")
     ap.add_argument("--no-workloads", action="store_true", help="skip the cfg3 / cfg4 sub-records")
     ap.add_argument("--no-roundtrip", action="store_true")
+    ap.add_argument("--no-balanced", action="store_true", help="skip the link-weighted sharding of the end-to-end leg (N > 1)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-callback", action="store_true")
     ap.add_argument("--no-probe", action="store_true")

@@ -316,6 +316,12 @@ int perseus_gpu_probe_pcie(perseus_gpu *h, int kind, size_t nbytes, size_t d2h_n
 /* Shard `shard` of `nshards` of a recording of `total_buffers` transfers gets
  * [*first, *first + *count) with first = floor(shard*total/nshards). */
 int perseus_gpu_shard_range(uint64_t total_buffers, int nshards, int shard, uint64_t *first, uint64_t *count);
+/* Same, with shards proportional to weights[0..nshards) (>= 0, not all zero) -- e.g. each GPU's measured host-link rate, for
+ * host-fed recordings on a box whose GPUs do not all reach host memory equally fast: shard s gets
+ * [floor(total * W(s) / W(nshards)), floor(total * W(s+1) / W(nshards))) with W(k) = weights[0] + ... + weights[k-1].
+ * Every rank must pass the same weights.  Equal weights give exactly perseus_gpu_shard_range. */
+int perseus_gpu_shard_range_weighted(uint64_t total_buffers, int nshards, const double *weights, int shard,
+                                     uint64_t *first, uint64_t *count);
 
 /* ---- virtual receiver: the reference's delivery semantics without the hardware ----------------
  * Reproduces what perseus_start_async_input() + perseus-in.c do with a real device: a ring of

@@ -147,6 +147,7 @@ def lib() -> C.CDLL:
         "perseus_gpu_checksum": (ci, [vp, vp, sz, u64, P(u64)]),
         "perseus_gpu_verify": (ci, [vp, vp, sz, vp, vp, C.c_uint, P(u64), P(u64)]),
         "perseus_gpu_shard_range": (ci, [u64, ci, ci, P(u64), P(u64)]),
+        "perseus_gpu_shard_range_weighted": (ci, [u64, ci, P(C.c_double), ci, P(u64), P(u64)]),
         "perseus_gpu_probe_hbm": (ci, [vp, ci, sz, ci, P(C.c_double)]),
         "perseus_gpu_probe_pcie": (ci, [vp, ci, sz, sz, ci, P(C.c_double), P(C.c_double)]),
         "perseus_vrx_open": (ci, [P(vp), P(VrxConfig)]),
@@ -180,6 +181,14 @@ def check(rc: int) -> int:
 def shard_range(total_buffers: int, nshards: int, shard: int) -> tuple[int, int]:
     a, n = C.c_uint64(), C.c_uint64()
     check(lib().perseus_gpu_shard_range(total_buffers, nshards, shard, C.byref(a), C.byref(n)))
+    return a.value, n.value
+
+
+def shard_range_weighted(total_buffers: int, weights, shard: int) -> tuple[int, int]:
+    """Shards proportional to `weights` (e.g. each GPU's measured host-link rate)."""
+    a, n = C.c_uint64(), C.c_uint64()
+    w = (C.c_double * len(weights))(*weights)
+    check(lib().perseus_gpu_shard_range_weighted(total_buffers, len(weights), w, shard, C.byref(a), C.byref(n)))
     return a.value, n.value
 
 

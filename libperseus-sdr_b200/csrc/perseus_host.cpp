@@ -86,4 +86,29 @@ int perseus_gpu_shard_range(uint64_t total, int nshards, int shard, uint64_t *fi
 	return 0;
 }
 
+int perseus_gpu_shard_range_weighted(uint64_t total, int nshards, const double *weights, int shard, uint64_t *first, uint64_t *count)
+{
+	if (nshards < 1 || shard < 0 || shard >= nshards || !weights || !first || !count) return pg::fail(PERSEUS_GPU_ERRPARAM, "bad shard arguments");
+	long double sum = 0.0L, before = 0.0L;
+	bool equal = true;
+	for (int k = 0; k < nshards; ++k) {
+		if (!(weights[k] >= 0.0) || weights[k] > 1e300) return pg::fail(PERSEUS_GPU_ERRPARAM, "weight %d is negative or not finite", k);
+		if (weights[k] != weights[0]) equal = false;
+		if (k < shard) before += (long double)weights[k];
+		sum += (long double)weights[k];
+	}
+	if (!(sum > 0.0L)) return pg::fail(PERSEUS_GPU_ERRPARAM, "all weights are zero");
+	if (equal) return perseus_gpu_shard_range(total, nshards, shard, first, count);   // exact integer arithmetic
+	auto cut = [&](long double w) -> uint64_t {
+		long double x = (long double)total * (w / sum);
+		uint64_t b = x <= 0.0L ? 0 : (uint64_t)x;
+		return b > total ? total : b;
+	};
+	const uint64_t a = shard == 0 ? 0 : cut(before);
+	const uint64_t b = shard == nshards - 1 ? total : cut(before + (long double)weights[shard]);
+	*first = a;
+	*count = b > a ? b - a : 0;
+	return 0;
+}
+
 }  // extern "C"

@@ -44,6 +44,18 @@ def allreduce_sum_u64(x: int) -> int:
     return sum(int(v) << (16 * k) for k, v in enumerate(limbs.tolist())) & MASK64
 
 
+def allgather_float(x: float) -> list[float]:
+    """Every rank's value, in rank order (e.g. the host-link rates that weight the shards of a host-fed recording)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [float(x)]
+    mine = torch.tensor([x], dtype=torch.float64, device=_device_for(dist))
+    out = [torch.zeros_like(mine) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, mine)
+    return [float(t.item()) for t in out]
+
+
 def gather_ranges(first: int, count: int) -> list[tuple[int, int]]:
     """Every rank's (first, count), in rank order."""
     import torch

@@ -89,3 +89,34 @@ def test_reference_queue_feeds_oracle_unpack(coracle):
     rq.close()
     want = coracle.unpack(coracle.synth_random(24 * 6144, 99), O.MODE_I32)
     assert np.array_equal(np.concatenate(chunks), want)
+
+
+# ------------------------------------------------------------------ property test: arbitrary fault schedules
+
+from hypothesis import HealthCheck, given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=120, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(n=st.integers(1, 150), drop=st.integers(0, 11), swap=st.integers(0, 11), timeout=st.integers(0, 11),
+       fail_at=st.integers(0, 60), status=st.sampled_from([1, 4, 5, 6]), size=st.sampled_from([(6144, 512), (12288, 512), (510, 510), (510 * 7, 510)]))
+def test_virtual_receiver_equals_reference_queue_for_any_fault_schedule(pg, n, drop, swap, timeout, fail_at, status, size):
+    """Hypothesis: any combination of short / swapped / timed-out transfers and one failing transfer, any length of run:
+    perseus_vrx_* makes exactly the callbacks the reference's completion handler (perseus-in.c:187-264) makes."""
+    buffersize, ep = size
+    faults = dict(drop_every=drop, swap_every=swap, timeout_every=timeout, fail_at=fail_at, fail_status=status if fail_at else 0)
+    ref_calls, calls = [], []
+    rq = O.RefQueue(seed=7, **faults)
+    rq.start(buffersize, lambda buf, sz, extra: ref_calls.append((buf, sz, bytes((C.c_ubyte * sz).from_address(buf)))) or 0)
+    pumped = rq.pump(n)
+    received = rq.bytes_received
+    rq.stop()
+    rq.close()
+    v = pg.VirtualReceiver(sample_rate=2_000_000, ep_max_packet=ep, seed=7, **faults)
+    st_ = v.run(buffersize, lambda buf, sz, extra: calls.append((buf, sz, bytes((C.c_ubyte * sz).from_address(buf)))) or 0, None, n)
+    v.close()
+    assert pumped == n
+    assert len(calls) == len(ref_calls) == st_["delivered"]
+    if calls:
+        assert [(a - calls[0][0], s, b) for a, s, b in calls] == [(a - ref_calls[0][0], s, b) for a, s, b in ref_calls]
+    assert st_["bytes_received"] == received
+    assert st_["delivered"] + st_["dropped_short"] + st_["dropped_sequence"] + st_["timed_out"] + st_["retired"] == n

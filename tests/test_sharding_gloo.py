@@ -33,7 +33,12 @@ def _worker(rank, world, initfile, q):
         total = sh.allreduce_sum_u64(mine)
         slowest = sh.allreduce_max(1.0 + rank)
         big = sh.allreduce_sum_u64((1 << 64) - 1 - rank)                                      # wraps modulo 2^64
-        q.put((rank, ranges, total, slowest, big))
+        # link-weighted shards (bench.py's host-fed leg): every rank contributes its "link rate", all ranks cut the same recording
+        rates = sh.allgather_float(10.0 + 7.5 * rank)
+        wfirst, wcount = pg.shard_range_weighted(NBUF, rates, rank)
+        wwire = pg.synth_fill(wcount * 6144, pg.SYNTH_RANDOM, pg.SYNTH_SEED, wfirst * 6144)
+        wtotal = sh.allreduce_sum_u64(co.checksum32(co.unpack(wwire, O.MODE_F32).reshape(-1), first_index=wfirst * 2048))
+        q.put((rank, ranges, total, slowest, big, rates, (wfirst, wcount), wtotal))
     finally:
         dist.destroy_process_group()
 
@@ -53,7 +58,11 @@ def test_shards_combine_over_gloo(world, coracle):
             assert p.exitcode == 0
     whole = coracle.unpack(coracle.synth_random(NBUF * 6144, O.SYNTH_SEED), O.MODE_F32).reshape(-1)
     want = coracle.checksum32(whole)
-    for rank, ranges, total, slowest, big in res:
+    wranges = {}
+    for rank, ranges, total, slowest, big, rates, wrange, wtotal in res:
+        assert rates == [10.0 + 7.5 * r for r in range(world)]
+        assert wtotal == want                                             # another sharding of the same recording: same checksum
+        wranges[rank] = wrange
         assert total == want                                              # checksum of checksums
         assert slowest == float(world)                                     # max over ranks
         assert big == (sum((1 << 64) - 1 - r for r in range(world))) % (1 << 64)
@@ -62,3 +71,22 @@ def test_shards_combine_over_gloo(world, coracle):
             assert first == pos
             pos += count
         assert pos == NBUF
+    pos = 0
+    for r in range(world):                                                 # weighted shards tile the recording too, bigger for faster links
+        assert wranges[r][0] == pos
+        pos += wranges[r][1]
+    assert pos == NBUF and [wranges[r][1] for r in range(world)] == sorted(wranges[r][1] for r in range(world))
+
+
+def test_weighted_shard_planner(pg):
+    total = 8 * 174_762
+    assert [pg.shard_range_weighted(total, [3.25] * 8, s) for s in range(8)] == [pg.shard_range(total, 8, s) for s in range(8)]
+    rates = [23.3] * 4 + [35.6] * 4                                        # the 8-GPU box of profiles/r2_h2d_matrix_8gpu.md
+    shards = [pg.shard_range_weighted(total, rates, s) for s in range(8)]
+    assert sum(c for _, c in shards) == total and all(shards[k][0] + shards[k][1] == shards[k + 1][0] for k in range(7))
+    assert abs(shards[7][1] / shards[0][1] - 35.6 / 23.3) < 1e-3
+    assert max(c / r for (_, c), r in zip(shards, rates)) / min(c / r for (_, c), r in zip(shards, rates)) < 1.0001   # equal finish times
+    assert [pg.shard_range_weighted(10, [0, 1, 0, 3], s) for s in range(4)] == [(0, 0), (0, 2), (2, 0), (2, 8)]
+    for bad in ([], [0, 0], [1, -1], [float("nan"), 1]):
+        with pytest.raises(pg.PerseusGpuError):
+            pg.shard_range_weighted(10, bad, 0)
