@@ -113,8 +113,8 @@ typedef struct perseus_gpu_config {
 	                             waited this long, checked at every callback (0 = 50 000 us; 0xFFFFFFFF = only
 	                             when full).  At 95 kS/s a transfer arrives every 10.8 ms, so slabs are
 	                             time-bounded, not size-bounded, on a real receiver.                */
-	uint64_t chunk_bytes;     /* host<->device staging chunk for perseus_gpu_unpack with host
-	                             pointers, rounded down to a multiple of 48       (0 = 32 MiB)  */
+	uint64_t chunk_bytes;     /* host<->device staging chunk for perseus_gpu_unpack with host pointers, rounded down to a
+	                             multiple of 12288 (whole pages in and out; of 48 below that)  (0 = 32 MiB)  */
 	perseus_gpu_tuning tuning;
 	uint32_t options;         /* PERSEUS_GPU_OPT_*                                              */
 	uint32_t stage_slots;     /* staging slots of the host-pointer pipeline, 2..8   (0 = 3): chunk c is copied in while

@@ -218,7 +218,12 @@ Mem classify(const void *p)
 	switch (a.type) {
 	case cudaMemoryTypeDevice: return Mem::Device;
 	case cudaMemoryTypeManaged: return Mem::Device;
-	case cudaMemoryTypeHost: return Mem::PinnedHost;
+	case cudaMemoryTypeHost: {
+		// EXPERIMENT (tools only): let the kernel read / write pinned host memory directly over PCIe instead of staging it
+		static const char *zc = getenv("PERSEUS_GPU_EXPERIMENT_ZEROCOPY");
+		if (zc && *zc == '1') return Mem::Device;
+		return Mem::PinnedHost;
+	}
 	default: return Mem::PageableHost;
 	}
 }
@@ -753,7 +758,10 @@ int perseus_gpu_open(perseus_gpu **out, const perseus_gpu_config *ucfg)
 	uint64_t slab = cfg.slab_bytes ? cfg.slab_bytes : (8ull << 20);
 	slab -= slab % 48;
 	uint64_t chunk = cfg.chunk_bytes ? cfg.chunk_bytes : (32ull << 20);
-	chunk -= chunk % 48;
+	// Whole pages on both sides of the link: 12288 wire bytes (3 pages) become 16384 output bytes (4 pages), so every staged
+	// copy starts and ends on a page boundary of the caller's pinned buffers.  The copy engines need that: chunks that are
+	// only 128-byte aligned reach 52.5-53.5 GB/s device->host, page-aligned ones 56.1-56.6 (tools/d2h_probe.py).
+	chunk -= chunk % (chunk >= 12288 ? 12288 : 48);
 	if (slab < 48 || chunk < 48) return fail(PERSEUS_GPU_BUFFERSIZE, "slab_bytes/chunk_bytes must be at least 48");
 
 	perseus_gpu *h = new (std::nothrow) perseus_gpu();
