@@ -525,157 +525,159 @@ def ours(args):
     # -- supporting numbers: single-format kernels (14 B/sample)
     extra = {}
     short = max(3, min(args.steps, 50))
-    for name, flags, oi, of in (("int32_only", pg.OUT_INT32, d_i32, None), ("float_only", pg.OUT_FLOAT, None, d_f32)):
+    for name, flags, oi, of in (() if args.no_single else (("int32_only", pg.OUT_INT32, d_i32, None), ("float_only", pg.OUT_FLOAT, None, d_f32))):
         ms = timed(lambda: h.unpack(d_in, nbytes, oi, of, flags | pg.ASYNC), short, 3)
         gbs = BYTES_PER_SAMPLE_SINGLE * ns / (ms * 1e-3) / 1e9
         extra[name] = {"msamples_per_s": round(total_samples / (ms * 1e-3) / 1e6, 1), "ms_per_step": round(ms, 4),
                        "hbm_gbs_per_gpu": round(gbs, 1), "frac_of_peak": round(gbs / peak, 4)}
 
-    # -- end to end: pinned host wire -> H2D -> unpack (outputs stay on device) -> D2H of the step's result
-    e2e_steps = max(3, min(args.steps, args.e2e_steps))
-    wc_rt = None
-    if args.pinned_wc:   # experiment: write-combined pinned memory (DMA reads need not snoop the CPU caches)
-        wc_rt = C.CDLL("libcudart.so.12")
-        pp = C.c_void_p()
-        assert wc_rt.cudaHostAlloc(C.byref(pp), C.c_size_t(nbytes), C.c_uint(0x04 | 0x01)) == 0   # WriteCombined | Portable
-        pin = pp.value
-    else:
-        pin = h.host_alloc(nbytes)
-    h.memcpy(pin, d_in, nbytes)                                           # the synthetic recording, now in pinned host memory
+    e2e = e2e_bal = e2e_rt = None
+    if not args.no_e2e:
+        # -- end to end: pinned host wire -> H2D -> unpack (outputs stay on device) -> D2H of the step's result
+        e2e_steps = max(3, min(args.steps, args.e2e_steps))
+        wc_rt = None
+        if args.pinned_wc:   # experiment: write-combined pinned memory (DMA reads need not snoop the CPU caches)
+            wc_rt = C.CDLL("libcudart.so.12")
+            pp = C.c_void_p()
+            assert wc_rt.cudaHostAlloc(C.byref(pp), C.c_size_t(nbytes), C.c_uint(0x04 | 0x01)) == 0   # WriteCombined | Portable
+            pin = pp.value
+        else:
+            pin = h.host_alloc(nbytes)
+        h.memcpy(pin, d_in, nbytes)                                           # the synthetic recording, now in pinned host memory
 
-    def pcie(kind, up=256 << 20, down=0):
-        """In-run PCIe roofline of THIS GPU alone: plain pinned copies by the library's probe (ranks take turns)."""
-        res = None
-        for r in range(world):
-            if r == rank:
-                res = h.probe_pcie(kind, up, down, 3)
-            barrier()
-        return res
+        def pcie(kind, up=256 << 20, down=0):
+            """In-run PCIe roofline of THIS GPU alone: plain pinned copies by the library's probe (ranks take turns)."""
+            res = None
+            for r in range(world):
+                if r == rank:
+                    res = h.probe_pcie(kind, up, down, 3)
+                barrier()
+            return res
 
-    own_rate = {}
+        own_rate = {}
 
-    def all_ranks_at_once(dst, src, n, key=None):
-        """The same plain copy with every rank copying at the same time, between buffers that already exist: GB/s of the slowest
-        rank (this rank's own rate is kept in own_rate[key])."""
-        if world == 1:
-            return None
-        times, mine = [], []
-        for _ in range(2):
-            barrier()
-            h.event_record(2); h.memcpy(dst, src, n); h.event_record(3)
-            mine.append(h.event_elapsed_ms(2, 3))
-            times.append(allmax(mine[-1]))
-        if key:
-            own_rate[key] = n / (min(mine) * 1e-3) / 1e9
-        return n / (min(times) * 1e-3) / 1e9
+        def all_ranks_at_once(dst, src, n, key=None):
+            """The same plain copy with every rank copying at the same time, between buffers that already exist: GB/s of the slowest
+            rank (this rank's own rate is kept in own_rate[key])."""
+            if world == 1:
+                return None
+            times, mine = [], []
+            for _ in range(2):
+                barrier()
+                h.event_record(2); h.memcpy(dst, src, n); h.event_record(3)
+                mine.append(h.event_elapsed_ms(2, 3))
+                times.append(allmax(mine[-1]))
+            if key:
+                own_rate[key] = n / (min(mine) * 1e-3) / 1e9
+            return n / (min(times) * 1e-3) / 1e9
 
-    h2d_gbs, _ = pcie(pg.PCIE_H2D)
-    h2d_conc = all_ranks_at_once(d_in, pin, nbytes, "h2d")
-    sums = []
+        h2d_gbs, _ = pcie(pg.PCIE_H2D)
+        h2d_conc = all_ranks_at_once(d_in, pin, nbytes, "h2d")
+        sums = []
 
-    def e2e_step():
-        # chunked H2D + unpack kernels + per-chunk checksum kernels, overlapped on the handle's streams ...
-        h.unpack(pin, nbytes, d_i32, d_f32, FUSED | pg.ASYNC | pg.CHECKSUM)
-        sums.append(h.get_checksums())                                   # ... then wait and read the 16-byte result
-
-    s0 = h.stats()
-    ms_e2e = timed(e2e_step, e2e_steps, 2)
-    s1 = h.stats()
-    assert len(set(sums)) == 1, "end-to-end results changed between steps"
-    assert sums[0] == (h.checksum(d_i32, ns * 2), h.checksum(d_f32, ns * 2)), "overlapped checksum differs from the whole-output checksum"
-    h2d_per_step = (s1["h2d_bytes"] - s0["h2d_bytes"]) // (e2e_steps + 2)
-    e2e_val = total_samples / (ms_e2e * 1e-3) / 1e6
-    e2e_gbs = 6 * ns / (ms_e2e * 1e-3) / 1e9
-    e2e = {"value": round(e2e_val, 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d_per_step), "d2h_bytes_per_step": 16,
-           "ms_per_step": round(ms_e2e, 3), "steps": e2e_steps,
-           "what": "perseus_gpu_unpack(pinned host wire -> device int32+float, PERSEUS_GPU_CHECKSUM): H2D in chunks on the copy-in stream, "
-                   "unpack and checksum kernels behind them on the launch stream, then the checksums of both outputs read back (outputs stay "
-                   "in HBM, as north_star's end-to-end mode specifies)",
-           "h2d_gbs_per_gpu": round(e2e_gbs, 2), "pcie_h2d_gbs_measured": round(h2d_gbs, 2),
-           "frac_of_measured_pcie": round(e2e_gbs / h2d_gbs, 4),
-           "frac_of_gen5_x16_theory": round(e2e_gbs / PCIE_GEN5_X16_GBS, 4),
-           "pinned_memory": "write-combined" if args.pinned_wc else "default (cudaHostAlloc portable)"}
-    if h2d_conc:
-        e2e["pcie_h2d_gbs_all_ranks_at_once"] = round(h2d_conc, 2)
-        e2e["frac_of_concurrent_pcie"] = round(e2e_gbs / h2d_conc, 4)
-
-    # -- the same N x cfg2 recording, host-fed, with shards proportional to each GPU's measured host-link rate: on a box whose
-    #    GPUs do not all reach host memory equally fast (profiles/r2_h2d_matrix_8gpu.md) equal shards wait for the slowest link
-    e2e_bal = None
-    if world > 1 and not args.no_balanced:
-        rates = sharding.allgather_float(own_rate["h2d"])
-        first_b, count_b = pg.shard_range_weighted(nbuf * world, rates, rank)
-        nb_b = count_b * BUF
-        ns_b = nb_b // 6
-        d_gen = h.dev_alloc(max(nb_b, 1))
-        h.generate(d_gen, nb_b, pg.SYNTH_RANDOM, pg.SYNTH_SEED, first_b * BUF)
-        pin_b = h.host_alloc(max(nb_b, 1))
-        h.memcpy(pin_b, d_gen, nb_b)
-        h.dev_free(d_gen)
-        d_ib, d_fb = h.dev_alloc(max(ns_b * 8, 1)), h.dev_alloc(max(ns_b * 8, 1))
-        sums_b = []
-
-        def bal_step():
-            h.unpack(pin_b, nb_b, d_ib, d_fb, FUSED | pg.ASYNC | pg.CHECKSUM)
-            sums_b.append(h.get_checksums())
-
-        ms_bal = timed(bal_step, e2e_steps, 2)
-        assert len(set(sums_b)) == 1 and sums_b[0] == (h.checksum(d_ib, ns_b * 2), h.checksum(d_fb, ns_b * 2))
-        # a different sharding of the SAME recording: the shard checksums must add up to the same whole-recording checksum
-        assert sharding.allreduce_sum_u64(h.checksum(d_fb, ns_b * 2, first_index=first_b * 2048)) == recording_checksum
-        shares = sharding.allgather_float(float(count_b))
-        e2e_bal = {"value": round(total_samples / (ms_bal * 1e-3) / 1e6, 1), "unit": UNIT, "ms_per_step": round(ms_bal, 3),
-                   "h2d_bytes_per_step_all_gpus": int(nbytes * world), "d2h_bytes_per_step": 16,
-                   "aggregate_h2d_gbs": round(nbytes * world / (ms_bal * 1e-3) / 1e9, 1),
-                   "link_gbs_per_rank": [round(r, 1) for r in rates], "transfers_per_rank": [int(c) for c in shares],
-                   "what": "the same call on the same N x cfg2 recording, sharded with perseus_gpu_shard_range_weighted by each rank's rate in the "
-                           "concurrent plain pinned copy measured just before; shard checksums add up to the equal-shard recording checksum"}
-        h.host_free(pin_b); h.dev_free(d_ib); h.dev_free(d_fb)
-
-    e2e_rt = None
-    if not args.no_roundtrip:
-        po_i, po_f = h.host_alloc(ns * 8), h.host_alloc(ns * 8)
-        rt_steps = max(2, min(e2e_steps, 5))
-        _, d2h_gbs = pcie(pg.PCIE_D2H)
-        d2h_conc = all_ranks_at_once(po_f, d_f32, ns * 8)
-        # plain copies of the round trip's own traffic, both directions at once: the whole recording up (6 B/sample) while the
-        # whole output comes down (16 B/sample fused, 8 B/sample one format), each as ONE cudaMemcpyAsync on its own stream
-        dup16_up, dup16_down = pcie(pg.PCIE_DUPLEX, nbytes, ns * 16)
-        dup8_up, dup8_down = pcie(pg.PCIE_DUPLEX, nbytes, ns * 8)
-
-        def copy_bound_ms(up_gbs, down_gbs, down_bytes_per_sample):
-            return max(6 * ns / (up_gbs * 1e9), down_bytes_per_sample * ns / (down_gbs * 1e9)) * 1e3
+        def e2e_step():
+            # chunked H2D + unpack kernels + per-chunk checksum kernels, overlapped on the handle's streams ...
+            h.unpack(pin, nbytes, d_i32, d_f32, FUSED | pg.ASYNC | pg.CHECKSUM)
+            sums.append(h.get_checksums())                                   # ... then wait and read the 16-byte result
 
         s0 = h.stats()
-        ms_rt = timed(lambda: h.unpack(pin, nbytes, po_i, po_f, FUSED), rt_steps, 1)
+        ms_e2e = timed(e2e_step, e2e_steps, 2)
         s1 = h.stats()
-        tail = np.ctypeslib.as_array((C.c_uint32 * 2048).from_address(po_f + ns * 8 - 8192))
-        assert np.array_equal(tail, h.to_host(d_f32 + ns * 8 - 8192, 8192, np.uint32)), "round-trip output differs"
-        ms_rt1 = timed(lambda: h.unpack(pin, nbytes, None, po_f, pg.OUT_FLOAT), rt_steps, 1)
-        d2h_rate = 16 * ns / (ms_rt * 1e-3) / 1e9
-        e2e_rt = {"value": round(total_samples / (ms_rt * 1e-3) / 1e6, 1), "unit": UNIT, "ms_per_step": round(ms_rt, 3),
-                  "h2d_bytes_per_step": int((s1["h2d_bytes"] - s0["h2d_bytes"]) // (rt_steps + 1)),
-                  "d2h_bytes_per_step": int((s1["d2h_bytes"] - s0["d2h_bytes"]) // (rt_steps + 1)),
-                  "what": "same call with pinned HOST outputs: both formats copied back (16 B/sample D2H, full duplex with the 6 B/sample H2D); "
-                          "copy-in, kernels and copy-out each on their own stream, three staging slots",
-                  "d2h_gbs_per_gpu": round(d2h_rate, 2), "pcie_d2h_gbs_measured": round(d2h_gbs, 2),
-                  "frac_of_d2h_peak": round(d2h_rate / d2h_gbs, 4),
-                  "duplex_plain_copies_gbs": {"h2d": round(dup16_up, 2), "d2h": round(dup16_down, 2),
-                                              "what": "the same bytes as two plain pinned copies queued at once: the recording up, both outputs' worth down (perseus_gpu_probe_pcie)"},
-                  "frac_of_duplex_copy_bound": round(copy_bound_ms(dup16_up, dup16_down, 16) / ms_rt, 4),
-                  "single_format": {"value": round(total_samples / (ms_rt1 * 1e-3) / 1e6, 1), "ms_per_step": round(ms_rt1, 3),
-                                    "d2h_gbs_per_gpu": round(8 * ns / (ms_rt1 * 1e-3) / 1e9, 2),
-                                    "frac_of_d2h_peak": round(8 * ns / (ms_rt1 * 1e-3) / 1e9 / d2h_gbs, 4),
-                                    "frac_of_duplex_copy_bound": round(copy_bound_ms(dup8_up, dup8_down, 8) / ms_rt1, 4),
-                                    "what": "float only: 8 B/sample D2H against 6 B/sample H2D"}}
-        if d2h_conc:
-            e2e_rt["pcie_d2h_gbs_all_ranks_at_once"] = round(d2h_conc, 2)
-            e2e_rt["frac_of_concurrent_d2h"] = round(d2h_rate / d2h_conc, 4)
-        h.host_free(po_i); h.host_free(po_f)
-    if wc_rt is not None:
-        wc_rt.cudaFreeHost(C.c_void_p(pin))
-    else:
-        h.host_free(pin)
+        assert len(set(sums)) == 1, "end-to-end results changed between steps"
+        assert sums[0] == (h.checksum(d_i32, ns * 2), h.checksum(d_f32, ns * 2)), "overlapped checksum differs from the whole-output checksum"
+        h2d_per_step = (s1["h2d_bytes"] - s0["h2d_bytes"]) // (e2e_steps + 2)
+        e2e_val = total_samples / (ms_e2e * 1e-3) / 1e6
+        e2e_gbs = 6 * ns / (ms_e2e * 1e-3) / 1e9
+        e2e = {"value": round(e2e_val, 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d_per_step), "d2h_bytes_per_step": 16,
+               "ms_per_step": round(ms_e2e, 3), "steps": e2e_steps,
+               "what": "perseus_gpu_unpack(pinned host wire -> device int32+float, PERSEUS_GPU_CHECKSUM): H2D in chunks on the copy-in stream, "
+                       "unpack and checksum kernels behind them on the launch stream, then the checksums of both outputs read back (outputs stay "
+                       "in HBM, as north_star's end-to-end mode specifies)",
+               "h2d_gbs_per_gpu": round(e2e_gbs, 2), "pcie_h2d_gbs_measured": round(h2d_gbs, 2),
+               "frac_of_measured_pcie": round(e2e_gbs / h2d_gbs, 4),
+               "frac_of_gen5_x16_theory": round(e2e_gbs / PCIE_GEN5_X16_GBS, 4),
+               "pinned_memory": "write-combined" if args.pinned_wc else "default (cudaHostAlloc portable)"}
+        if h2d_conc:
+            e2e["pcie_h2d_gbs_all_ranks_at_once"] = round(h2d_conc, 2)
+            e2e["frac_of_concurrent_pcie"] = round(e2e_gbs / h2d_conc, 4)
+
+        # -- the same N x cfg2 recording, host-fed, with shards proportional to each GPU's measured host-link rate: on a box whose
+        #    GPUs do not all reach host memory equally fast (profiles/r2_h2d_matrix_8gpu.md) equal shards wait for the slowest link
+        e2e_bal = None
+        if world > 1 and not args.no_balanced:
+            rates = sharding.allgather_float(own_rate["h2d"])
+            first_b, count_b = pg.shard_range_weighted(nbuf * world, rates, rank)
+            nb_b = count_b * BUF
+            ns_b = nb_b // 6
+            d_gen = h.dev_alloc(max(nb_b, 1))
+            h.generate(d_gen, nb_b, pg.SYNTH_RANDOM, pg.SYNTH_SEED, first_b * BUF)
+            pin_b = h.host_alloc(max(nb_b, 1))
+            h.memcpy(pin_b, d_gen, nb_b)
+            h.dev_free(d_gen)
+            d_ib, d_fb = h.dev_alloc(max(ns_b * 8, 1)), h.dev_alloc(max(ns_b * 8, 1))
+            sums_b = []
+
+            def bal_step():
+                h.unpack(pin_b, nb_b, d_ib, d_fb, FUSED | pg.ASYNC | pg.CHECKSUM)
+                sums_b.append(h.get_checksums())
+
+            ms_bal = timed(bal_step, e2e_steps, 2)
+            assert len(set(sums_b)) == 1 and sums_b[0] == (h.checksum(d_ib, ns_b * 2), h.checksum(d_fb, ns_b * 2))
+            # a different sharding of the SAME recording: the shard checksums must add up to the same whole-recording checksum
+            assert sharding.allreduce_sum_u64(h.checksum(d_fb, ns_b * 2, first_index=first_b * 2048)) == recording_checksum
+            shares = sharding.allgather_float(float(count_b))
+            e2e_bal = {"value": round(total_samples / (ms_bal * 1e-3) / 1e6, 1), "unit": UNIT, "ms_per_step": round(ms_bal, 3),
+                       "h2d_bytes_per_step_all_gpus": int(nbytes * world), "d2h_bytes_per_step": 16,
+                       "aggregate_h2d_gbs": round(nbytes * world / (ms_bal * 1e-3) / 1e9, 1),
+                       "link_gbs_per_rank": [round(r, 1) for r in rates], "transfers_per_rank": [int(c) for c in shares],
+                       "what": "the same call on the same N x cfg2 recording, sharded with perseus_gpu_shard_range_weighted by each rank's rate in the "
+                               "concurrent plain pinned copy measured just before; shard checksums add up to the equal-shard recording checksum"}
+            h.host_free(pin_b); h.dev_free(d_ib); h.dev_free(d_fb)
+
+        e2e_rt = None
+        if not args.no_roundtrip:
+            po_i, po_f = h.host_alloc(ns * 8), h.host_alloc(ns * 8)
+            rt_steps = max(2, min(e2e_steps, 5))
+            _, d2h_gbs = pcie(pg.PCIE_D2H)
+            d2h_conc = all_ranks_at_once(po_f, d_f32, ns * 8)
+            # plain copies of the round trip's own traffic, both directions at once: the whole recording up (6 B/sample) while the
+            # whole output comes down (16 B/sample fused, 8 B/sample one format), each as ONE cudaMemcpyAsync on its own stream
+            dup16_up, dup16_down = pcie(pg.PCIE_DUPLEX, nbytes, ns * 16)
+            dup8_up, dup8_down = pcie(pg.PCIE_DUPLEX, nbytes, ns * 8)
+
+            def copy_bound_ms(up_gbs, down_gbs, down_bytes_per_sample):
+                return max(6 * ns / (up_gbs * 1e9), down_bytes_per_sample * ns / (down_gbs * 1e9)) * 1e3
+
+            s0 = h.stats()
+            ms_rt = timed(lambda: h.unpack(pin, nbytes, po_i, po_f, FUSED), rt_steps, 1)
+            s1 = h.stats()
+            tail = np.ctypeslib.as_array((C.c_uint32 * 2048).from_address(po_f + ns * 8 - 8192))
+            assert np.array_equal(tail, h.to_host(d_f32 + ns * 8 - 8192, 8192, np.uint32)), "round-trip output differs"
+            ms_rt1 = timed(lambda: h.unpack(pin, nbytes, None, po_f, pg.OUT_FLOAT), rt_steps, 1)
+            d2h_rate = 16 * ns / (ms_rt * 1e-3) / 1e9
+            e2e_rt = {"value": round(total_samples / (ms_rt * 1e-3) / 1e6, 1), "unit": UNIT, "ms_per_step": round(ms_rt, 3),
+                      "h2d_bytes_per_step": int((s1["h2d_bytes"] - s0["h2d_bytes"]) // (rt_steps + 1)),
+                      "d2h_bytes_per_step": int((s1["d2h_bytes"] - s0["d2h_bytes"]) // (rt_steps + 1)),
+                      "what": "same call with pinned HOST outputs: both formats copied back (16 B/sample D2H, full duplex with the 6 B/sample H2D); "
+                              "copy-in, kernels and copy-out each on their own stream, three staging slots",
+                      "d2h_gbs_per_gpu": round(d2h_rate, 2), "pcie_d2h_gbs_measured": round(d2h_gbs, 2),
+                      "frac_of_d2h_peak": round(d2h_rate / d2h_gbs, 4),
+                      "duplex_plain_copies_gbs": {"h2d": round(dup16_up, 2), "d2h": round(dup16_down, 2),
+                                                  "what": "the same bytes as two plain pinned copies queued at once: the recording up, both outputs' worth down (perseus_gpu_probe_pcie)"},
+                      "frac_of_duplex_copy_bound": round(copy_bound_ms(dup16_up, dup16_down, 16) / ms_rt, 4),
+                      "single_format": {"value": round(total_samples / (ms_rt1 * 1e-3) / 1e6, 1), "ms_per_step": round(ms_rt1, 3),
+                                        "d2h_gbs_per_gpu": round(8 * ns / (ms_rt1 * 1e-3) / 1e9, 2),
+                                        "frac_of_d2h_peak": round(8 * ns / (ms_rt1 * 1e-3) / 1e9 / d2h_gbs, 4),
+                                        "frac_of_duplex_copy_bound": round(copy_bound_ms(dup8_up, dup8_down, 8) / ms_rt1, 4),
+                                        "what": "float only: 8 B/sample D2H against 6 B/sample H2D"}}
+            if d2h_conc:
+                e2e_rt["pcie_d2h_gbs_all_ranks_at_once"] = round(d2h_conc, 2)
+                e2e_rt["frac_of_concurrent_d2h"] = round(d2h_rate / d2h_conc, 4)
+            h.host_free(po_i); h.host_free(po_f)
+        if wc_rt is not None:
+            wc_rt.cudaFreeHost(C.c_void_p(pin))
+        else:
+            h.host_free(pin)
 
     # -- the literal drop-in: 6144-byte transfers through perseus_gpu_input_callback (one host thread, like the
     #    reference's poll thread), delivered by the virtual receiver from its 8-slot pageable ring
@@ -799,10 +801,13 @@ def main():
     ap.add_argument("--slots", type=int, default=0, help="staging slots of the host-pointer pipeline (0 = library default, 3)")
     ap.add_argument("--no-workloads", action="store_true", help="skip the cfg3 / cfg4 sub-records")
     ap.add_argument("--no-roundtrip", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip every host-fed leg (the line then has e2e: null)")
+    ap.add_argument("--no-single", action="store_true", help="skip the one-format kernels")
     ap.add_argument("--no-balanced", action="store_true", help="skip the link-weighted sharding of the end-to-end leg (N > 1)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-callback", action="store_true")
     ap.add_argument("--no-probe", action="store_true")
+    ap.add_argument("--headline-only", action="store_true", help="only the HBM-resident fused leg (the short command ncu wraps for the launch list)")
     ap.add_argument("--autotune", action="store_true", help="let the library measure its pipeline geometry on this device first")
     ap.add_argument("--pinned-wc", action="store_true", help="experiment: end-to-end input in write-combined pinned memory")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4"],
@@ -812,6 +817,9 @@ def main():
     for k in ("variant", "tile", "stages", "ctas", "store"):
         ap.add_argument(f"--{k}", type=int, default=0)
     args = ap.parse_args()
+    if args.headline_only:
+        args.no_probe = args.no_roundtrip = args.no_cpu = args.no_callback = args.no_workloads = args.no_balanced = True
+        args.no_e2e = args.no_single = True
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3                                   # timing rule: at least 3 warm-up steps
     if args.gpus > 1 and "RANK" not in os.environ and args.impl == "ours":        # convenience: relaunch ourselves under torchrun
