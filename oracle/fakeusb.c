@@ -242,9 +242,38 @@ int libusb_handle_events_timeout(libusb_context *ctx, struct timeval *tv)
 
 /* ================================================================= enumeration and handles */
 
+int fakeusb_plug(const fakeusb_config *cfg);
+
+/* The reference's own APPLICATION (examples/perseustest.c, built unmodified as oracle/_ref/perseustest_ref) has no place to
+ * call fakeusb_plug(), so the receiver can also be plugged in from the environment: FAKEUSB_AUTOPLUG=1 and optionally
+ * FAKEUSB_LIMIT, FAKEUSB_SEED, FAKEUSB_EP, FAKEUSB_REALTIME, FAKEUSB_DROP_EVERY, FAKEUSB_SWAP_EVERY, FAKEUSB_TIMEOUT_EVERY. */
+static uint64_t env_u64(const char *name, uint64_t dflt)
+{
+	const char *v = getenv(name);
+	return v && *v ? strtoull(v, NULL, 0) : dflt;
+}
+
+static void autoplug(void)
+{
+	if (g_present || !env_u64("FAKEUSB_AUTOPLUG", 0)) return;
+	fakeusb_config c;
+	memset(&c, 0, sizeof(c));
+	c.struct_size = sizeof(c);
+	c.seed = env_u64("FAKEUSB_SEED", 0x5045525345555300ull);
+	c.limit = env_u64("FAKEUSB_LIMIT", 0);
+	c.ep_max_packet = (uint32_t)env_u64("FAKEUSB_EP", 512);
+	c.realtime = (uint32_t)env_u64("FAKEUSB_REALTIME", 0);
+	c.drop_every = (uint32_t)env_u64("FAKEUSB_DROP_EVERY", 0);
+	c.swap_every = (uint32_t)env_u64("FAKEUSB_SWAP_EVERY", 0);
+	c.timeout_every = (uint32_t)env_u64("FAKEUSB_TIMEOUT_EVERY", 0);
+	c.serial = (uint32_t)env_u64("FAKEUSB_SERIAL", 1234);
+	fakeusb_plug(&c);
+}
+
 int libusb_init(libusb_context **ctx)
 {
 	if (ctx) *ctx = &g_ctx;
+	autoplug();
 	g_rx.st.inits++;
 	return 0;
 }

@@ -9,6 +9,7 @@
 #define PERSEUS_ORACLE_FAKE_LIBUSB_H
 #include <stdint.h>
 #include <sys/types.h>
+#include <limits.h>   /* the real libusb.h includes it too; examples/perseustest.c relies on that for INT_MAX */
 #include <sys/time.h>
 
 #define LIBUSB_CALL

@@ -95,6 +95,23 @@ def main() -> None:
             codes[f"{ep}:stop_when_not_started"] = {"rc": rc, "message": rl.errorstr()}
     out["start_codes"] = codes
 
+    # the reference's own APPLICATION (examples/perseustest.c + fifo.c, unmodified: oracle/_ref/perseustest_ref) writing its
+    # output file from the synthetic receiver: the `perseustest -o` format, end to end
+    import os
+    from oracle import oracle as Om
+    co = Om.COracle()
+    app = {"args": "-a -d 0 -s 250000 -n 6 -b 1024 -t 1 -o FILE [-p]", "limit": 200, "seed": 77}
+    with tempfile.TemporaryDirectory() as td:
+        for name, flag in (("int32", []), ("float", ["-p"])):
+            out_file = f"{td}/{name}.bin"
+            env = dict(os.environ, FAKEUSB_AUTOPLUG="1", FAKEUSB_LIMIT=str(app["limit"]), FAKEUSB_SEED=str(app["seed"]))
+            subprocess.run([str(ROOT / "oracle" / "_ref" / "perseustest_ref"), "-a", "-d", "0", "-s", "250000", "-n", "6", "-b", "1024", "-t", "1",
+                            "-o", out_file, *flag], env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=60)
+            data = Path(out_file).read_bytes()
+            app[f"{name}_nbytes"] = len(data)
+            app[f"{name}_fnv1a64"] = f"{co.fnv1a64(data):016x}"
+    out["perseustest_app"] = app
+
     (HERE / "reflib.json").write_text(json.dumps(out, indent=1) + "\n")
     print(f"wrote {HERE / 'reflib.json'}: {len(out['rate_choice'])} rate probes, {len(codes)} start codes")
 

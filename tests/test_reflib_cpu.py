@@ -18,7 +18,7 @@ import time
 import numpy as np
 import pytest
 
-from conftest import GOLDEN
+from conftest import GOLDEN, ROOT
 from oracle import oracle as O
 
 GOLD = json.loads((GOLDEN / "reflib.json").read_text())
@@ -247,3 +247,30 @@ def test_reference_poll_thread_paces_like_the_bitstream(reflib):
         ksps = reflib.L.reflib_descr_bytes_received(d) / dt / 6000.0
         assert 800 < ksps < 1100, ksps
         assert len(n) == reflib.L.reflib_descr_bytes_received(d) // 6144
+
+
+APP = ROOT / "oracle" / "_ref" / "perseustest_ref"
+
+
+def run_reference_app(out_file, float_output=False, limit=200, seed=77, rate=250000, extra_env=None):
+    """Runs the reference's own application, unmodified, over the synthetic receiver; returns its exit status."""
+    import os
+    import subprocess
+    env = dict(os.environ, FAKEUSB_AUTOPLUG="1", FAKEUSB_LIMIT=str(limit), FAKEUSB_SEED=str(seed), **(extra_env or {}))
+    args = [str(APP), "-a", "-d", "0", "-s", str(rate), "-n", "6", "-b", "1024", "-t", "1", "-o", str(out_file)] + (["-p"] if float_output else [])
+    return subprocess.run(args, env=env, capture_output=True, text=True, timeout=60)
+
+
+@pytest.mark.skipif(not APP.exists(), reason="oracle/_ref/perseustest_ref not built")
+@pytest.mark.parametrize("float_output,mode,name", [(False, O.MODE_I32, "int32"), (True, O.MODE_F32, "float")])
+def test_reference_application_output_file(coracle, tmp_path, float_output, mode, name):
+    """examples/perseustest.c's main(), unmodified, from argument parsing to fclose: its output file is what the callbacks
+    alone write for the same transfers (oracle/_ref/libperseus_ref.so), and matches the hash frozen in reflib.json."""
+    out = tmp_path / "perseusdata"
+    r = run_reference_app(out, float_output)
+    assert "Perseus receivers found" in r.stderr and "Bye" in r.stderr, r.stderr[-2000:]
+    data = out.read_bytes()
+    wire = coracle.synth_random(200 * 6144, 77)
+    assert data == O.Ref().unpack(wire, mode, chunk=6144).tobytes()
+    g = GOLD["perseustest_app"]
+    assert (len(data), f"{coracle.fnv1a64(data):016x}") == (g[f"{name}_nbytes"], g[f"{name}_fnv1a64"])

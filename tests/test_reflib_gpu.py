@@ -123,3 +123,25 @@ def test_c_program_linking_libperseus_sdr_and_libperseus_gpu(coracle, tmp_path, 
     assert "200 transfers" in r.stdout
     wire = coracle.synth_random(200 * 6144, seed=O.SYNTH_SEED)
     assert out.read_bytes() == reference_file(wire, mode, 6144)
+
+
+APP = ROOT / "oracle" / "_ref" / "perseustest_ref"
+
+
+@pytest.mark.skipif(not (DEMO.exists() and APP.exists()), reason="oracle/_ref programs not built")
+@pytest.mark.parametrize("flag", [(), ("-p",)])
+def test_gpu_program_writes_the_same_file_as_the_reference_application(tmp_path, flag):
+    """Two programs, the same synthetic receiver, the same command line letters: the reference's own perseustest (unmodified,
+    CPU callbacks) and examples/perseus_gpu_libperseus.c (the same flow with perseus_gpu_input_callback).  Their output
+    files must be byte-identical."""
+    ref_out, gpu_out = tmp_path / "ref.bin", tmp_path / "gpu.bin"
+    env = dict(os.environ, FAKEUSB_AUTOPLUG="1", FAKEUSB_LIMIT="200", FAKEUSB_SEED=str(O.SYNTH_SEED),
+               LD_LIBRARY_PATH=f"{ROOT / 'oracle' / '_ref'}:{ROOT / 'libperseus-sdr_b200' / 'lib'}:" + os.environ.get("LD_LIBRARY_PATH", ""))
+    r = subprocess.run([str(APP), "-a", "-d", "0", "-s", "250000", "-n", "6", "-b", "1024", "-t", "1", "-o", str(ref_out), *flag], env=env,
+                       capture_output=True, text=True, timeout=60)
+    assert "Bye" in r.stderr, r.stderr[-2000:]
+    env.pop("FAKEUSB_AUTOPLUG")
+    g = subprocess.run([str(DEMO), "-s", "250000", "-n", "6", "-b", "1024", "-t", "200", "-o", str(gpu_out), *flag], env=env, capture_output=True,
+                       text=True, timeout=120)
+    assert g.returncode == 0, g.stderr + g.stdout
+    assert ref_out.stat().st_size == 200 * 8192 and ref_out.read_bytes() == gpu_out.read_bytes()
