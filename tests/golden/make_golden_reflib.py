@@ -112,6 +112,14 @@ def main() -> None:
             app[f"{name}_fnv1a64"] = f"{co.fnv1a64(data):016x}"
     out["perseustest_app"] = app
 
+    # examples/simple.c (the reference's `make check` program, its own copy of the int32 callback, simple.c:33-61): fixed 96 kS/s,
+    # 6 x 1024-byte transfers, 10 s, writes ./perseusdata.bin
+    with tempfile.TemporaryDirectory() as td:
+        env = dict(os.environ, FAKEUSB_AUTOPLUG="1", FAKEUSB_LIMIT="200", FAKEUSB_SEED="77")
+        subprocess.run([str(ROOT / "oracle" / "_ref" / "simple_ref")], cwd=td, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=60)
+        data = Path(f"{td}/perseusdata.bin").read_bytes()
+        out["simple_app"] = {"limit": 200, "seed": 77, "int32_nbytes": len(data), "int32_fnv1a64": f"{co.fnv1a64(data):016x}"}
+
     (HERE / "reflib.json").write_text(json.dumps(out, indent=1) + "\n")
     print(f"wrote {HERE / 'reflib.json'}: {len(out['rate_choice'])} rate probes, {len(codes)} start codes")
 

@@ -274,3 +274,14 @@ def test_reference_application_output_file(coracle, tmp_path, float_output, mode
     assert data == O.Ref().unpack(wire, mode, chunk=6144).tobytes()
     g = GOLD["perseustest_app"]
     assert (len(data), f"{coracle.fnv1a64(data):016x}") == (g[f"{name}_nbytes"], g[f"{name}_fnv1a64"])
+
+
+def test_simple_c_application_wrote_the_same_int32_file(coracle):
+    """examples/simple.c carries its own copy of the int32 callback (simple.c:33-61) and is the reference's `make check` program.
+    It runs 10 s, so it is executed only by tests/golden/make_golden_reflib.py; its frozen output must be what perseustest wrote
+    for the same stream, and what the restated oracle computes."""
+    g, p = GOLD["simple_app"], GOLD["perseustest_app"]
+    assert (g["limit"], g["seed"]) == (p["limit"], p["seed"])
+    assert (g["int32_nbytes"], g["int32_fnv1a64"]) == (p["int32_nbytes"], p["int32_fnv1a64"])
+    want = coracle.unpack(coracle.synth_random(g["limit"] * 6144, g["seed"]), O.MODE_I32)
+    assert f"{coracle.fnv1a64(want):016x}" == g["int32_fnv1a64"]
