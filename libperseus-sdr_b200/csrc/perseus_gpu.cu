@@ -273,7 +273,8 @@ int queue_checksums(perseus_gpu *h, const void *o_i32, const void *o_f32, uint64
 }
 
 // ---- streaming path -------------------------------------------------------------------------
-// All functions below this line that take a handle expect h->mu to be held by the caller.
+// All functions below this line that take a handle expect the caller to OWN the handle (struct perseus_gpu: the mutex, or the
+// callback thread inside its fast path).
 
 int ensure_streaming(perseus_gpu *h)
 {
