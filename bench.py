@@ -476,7 +476,7 @@ def ours(args):
     tuning["geometry_fused"] = h.get_geometry(pg.OUT_INT32 | pg.OUT_FLOAT)
     tuning["geometry_single"] = h.get_geometry(pg.OUT_FLOAT)
     tuning["autotuned"] = bool(args.autotune)
-    tuning["auto_rule"] = "0 = per format: tile 12288 B, ring of 3 stages when int32+float are fused, 4 stages for one format, 1 CTA/SM"
+    tuning["auto_rule"] = "0 = per format: int32+float fused -> tile 12288 B x 3 stages; one format -> tile 6144 B x 8 stages; 1 CTA/SM"
 
     nbuf = args.buffers
     first, count = sharding.rank_shard(pg, nbuf * world, world, rank)   # this rank's transfers of the N x cfg2 recording

@@ -32,8 +32,10 @@ inline Geometry resolve_geometry(const Tuning &t, unsigned fmt)
 	const bool fused = (fmt & FMT_I32) && (fmt & (FMT_F32 | FMT_POW2));
 	const Geometry &m = t.tuned[fused ? 1 : 0];             // measured on this device, if the caller asked for it
 	Geometry g;                                             // explicit settings win, then measured, then the defaults
-	g.tile_bytes = t.tile_bytes ? t.tile_bytes : m.tile_bytes ? m.tile_bytes : 12288;   // two 6144-byte transfers per stage
-	g.stages = t.stages ? t.stages : m.stages ? m.stages : (fused ? 3 : 4);
+	// fused: 3 stages of two 6144-byte transfers (36 KiB in flight); one format: 8 stages of one transfer (48 KiB) -- the same
+	// bytes in flight as 4 x 12288 but 0.5 % faster in the round-2 sweep (profiles/r2_sweep_fine.jsonl)
+	g.tile_bytes = t.tile_bytes ? t.tile_bytes : m.tile_bytes ? m.tile_bytes : (fused ? 12288 : 6144);
+	g.stages = t.stages ? t.stages : m.stages ? m.stages : (fused ? 3 : (g.tile_bytes == 6144 ? 8 : 4));
 	g.ctas_per_sm = t.ctas_per_sm ? t.ctas_per_sm : m.ctas_per_sm ? m.ctas_per_sm : 1;
 	return g;
 }
