@@ -858,6 +858,67 @@ def test_cfg1_95k_paced_float_file_equals_reference(pg, coracle, tmp_path):
     assert path.read_bytes() == O.Ref().unpack(wire, O.MODE_F32, chunk=6144).tobytes()
 
 
+def test_streaming_while_the_application_hammers_the_same_handle(pg, coracle, tmp_path):
+    """One handle, three parties at once: the receiver's thread calling perseus_gpu_input_callback as fast as it can (lock-free
+    fast path), the application thread polling statistics / perseus_gpu_poll / perseus_gpu_sync (each of which takes the handle
+    away from the callback through the membarrier handshake), and the latency watchdog.  The file must still be the unpack of
+    every transfer, in order, and no transfer may be lost or counted twice."""
+    import threading
+    n = 30_000                                           # 184 MB of wire, a few hundred hand-offs
+    path = tmp_path / "perseusdata"
+    with pg.PerseusGpu(device=0, stream_flags=pg.OUT_INT32, slab_bytes=1 << 20, nslabs=4, max_latency_us=1000) as h:
+        h.stream_to_file(str(path))
+        v = pg.VirtualReceiver(sample_rate=2_000_000, seed=31337)
+        cbp, cbx = h.callback
+        done, res = threading.Event(), {}
+
+        def feed():
+            res["st"] = v.run(6144, cbp, cbx, n)
+            done.set()
+
+        t = threading.Thread(target=feed)
+        t.start()
+        polls = 0
+        while not done.is_set():
+            s = h.stats()
+            assert s["callbacks"] <= n and s["dropped_callbacks"] == 0
+            h.poll()
+            if polls % 5 == 0:
+                h.sync()
+            polls += 1
+        t.join()
+        h.flush()
+        h.stream_to_file(None)
+        v.close()
+        s = h.stats()
+        assert res["st"]["delivered"] == n and s["callbacks"] == n and s["samples"] == n * 1024 and polls > 20, (s, polls)
+    got = np.fromfile(path, np.uint32)
+    want = coracle.unpack(coracle.synth_random(n * 6144, seed=31337), O.MODE_I32, nthreads=4).view(np.uint32).reshape(-1)
+    assert got.size == want.size and np.array_equal(got, want)
+
+
+def test_sink_on_the_watchdog_thread_may_use_its_handle(pg, coracle):
+    """The sink runs on whichever thread submits the slab -- here the watchdog -- and may call the handle's plumbing from there."""
+    import time
+    wire = coracle.synth_random(6144 * 2, seed=77).reshape(2, 6144)
+    with pg.PerseusGpu(device=0, stream_flags=pg.OUT_FLOAT, max_latency_us=5000) as h:
+        got, seen = [], []
+
+        def sink(blk, extra):
+            h.sync()
+            got.append(h.to_host(blk.contents.dev_f32, blk.contents.nsamples * 8, np.uint32))
+            seen.append(h.stats()["callbacks"])
+
+        h.set_sink(sink)
+        for k in range(2):
+            h.input_callback(wire[k].ctypes.data, 6144)
+        t0 = time.perf_counter()
+        while not got and time.perf_counter() - t0 < 2.0:
+            time.sleep(0.001)
+        assert len(got) == 1 and seen == [2] and h.stats()["watchdog_submits"] == 1
+        assert np.array_equal(got[0], coracle.unpack(wire.reshape(-1), O.MODE_F32).view(np.uint32).reshape(-1))
+
+
 def test_two_handles_on_two_threads(pg, coracle):
     """Handles are independent: distinct handles may be driven from distinct threads at the same time."""
     import threading
