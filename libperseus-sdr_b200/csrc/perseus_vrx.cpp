@@ -14,7 +14,7 @@
 // Checked against the reference's own code (perseus-in.c and perseus-sdr.c compiled unmodified over a
 // fake libusb, oracle/_ref) by tests/test_refqueue_cpu.py and tests/test_reflib_cpu.py.
 //
-// No CUDA in this file: it builds with a plain C++ compiler (tools/sanitize.sh runs it under TSAN/ASAN).
+// No CUDA in this file: it builds with a plain C++ compiler (tests/sanitize/sanitize.sh runs it under TSAN/ASAN).
 #include "../../include/perseus-gpu.h"
 #include "host_common.h"
 

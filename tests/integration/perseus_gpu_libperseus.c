@@ -13,7 +13,7 @@
  * lines a real deployment would not have are the two that plug in the synthetic receiver (fakeusb_plug): with real
  * hardware and the real libusb the rest is unchanged.
  *
- *   gcc -std=gnu99 -I include -I /root/reference -I oracle -I oracle/fakeusb examples/perseus_gpu_libperseus.c \
+ *   gcc -std=gnu99 -I include -I /root/reference -I oracle -I oracle/fakeusb tests/integration/perseus_gpu_libperseus.c \
  *       -L oracle/_ref -lperseus_sdr_ref -L libperseus-sdr_b200/lib -lperseus_gpu
  */
 #include <stdio.h>

@@ -1,6 +1,6 @@
 // TEST INFRASTRUCTURE ONLY (tests/sanitize/): a stand-in for <cuda_runtime.h> so that the HOST code of
 // libperseus-sdr_b200/csrc/perseus_gpu.cu -- handle lock, slab ring, latency watchdog, staging pipeline bookkeeping --
-// can be compiled with a plain C++ compiler and run under ThreadSanitizer / AddressSanitizer (tools/sanitize.sh).
+// can be compiled with a plain C++ compiler and run under ThreadSanitizer / AddressSanitizer (tests/sanitize/sanitize.sh).
 // "Device" memory is host memory, every stream operation completes before it returns, events are always complete.
 // Nothing here is part of the product, and the product never compiles against it.
 #pragma once

@@ -1,6 +1,6 @@
 // TEST INFRASTRUCTURE ONLY: drives the host layer of libperseus_gpu (perseus_gpu.cu's host code, perseus_vrx.cpp,
 // perseus_host.cpp) from several threads at once so ThreadSanitizer / AddressSanitizer can see it.  Built by
-// tools/sanitize.sh against tests/sanitize/fake_cuda (no GPU involved); results are also checked against the CPU oracle.
+// tests/sanitize/sanitize.sh against tests/sanitize/fake_cuda (no GPU involved); results are also checked against the CPU oracle.
 #include "../../include/perseus-gpu.h"
 
 #include <atomic>

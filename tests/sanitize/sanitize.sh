@@ -3,9 +3,9 @@
 # perseus_host.cpp -- with a plain C++ compiler against the CUDA stand-in in tests/sanitize/fake_cuda, once with
 # ThreadSanitizer and once with AddressSanitizer + UBSan, and runs tests/sanitize/host_stress.cpp under each.
 # No GPU involved; the device kernels have their own compute-sanitizer runs (profiles/sanitizer_*).
-#   tools/sanitize.sh [outdir]      logs -> <outdir>/r2_sanitizer_host_{tsan,asan}.txt   (default: profiles/)
+#   tests/sanitize/sanitize.sh [outdir]      logs -> <outdir>/r2_sanitizer_host_{tsan,asan}.txt   (default: profiles/)
 set -u
-ROOT="$(cd "$(dirname "$0")/.." && pwd)"
+ROOT="$(cd "$(dirname "$0")/../.." && pwd)"
 OUT="${1:-$ROOT/profiles}"
 BUILD="$(mktemp -d)"
 CSRC="$ROOT/libperseus-sdr_b200/csrc"

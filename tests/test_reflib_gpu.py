@@ -113,7 +113,7 @@ DEMO = ROOT / "oracle" / "_ref" / "perseus_gpu_libperseus_demo"
 @pytest.mark.skipif(not DEMO.exists(), reason="oracle/_ref/perseus_gpu_libperseus_demo not built")
 @pytest.mark.parametrize("flag,mode", [((), O.MODE_I32), (("-p",), O.MODE_F32)])
 def test_c_program_linking_libperseus_sdr_and_libperseus_gpu(coracle, tmp_path, flag, mode):
-    """examples/perseus_gpu_libperseus.c is INTEGRATION.md §1 as a program: plain C against the reference's perseus-sdr.h and
+    """tests/integration/perseus_gpu_libperseus.c is INTEGRATION.md §1 as a program: plain C against the reference's perseus-sdr.h and
     perseus-gpu.h, linked with the reference library (over the fake libusb) and libperseus_gpu.so."""
     out = tmp_path / "perseusdata"
     env = dict(os.environ, LD_LIBRARY_PATH=f"{ROOT / 'oracle' / '_ref'}:{ROOT / 'libperseus-sdr_b200' / 'lib'}:" + os.environ.get("LD_LIBRARY_PATH", ""))
@@ -132,7 +132,7 @@ APP = ROOT / "oracle" / "_ref" / "perseustest_ref"
 @pytest.mark.parametrize("flag", [(), ("-p",)])
 def test_gpu_program_writes_the_same_file_as_the_reference_application(tmp_path, flag):
     """Two programs, the same synthetic receiver, the same command line letters: the reference's own perseustest (unmodified,
-    CPU callbacks) and examples/perseus_gpu_libperseus.c (the same flow with perseus_gpu_input_callback).  Their output
+    CPU callbacks) and tests/integration/perseus_gpu_libperseus.c (the same flow with perseus_gpu_input_callback).  Their output
     files must be byte-identical."""
     ref_out, gpu_out = tmp_path / "ref.bin", tmp_path / "gpu.bin"
     env = dict(os.environ, FAKEUSB_AUTOPLUG="1", FAKEUSB_LIMIT="200", FAKEUSB_SEED=str(O.SYNTH_SEED),

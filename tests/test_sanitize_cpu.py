@@ -1,4 +1,4 @@
-"""Host-layer thread hygiene: tools/sanitize.sh builds perseus_gpu.cu's host code, perseus_vrx.cpp and
+"""Host-layer thread hygiene: tests/sanitize/sanitize.sh builds perseus_gpu.cu's host code, perseus_vrx.cpp and
 perseus_host.cpp with g++ against a CUDA stand-in (tests/sanitize/fake_cuda) under ThreadSanitizer and under
 AddressSanitizer+UBSan and runs the multi-threaded stress driver tests/sanitize/host_stress.cpp under both."""
 import shutil
@@ -15,7 +15,7 @@ def test_host_layer_is_clean_under_tsan_and_asan(tmp_path):
                            text=True, capture_output=True)
     if probe.returncode != 0:
         pytest.skip("sanitizer runtimes not installed")
-    r = subprocess.run([str(ROOT / "tools" / "sanitize.sh"), str(tmp_path)], capture_output=True, text=True, timeout=600)
+    r = subprocess.run([str(ROOT / "tests" / "sanitize" / "sanitize.sh"), str(tmp_path)], capture_output=True, text=True, timeout=600)
     logs = "".join((tmp_path / f"r2_sanitizer_host_{s}.txt").read_text() for s in ("tsan", "asan"))
     assert r.returncode == 0, logs[-4000:]
     assert logs.count("host_stress: all scenarios passed") == 4      # tsan, asan x membarrier, fence fallback
