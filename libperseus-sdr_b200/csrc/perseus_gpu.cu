@@ -218,12 +218,7 @@ Mem classify(const void *p)
 	switch (a.type) {
 	case cudaMemoryTypeDevice: return Mem::Device;
 	case cudaMemoryTypeManaged: return Mem::Device;
-	case cudaMemoryTypeHost: {
-		// EXPERIMENT (tools only): let the kernel read / write pinned host memory directly over PCIe instead of staging it
-		static const char *zc = getenv("PERSEUS_GPU_EXPERIMENT_ZEROCOPY");
-		if (zc && *zc == '1') return Mem::Device;
-		return Mem::PinnedHost;
-	}
+	case cudaMemoryTypeHost: return Mem::PinnedHost;
 	default: return Mem::PageableHost;
 	}
 }
