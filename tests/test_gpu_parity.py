@@ -418,7 +418,7 @@ def test_host_pointer_pipeline_rotates_its_slots(pg, coracle, slots, chunk):
 
 def test_autotune_measures_and_keeps_a_geometry(pg, coracle):
     with pg.PerseusGpu(device=0) as h:
-        assert h.get_geometry(pg.OUT_FLOAT) == {"tile_bytes": 12288, "stages": 4, "ctas_per_sm": 1}              # B200 defaults
+        assert h.get_geometry(pg.OUT_FLOAT) == {"tile_bytes": 6144, "stages": 8, "ctas_per_sm": 1}               # B200 defaults
         assert h.get_geometry(pg.OUT_INT32 | pg.OUT_FLOAT) == {"tile_bytes": 12288, "stages": 3, "ctas_per_sm": 1}
         single, fused = h.autotune()
         assert single > 4000 and fused > 4000, (single, fused)            # GB/s of the winners on a B200-class device
