@@ -119,7 +119,12 @@ typedef struct perseus_gpu_config {
 	uint32_t options;         /* PERSEUS_GPU_OPT_*                                              */
 	uint32_t stage_slots;     /* staging slots of the host-pointer pipeline, 2..8   (0 = 3): chunk c is copied in while
 	                             chunk c-1 is unpacked and chunk c-2 is copied out, each on its own stream */
-	uint32_t reserved[2];
+	uint32_t direct_bytes;    /* streaming path: a slab of at most this many bytes is unpacked by ONE kernel launch that
+	                             reads the pinned slab over the link itself (no copy into HBM first) and, when only the host
+	                             wants the samples (file / host sink, no device sink), stores them straight into pinned host
+	                             memory: the short way for the small, latency-bounded slabs of a real receiver.  Larger
+	                             slabs are copied by the copy engine.  (0 = 256 KiB; 0xFFFFFFFF = never)             */
+	uint32_t reserved[1];
 } perseus_gpu_config;
 
 /* perseus_gpu_config.options */
@@ -202,7 +207,8 @@ int perseus_gpu_poll(perseus_gpu *h);
  * that submitted the slab (the callback thread, the caller of flush/poll, or the watchdog),
  * under the handle's lock, right after the unpack kernel was ENQUEUED on `stream`
  * (a cudaStream_t): work the sink enqueues on that stream runs after the unpack and before
- * the block's memory is reused. */
+ * the block's memory is reused.  (With a device sink set, slabs always land in device memory;
+ * see perseus_gpu_config.direct_bytes.) */
 typedef struct perseus_gpu_block {
 	uint64_t first_sample;   /* index of the block's first complex sample since open */
 	uint64_t nsamples;
@@ -213,9 +219,24 @@ typedef struct perseus_gpu_block {
 typedef void (*perseus_gpu_sink)(const perseus_gpu_block *blk, void *extra);
 int perseus_gpu_set_sink(perseus_gpu *h, perseus_gpu_sink sink, void *extra);
 
+/* A block of unpacked samples in (pinned) HOST memory: what the reference's callbacks have in hand when they fwrite
+ * (perseustest.c:457,499), for applications whose consumer stays on the CPU.  The host sink is called once per slab, in
+ * stream order, as soon as the slab's samples have arrived in host memory -- no flush needed -- on a thread of the CUDA
+ * runtime, NOT under the handle's lock: it must not call perseus_gpu_* on this handle nor any CUDA function, and the
+ * pointers are valid only during the call.  Setting or clearing the sink flushes the stream first.  */
+typedef struct perseus_gpu_host_block {
+	uint64_t    first_sample;  /* index of the block's first complex sample since open */
+	uint64_t    nsamples;
+	const void *i32;           /* nsamples x {int32 I, int32 Q}, or NULL when the handle does not stream int32 */
+	const void *f32;           /* nsamples x {float I, float Q}, or NULL when the handle does not stream floats */
+} perseus_gpu_host_block;
+typedef void (*perseus_gpu_host_sink)(const perseus_gpu_host_block *blk, void *extra);
+int perseus_gpu_set_host_sink(perseus_gpu *h, perseus_gpu_host_sink sink, void *extra);
+
 /* Also writes the stream to `path` exactly as `perseustest -o path [-p]` would: a raw,
  * headerless sequence of {int32 I,int32 Q} (or {float I,float Q} when the handle streams
- * floats), 8 bytes per sample (perseustest.c:337-343,457,499).  path == NULL stops. */
+ * floats), 8 bytes per sample (perseustest.c:337-343,457,499).  path == NULL stops.  Blocks are written as they complete (same
+ * delivery as the host sink); perseus_gpu_flush / close make the file complete. */
 int perseus_gpu_stream_to_file(perseus_gpu *h, const char *path);
 
 /* Submits the partly filled slab and waits until every submitted slab has been unpacked
@@ -235,7 +256,7 @@ typedef struct perseus_gpu_stats {
 	uint64_t dropped_callbacks; /* callbacks ignored because an error was latched      */
 	uint64_t dropped_bytes;     /* wire bytes of those callbacks                       */
 	uint64_t watchdog_submits;  /* partial slabs submitted by the watchdog / poll      */
-	uint64_t reserved[1];
+	uint64_t host_blocks;       /* blocks written to the stream file / handed to the host sink */
 } perseus_gpu_stats;
 int perseus_gpu_get_stats(perseus_gpu *h, perseus_gpu_stats *out);
 

@@ -49,7 +49,8 @@ class Tuning(C.Structure):
 class Config(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("stream_flags", C.c_uint32), ("nslabs", C.c_uint32),
                 ("slab_bytes", C.c_uint64), ("nstreams", C.c_uint32), ("max_latency_us", C.c_uint32), ("chunk_bytes", C.c_uint64),
-                ("tuning", Tuning), ("options", C.c_uint32), ("stage_slots", C.c_uint32), ("reserved", C.c_uint32 * 2)]
+                ("tuning", Tuning), ("options", C.c_uint32), ("stage_slots", C.c_uint32), ("direct_bytes", C.c_uint32),
+                ("reserved", C.c_uint32 * 1)]
 
 
 class Seg(C.Structure):
@@ -64,13 +65,21 @@ class Block(C.Structure):
 SINK = C.CFUNCTYPE(None, C.POINTER(Block), C.c_void_p)
 
 
+class HostBlock(C.Structure):
+    _fields_ = [("first_sample", C.c_uint64), ("nsamples", C.c_uint64), ("i32", C.c_void_p), ("f32", C.c_void_p)]
+
+
+HOST_SINK = C.CFUNCTYPE(None, C.POINTER(HostBlock), C.c_void_p)
+DIRECT_NEVER = 0xFFFFFFFF
+
+
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("kernel_launches", "samples", "bytes_in", "h2d_bytes", "d2h_bytes", "callbacks",
-                                          "slabs", "stalls", "dropped_callbacks", "dropped_bytes", "watchdog_submits")] + \
-               [("reserved", C.c_uint64 * 1)]
+                                          "slabs", "stalls", "dropped_callbacks", "dropped_bytes", "watchdog_submits",
+                                          "host_blocks")]
 
     def asdict(self):
-        return {n: int(getattr(self, n)) for n, _ in self._fields_[:-1]}
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
 class VrxConfig(C.Structure):
@@ -121,6 +130,7 @@ def lib() -> C.CDLL:
         "perseus_gpu_plan_destroy": (ci, [vp, vp]),
         "perseus_gpu_input_callback": (ci, [vp, ci, vp]),
         "perseus_gpu_set_sink": (ci, [vp, SINK, vp]),
+        "perseus_gpu_set_host_sink": (ci, [vp, HOST_SINK, vp]),
         "perseus_gpu_stream_to_file": (ci, [vp, C.c_char_p]),
         "perseus_gpu_flush": (ci, [vp]),
         "perseus_gpu_poll": (ci, [vp]),
@@ -219,13 +229,14 @@ class PerseusGpu:
     """perseus_gpu handle.  Pointers are plain integers (device or host addresses)."""
 
     def __init__(self, device: int = 0, stream_flags: int = 0, nslabs: int = 0, slab_bytes: int = 0, nstreams: int = 0,
-                 chunk_bytes: int = 0, max_latency_us: int = 0, options: int = 0, stage_slots: int = 0, **tuning):
+                 chunk_bytes: int = 0, max_latency_us: int = 0, options: int = 0, stage_slots: int = 0, direct_bytes: int = 0,
+                 **tuning):
         L = lib()
         cfg = Config()
         cfg.struct_size = C.sizeof(Config)
         cfg.device, cfg.stream_flags, cfg.nslabs, cfg.slab_bytes = device, stream_flags, nslabs, slab_bytes
         cfg.nstreams, cfg.chunk_bytes, cfg.max_latency_us = nstreams, chunk_bytes, max_latency_us
-        cfg.options, cfg.stage_slots = options, stage_slots
+        cfg.options, cfg.stage_slots, cfg.direct_bytes = options, stage_slots, direct_bytes
         for k, v in tuning.items():
             setattr(cfg.tuning, k, v)
         self.h = C.c_void_p()
@@ -286,6 +297,11 @@ class PerseusGpu:
     def set_sink(self, fn) -> None:
         self._sink = SINK(fn) if fn else C.cast(None, SINK)
         check(self.L.perseus_gpu_set_sink(self.h, self._sink, None))
+
+    def set_host_sink(self, fn) -> None:
+        """fn(HostBlock pointer, extra) is called on a CUDA runtime thread, once per slab, in stream order."""
+        self._host_sink = HOST_SINK(fn) if fn else C.cast(None, HOST_SINK)
+        check(self.L.perseus_gpu_set_host_sink(self.h, self._host_sink, None))
 
     def stream_to_file(self, path: str | None) -> None:
         check(self.L.perseus_gpu_stream_to_file(self.h, path.encode() if path else None))

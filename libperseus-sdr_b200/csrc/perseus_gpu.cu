@@ -41,16 +41,21 @@ constexpr int kMaxStreams = 8;
 constexpr int kMaxSlabs = 64;
 constexpr int kEventSlots = 32;
 constexpr int kMaxStageSlots = 8;
+constexpr size_t kDefaultDirectBytes = 256u << 10;   // perseus_gpu_config.direct_bytes = 0
 
 struct Slab {
 	uint8_t *host = nullptr;       // pinned wire bytes being filled by the callback
 	uint8_t *dev_in = nullptr;     // device copy
 	uint8_t *dev_i32 = nullptr;    // device outputs of this slab
 	uint8_t *dev_f32 = nullptr;
-	uint8_t *host_out = nullptr;   // pinned copy of the output, only with a file sink
+	uint8_t *host_out[2] = {nullptr, nullptr};   // pinned copies of the outputs (int32, float): only with a file / host sink
+	cudaEvent_t unpacked = nullptr;   // recorded behind the slab's kernel (and whatever the device sink queued): host delivery waits for it
 	cudaEvent_t done = nullptr;    // recorded after the slab's last operation
+	perseus_gpu *owner = nullptr;  // for deliver_slab, which only gets the slab
 	uint64_t first_sample = 0;
-	size_t out_bytes = 0;          // bytes to write to the file sink once `done`
+	uint64_t nsamples = 0;
+	size_t file_bytes = 0;         // bytes deliver_slab writes to the file sink
+	int file_fmt = 0;              // which host_out[] the file holds (perseustest writes ONE format per run)
 	bool busy = false;
 };
 
@@ -81,6 +86,7 @@ struct perseus_gpu {
 	int nstreams = 0;
 	cudaStream_t streams[kMaxStreams]{};        // [0] = the launch stream of everything device-resident; slabs rotate over all
 	cudaStream_t s_in = nullptr, s_out = nullptr;   // copy-in / copy-out streams of the host-pointer pipeline
+	cudaStream_t s_dlv = nullptr;               // host delivery of the streaming path: every slab's copy-out + deliver_slab, in stream order
 	cudaEvent_t events[kEventSlots]{};          // the caller's timing slots (perseus_gpu_event_*)
 	cudaEvent_t tev[4]{};                       // private timing events (autotune, probes)
 	unsigned long long *d_scratch = nullptr;   // 2 x u64: checksum / verify results
@@ -108,7 +114,14 @@ struct perseus_gpu {
 	uint64_t samples_submitted = 0;
 	perseus_gpu_sink sink = nullptr;
 	void *sink_extra = nullptr;
+	// host delivery (file sink, host sink): written by the owner only while nothing is in flight (after a flush), read by
+	// deliver_slab on the CUDA runtime's callback thread
+	perseus_gpu_host_sink host_sink = nullptr;
+	void *host_sink_extra = nullptr;
 	FILE *fout = nullptr;
+	std::atomic<int> io_error{0};                // deliver_slab could not write the file: surfaced at the next retire / flush
+	std::atomic<uint64_t> host_blocks{0};        // blocks deliver_slab has handed over
+	size_t direct_bytes = 0;                     // slabs up to this size are unpacked straight from the pinned slab (no H2D copy)
 	// latency watchdog (started with the first callback unless PERSEUS_GPU_OPT_NO_WATCHDOG)
 	std::thread watchdog;
 	std::mutex wd_mu;                            // only for wd_cv / wd_stop
@@ -279,6 +292,7 @@ int ensure_streaming(perseus_gpu *h)
 	const bool want_f32 = h->stream_fmt & (PERSEUS_GPU_OUT_FLOAT | PERSEUS_GPU_OUT_FLOAT_POW2);
 	for (int k = 0; k < h->nslabs; ++k) {
 		Slab &s = h->slabs[k];
+		s.owner = h;
 		// each guarded, so a call that failed half way (out of memory) can be retried without leaking
 		if (!s.host) CU(h, cudaHostAlloc(&s.host, h->slab_bytes, cudaHostAllocDefault));
 		if (!s.dev_in) CU(h, cudaMalloc(&s.dev_in, h->slab_bytes));
@@ -287,27 +301,42 @@ int ensure_streaming(perseus_gpu *h)
 		// BlockingSync: back-pressure waits happen on the caller of the callback -- in the reference a SCHED_FIFO
 		// thread (perseus-sdr.c:749-753) -- and must sleep, not spin
 		if (!s.done) CU(h, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming | cudaEventBlockingSync));
+		if (!s.unpacked) CU(h, cudaEventCreateWithFlags(&s.unpacked, cudaEventDisableTiming));
 	}
 	h->streaming_ready = true;
 	return 0;
 }
 
-// Retires the `count` oldest slabs in ring order: waits for each, writes its output to the file sink if there is one.
-int drain_file(perseus_gpu *h, int count)
+// Host delivery of one slab, queued on s_dlv behind the slab's outputs reaching pinned host memory: runs on the CUDA runtime's
+// callback thread, slabs strictly in stream order.  Does what the reference's callbacks do with their samples -- fwrite them
+// (perseustest.c:457,499) -- and/or hands them to the application's host sink.  No CUDA call is allowed here.
+void CUDART_CB deliver_slab(void *p)
+{
+	Slab *s = static_cast<Slab *>(p);
+	perseus_gpu *h = s->owner;
+	if (h->fout && s->file_bytes && !h->io_error.load(std::memory_order_relaxed)) {
+		if (fwrite(s->host_out[s->file_fmt], 1, s->file_bytes, h->fout) != s->file_bytes) h->io_error.store(1, std::memory_order_relaxed);
+	}
+	if (h->host_sink) {
+		const perseus_gpu_host_block b{s->first_sample, s->nsamples, (h->stream_fmt & PERSEUS_GPU_OUT_INT32) ? s->host_out[0] : nullptr,
+		                               (h->stream_fmt & (PERSEUS_GPU_OUT_FLOAT | PERSEUS_GPU_OUT_FLOAT_POW2)) ? s->host_out[1] : nullptr};
+		h->host_sink(&b, h->host_sink_extra);
+	}
+	h->host_blocks.fetch_add(1, std::memory_order_relaxed);
+}
+
+// Retires the `count` oldest slabs in ring order: waits until each one's last operation (kernel, or host delivery) is done.
+int retire_slabs(perseus_gpu *h, int count)
 {
 	for (int n = 0; n < count; ++n) {
 		Slab &s = h->slabs[h->next_to_write];
 		if (s.busy) {
 			CU(h, cudaEventSynchronize(s.done));
-			if (h->fout && s.out_bytes) {
-				if (fwrite(s.host_out, 1, s.out_bytes, h->fout) != s.out_bytes)
-					return fail(PERSEUS_GPU_IOERROR, "short write to stream file");
-			}
-			s.out_bytes = 0;
 			s.busy = false;
 		}
 		h->next_to_write = (h->next_to_write + 1) % h->nslabs;
 	}
+	if (h->io_error.exchange(0, std::memory_order_relaxed)) return fail(PERSEUS_GPU_IOERROR, "short write to stream file");
 	return 0;
 }
 
@@ -318,28 +347,56 @@ int submit_slab(perseus_gpu *h)
 	if (nbytes == 0) return 0;
 	CU(h, cudaSetDevice(h->device));   // the only place the callback path needs the device: once per slab, not per transfer
 	cudaStream_t st = h->streams[h->cur % h->nstreams];
-	s.first_sample = h->samples_submitted;
-#if defined(__SSE2__)
-	_mm_sfence();   // the slab was filled with non-temporal stores: make them visible before the DMA reads it
-#endif
-	CU(h, cudaMemcpyAsync(s.dev_in, s.host, nbytes, cudaMemcpyHostToDevice, st));
-	h->stats.h2d_bytes += nbytes;
-	int rc = do_launch(h, s.dev_in, nbytes, s.dev_i32, s.dev_f32, h->stream_fmt, st);
-	if (rc) return rc;
 	const uint64_t ns = nbytes / 6;
+	const bool produced[2] = {(h->stream_fmt & PERSEUS_GPU_OUT_INT32) != 0,
+	                          (h->stream_fmt & (PERSEUS_GPU_OUT_FLOAT | PERSEUS_GPU_OUT_FLOAT_POW2)) != 0};
+	const bool host_delivery = h->fout || h->host_sink;
+	// A small slab (a real receiver delivers 0.6-12 MB/s: slabs are cut by the latency bound, not by their size) is unpacked
+	// by ONE launch that reads the pinned slab over the link itself -- the producer's bulk copies take host addresses as they
+	// take device ones -- instead of a copy and a launch that waits for it; and when only the host wants the samples the
+	// same launch stores them straight into the pinned output.  Large slabs go through HBM: the copy engine moves them
+	// without occupying the SMs.
+	const bool direct = nbytes <= h->direct_bytes;
+	const bool direct_out = direct && host_delivery && !h->sink;
+	s.first_sample = h->samples_submitted;
+	s.nsamples = ns;
+	if (host_delivery)
+		for (int k = 0; k < 2; ++k)
+			if (produced[k] && !s.host_out[k]) CU(h, cudaHostAlloc(&s.host_out[k], h->slab_bytes / 6 * 8, cudaHostAllocDefault));
+#if defined(__SSE2__)
+	_mm_sfence();   // the slab was filled with non-temporal stores: make them visible before the device reads it
+#endif
+	const uint8_t *kin = s.host;
+	if (!direct) {
+		CU(h, cudaMemcpyAsync(s.dev_in, s.host, nbytes, cudaMemcpyHostToDevice, st));
+		kin = s.dev_in;
+	}
+	h->stats.h2d_bytes += nbytes;
+	uint8_t *kout[2] = {produced[0] ? (direct_out ? s.host_out[0] : s.dev_i32) : nullptr,
+	                    produced[1] ? (direct_out ? s.host_out[1] : s.dev_f32) : nullptr};
+	int rc = do_launch(h, kin, nbytes, kout[0], kout[1], h->stream_fmt, st);
+	if (rc) return rc;
 	if (h->sink) {
 		perseus_gpu_block b{s.first_sample, ns, s.dev_i32, s.dev_f32, (void *)st};
 		h->sink(&b, h->sink_extra);
 	}
-	if (h->fout) {
-		// perseustest writes ONE format per run (-p selects float, perseustest.c:348-352)
-		const uint8_t *src = (h->stream_fmt & PERSEUS_GPU_OUT_INT32) ? s.dev_i32 : s.dev_f32;
-		if (!s.host_out) CU(h, cudaHostAlloc(&s.host_out, h->slab_bytes / 6 * 8, cudaHostAllocDefault));
-		CU(h, cudaMemcpyAsync(s.host_out, src, ns * 8, cudaMemcpyDeviceToHost, st));
-		h->stats.d2h_bytes += ns * 8;
-		s.out_bytes = ns * 8;
+	if (host_delivery) {
+		// every slab's copy-out and hand-over go through the ONE delivery stream, so blocks reach the host in stream order
+		// whichever of the handle's streams unpacked them
+		CU(h, cudaEventRecord(s.unpacked, st));
+		CU(h, cudaStreamWaitEvent(h->s_dlv, s.unpacked, 0));
+		for (int k = 0; k < 2; ++k) {
+			if (!produced[k]) continue;
+			if (!direct_out) CU(h, cudaMemcpyAsync(s.host_out[k], k ? s.dev_f32 : s.dev_i32, ns * 8, cudaMemcpyDeviceToHost, h->s_dlv));
+			h->stats.d2h_bytes += ns * 8;
+		}
+		s.file_fmt = produced[0] ? 0 : 1;   // a stream file holds one format (perseus_gpu_stream_to_file checks)
+		s.file_bytes = h->fout ? ns * 8 : 0;
+		CU(h, cudaLaunchHostFunc(h->s_dlv, deliver_slab, &s));
+		CU(h, cudaEventRecord(s.done, h->s_dlv));
+	} else {
+		CU(h, cudaEventRecord(s.done, st));
 	}
-	CU(h, cudaEventRecord(s.done, st));
 	s.busy = true;
 	h->samples_submitted += ns;
 	h->stats.slabs++;
@@ -353,7 +410,7 @@ int submit_slab(perseus_gpu *h)
 		cudaGetLastError();
 		// everything older than `next` (inclusive) completes in order
 		int count = (h->cur - h->next_to_write + h->nslabs) % h->nslabs + 1;
-		rc = drain_file(h, count);
+		rc = retire_slabs(h, count);
 		if (rc) return rc;
 	}
 	return 0;
@@ -548,11 +605,12 @@ int stream_push(perseus_gpu *h, const uint8_t *buf, size_t nbytes)
 
 int sync_locked(perseus_gpu *h)
 {
-	cudaStream_t all[kMaxStreams + 2];
+	cudaStream_t all[kMaxStreams + 3];
 	int n = 0;
 	for (int s = 0; s < h->nstreams; ++s) all[n++] = h->streams[s];
 	all[n++] = h->s_in;
 	all[n++] = h->s_out;
+	all[n++] = h->s_dlv;
 	for (int s = 0; s < n; ++s) {
 		if (!all[s]) continue;
 		cudaError_t e = cudaStreamSynchronize(all[s]);
@@ -576,7 +634,8 @@ int flush_locked(perseus_gpu *h)
 		// costs ~0.2 ms of wake-up latency.  flush is called by the application and wants the result now: spin on the
 		// streams first, after which every slab event is already complete and draining never sleeps.
 		for (int s = 0; s < h->nstreams; ++s) cudaStreamSynchronize(h->streams[s]);
-		rc = drain_file(h, h->nslabs);   // oldest first, so the file keeps stream order
+		cudaStreamSynchronize(h->s_dlv);   // every block has been written / handed to the host sink
+		rc = retire_slabs(h, h->nslabs);
 		if (rc) latch(h, rc);
 		h->next_to_write = h->cur;       // nothing in flight: the next slab submitted is the oldest
 		if (h->fout) fflush(h->fout);
@@ -773,6 +832,7 @@ int perseus_gpu_open(perseus_gpu **out, const perseus_gpu_config *ucfg)
 	h->slab_bytes = (size_t)slab;
 	h->max_latency_ns = cfg.max_latency_us == 0xFFFFFFFFu ? 0 : (uint64_t)(cfg.max_latency_us ? cfg.max_latency_us : 50000u) * 1000ull;
 	h->chunk_bytes = (size_t)chunk;
+	h->direct_bytes = cfg.direct_bytes == 0xFFFFFFFFu ? 0 : cfg.direct_bytes ? (size_t)cfg.direct_bytes : kDefaultDirectBytes;
 	h->asym = membarrier_available();
 	auto bail = [&](int code) {   // free what exists, keep the message of the original failure
 		const std::string keep = pg::last_error();
@@ -788,6 +848,7 @@ int perseus_gpu_open(perseus_gpu **out, const perseus_gpu_config *ucfg)
 	}
 	e = cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking);
+	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_dlv, cudaStreamNonBlocking);
 	if (e != cudaSuccess) return bail(fail(PERSEUS_GPU_CUDAERR, "cudaStreamCreate: %s", cudaGetErrorString(e)));
 	for (int k = 0; k < kEventSlots && e == cudaSuccess; ++k) e = cudaEventCreate(&h->events[k]);
 	for (int k = 0; k < 4 && e == cudaSuccess; ++k) e = cudaEventCreate(&h->tev[k]);
@@ -813,11 +874,13 @@ int perseus_gpu_close(perseus_gpu *h)
 			for (int k = 0; k < kMaxSlabs; ++k) {
 				Slab &s = h->slabs[k];
 				if (s.host) cudaFreeHost(s.host);
-				if (s.host_out) cudaFreeHost(s.host_out);
+				for (uint8_t *p : s.host_out)
+					if (p) cudaFreeHost(p);
 				if (s.dev_in) cudaFree(s.dev_in);
 				if (s.dev_i32) cudaFree(s.dev_i32);
 				if (s.dev_f32) cudaFree(s.dev_f32);
 				if (s.done) cudaEventDestroy(s.done);
+				if (s.unpacked) cudaEventDestroy(s.unpacked);
 			}
 			for (int s = 0; s < kMaxStageSlots; ++s) {
 				if (h->stage_in[s]) cudaFree(h->stage_in[s]);
@@ -838,6 +901,7 @@ int perseus_gpu_close(perseus_gpu *h)
 				if (h->streams[s]) cudaStreamDestroy(h->streams[s]);
 			if (h->s_in) cudaStreamDestroy(h->s_in);
 			if (h->s_out) cudaStreamDestroy(h->s_out);
+			if (h->s_dlv) cudaStreamDestroy(h->s_dlv);
 			cudaGetLastError();
 		}
 		if (h->fout) {
@@ -1055,6 +1119,17 @@ int perseus_gpu_set_sink(perseus_gpu *h, perseus_gpu_sink sink, void *extra)
 	return 0;
 }
 
+int perseus_gpu_set_host_sink(perseus_gpu *h, perseus_gpu_host_sink sink, void *extra)
+{
+	Entry en(h);
+	if (en.rc) return en.rc;
+	int rc = flush_locked(h);   // blocks in flight still belong to the previous sink; deliver_slab reads these fields unlocked
+	if (rc) return rc;
+	h->host_sink = sink;
+	h->host_sink_extra = extra;
+	return 0;
+}
+
 int perseus_gpu_stream_to_file(perseus_gpu *h, const char *path)
 {
 	Entry en(h);
@@ -1088,6 +1163,7 @@ int perseus_gpu_get_stats(perseus_gpu *h, perseus_gpu_stats *out)
 	if (en.rc) return en.rc;
 	if (!out) return fail(PERSEUS_GPU_ERRPARAM, "null stats pointer");
 	*out = h->stats;
+	out->host_blocks = h->host_blocks.load(std::memory_order_relaxed);
 	return 0;
 }
 

@@ -4,11 +4,14 @@
 #include "kernels.h"
 
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <map>
 #include <mutex>
+#include <thread>
 
 extern "C" size_t perseus_oracle_unpack(int mode, const uint8_t *in, size_t nbytes, void *out);
 extern "C" uint64_t perseus_oracle_checksum32(const uint32_t *words, size_t nwords, uint64_t first_index);
@@ -17,7 +20,51 @@ extern "C" void perseus_oracle_synth_random(uint8_t *dst, size_t nbytes, uint64_
 namespace {
 std::mutex g_mu;
 std::map<const void *, std::pair<size_t, cudaMemoryType>> g_allocs;   // base -> (size, kind)
-struct Ev { double t = 0; };
+struct Ev { double t = 0; uint64_t ticket = 0; };
+
+// cudaLaunchHostFunc: like the real runtime, host functions run on a thread of their own, in order, concurrently with the
+// caller; everything else "on the device" completes at once.  Events remember how many host functions were queued before
+// them, so waiting for an event / a stream waits for those functions, as it does on a real stream.
+struct HostFuncs {
+	std::mutex mu;
+	std::condition_variable cv;
+	std::deque<std::pair<cudaHostFn_t, void *>> q;
+	uint64_t queued = 0, done = 0;
+	bool stop = false;
+	std::thread th;
+	void run()
+	{
+		std::unique_lock<std::mutex> lk(mu);
+		for (;;) {
+			cv.wait(lk, [&] { return stop || !q.empty(); });
+			if (q.empty()) return;
+			auto f = q.front();
+			q.pop_front();
+			lk.unlock();
+			f.first(f.second);
+			lk.lock();
+			++done;
+			cv.notify_all();
+		}
+	}
+	void push(cudaHostFn_t fn, void *p)
+	{
+		std::lock_guard<std::mutex> lk(mu);
+		if (!th.joinable()) th = std::thread([this] { run(); });
+		q.emplace_back(fn, p);
+		++queued;
+		cv.notify_all();
+	}
+	uint64_t ticket() { std::lock_guard<std::mutex> lk(mu); return queued; }
+	bool reached(uint64_t t) { std::lock_guard<std::mutex> lk(mu); return done >= t; }
+	void wait(uint64_t t) { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return done >= t; }); }
+	~HostFuncs()
+	{
+		{ std::lock_guard<std::mutex> lk(mu); stop = true; }
+		cv.notify_all();
+		if (th.joinable()) th.join();
+	}
+} g_hostfuncs;
 double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 cudaError_t alloc(void **p, size_t n, cudaMemoryType kind)
 {
@@ -53,14 +100,21 @@ cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int)
 	return cudaSuccess;
 }
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = reinterpret_cast<cudaStream_t>(new int(0)); return cudaSuccess; }
-cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t) { g_hostfuncs.wait(g_hostfuncs.ticket()); return cudaSuccess; }
 cudaError_t cudaStreamDestroy(cudaStream_t s) { delete reinterpret_cast<int *>(s); return cudaSuccess; }
 cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+cudaError_t cudaLaunchHostFunc(cudaStream_t, cudaHostFn_t fn, void *p) { g_hostfuncs.push(fn, p); return cudaSuccess; }
 cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = reinterpret_cast<cudaEvent_t>(new Ev()); return cudaSuccess; }
 cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { return cudaEventCreate(e); }
-cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { reinterpret_cast<Ev *>(e)->t = now_ms(); return cudaSuccess; }
-cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
-cudaError_t cudaEventQuery(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t)
+{
+	Ev *ev = reinterpret_cast<Ev *>(e);
+	ev->t = now_ms();
+	ev->ticket = g_hostfuncs.ticket();
+	return cudaSuccess;
+}
+cudaError_t cudaEventSynchronize(cudaEvent_t e) { g_hostfuncs.wait(reinterpret_cast<Ev *>(e)->ticket); return cudaSuccess; }
+cudaError_t cudaEventQuery(cudaEvent_t e) { return g_hostfuncs.reached(reinterpret_cast<Ev *>(e)->ticket) ? cudaSuccess : cudaErrorNotReady; }
 cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) { *ms = float(reinterpret_cast<Ev *>(b)->t - reinterpret_cast<Ev *>(a)->t) + 1e-3f; return cudaSuccess; }
 cudaError_t cudaEventDestroy(cudaEvent_t e) { delete reinterpret_cast<Ev *>(e); return cudaSuccess; }
 cudaError_t cudaMalloc(void **p, size_t n) { return alloc(p, n, cudaMemoryTypeDevice); }

@@ -1,7 +1,8 @@
 // TEST INFRASTRUCTURE ONLY (tests/sanitize/): a stand-in for <cuda_runtime.h> so that the HOST code of
 // libperseus-sdr_b200/csrc/perseus_gpu.cu -- handle lock, slab ring, latency watchdog, staging pipeline bookkeeping --
 // can be compiled with a plain C++ compiler and run under ThreadSanitizer / AddressSanitizer (tests/sanitize/sanitize.sh).
-// "Device" memory is host memory, every stream operation completes before it returns, events are always complete.
+// "Device" memory is host memory; copies and kernels complete before the call returns; host functions (cudaLaunchHostFunc) run
+// on a thread of their own, in order, and events / stream synchronisation wait for the ones queued before them.
 // Nothing here is part of the product, and the product never compiles against it.
 #pragma once
 #include <cstddef>
@@ -29,6 +30,9 @@ cudaError_t cudaStreamCreateWithFlags(cudaStream_t *, unsigned);
 cudaError_t cudaStreamSynchronize(cudaStream_t);
 cudaError_t cudaStreamDestroy(cudaStream_t);
 cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned);
+#define CUDART_CB
+typedef void (*cudaHostFn_t)(void *);
+cudaError_t cudaLaunchHostFunc(cudaStream_t, cudaHostFn_t, void *);
 cudaError_t cudaEventCreate(cudaEvent_t *);
 cudaError_t cudaEventCreateWithFlags(cudaEvent_t *, unsigned);
 cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t);

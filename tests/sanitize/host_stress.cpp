@@ -183,12 +183,80 @@ static void scenario_edges()
 	CHECK(perseus_gpu_close(nullptr) == PERSEUS_GPU_NULLHANDLE);
 }
 
+// E: the host sink and the file sink are served on the runtime's callback thread while the receiver's thread keeps submitting
+//    slabs and an application thread reads statistics, polls and flushes
+static void host_sink(const perseus_gpu_host_block *b, void *extra)
+{
+	Collected *c = static_cast<Collected *>(extra);
+	std::lock_guard<std::mutex> lk(c->mu);
+	CHECK(c->bytes.size() == b->first_sample * 8 && b->f32 && !b->i32);
+	const uint8_t *p = static_cast<const uint8_t *>(b->f32);
+	c->bytes.insert(c->bytes.end(), p, p + b->nsamples * 8);
+}
+
+static void scenario_host_delivery()
+{
+	for (uint32_t direct : {0u, 0xFFFFFFFFu}) {
+		perseus_gpu_config cfg;
+		memset(&cfg, 0, sizeof cfg);
+		cfg.struct_size = sizeof cfg;
+		cfg.stream_flags = PERSEUS_GPU_OUT_FLOAT;
+		cfg.slab_bytes = 6144 * 3;
+		cfg.nslabs = 2;
+		cfg.max_latency_us = 500;
+		cfg.direct_bytes = direct;
+		perseus_gpu *h = nullptr;
+		CHECK(perseus_gpu_open(&h, &cfg) == 0);
+		Collected col;
+		CHECK(perseus_gpu_set_host_sink(h, host_sink, &col) == 0);
+		CHECK(perseus_gpu_stream_to_file(h, "/tmp/perseus_sanitize_e.bin") == 0);
+		perseus_vrx_config vc;
+		memset(&vc, 0, sizeof vc);
+		vc.struct_size = sizeof vc;
+		vc.sample_rate = 2000000;
+		vc.realtime = 1;
+		vc.seed = 9;
+		perseus_vrx *v = nullptr;
+		CHECK(perseus_vrx_open(&v, &vc) == 0);
+		CHECK(perseus_vrx_start_async_input(v, 6144, perseus_gpu_input_callback, h) == 0);
+		std::atomic<bool> stop{false};
+		std::thread app([&] {
+			while (!stop.load()) {
+				perseus_gpu_stats s;
+				CHECK(perseus_gpu_get_stats(h, &s) == 0 && s.host_blocks <= s.slabs);
+				CHECK(perseus_gpu_poll(h) >= 0);
+				if (s.slabs % 5 == 0) CHECK(perseus_gpu_flush(h) == 0);
+			}
+		});
+		sleep_ms(200);
+		CHECK(perseus_vrx_stop_async_input(v) == 0);
+		stop.store(true);
+		app.join();
+		perseus_vrx_stats vs;
+		perseus_gpu_stats gs;
+		CHECK(perseus_vrx_get_stats(v, &vs) == 0);
+		CHECK(perseus_gpu_set_host_sink(h, nullptr, nullptr) == 0);      // flushes: everything submitted has been delivered
+		CHECK(perseus_gpu_get_stats(h, &gs) == 0 && gs.host_blocks == gs.slabs && gs.samples == vs.delivered * 1024);
+		CHECK(perseus_gpu_close(h) == 0);
+		std::vector<uint8_t> wire(vs.delivered * 6144), want(vs.delivered * 8192), file(want.size());
+		CHECK(perseus_synth_fill(wire.data(), wire.size(), PERSEUS_SYNTH_RANDOM, 9, 0) == 0);
+		perseus_oracle_unpack(1, wire.data(), wire.size(), want.data());
+		CHECK(col.bytes.size() == want.size() && memcmp(col.bytes.data(), want.data(), want.size()) == 0);
+		FILE *f = fopen("/tmp/perseus_sanitize_e.bin", "rb");
+		CHECK(f != nullptr && fread(file.data(), 1, file.size() + 1, f) == want.size() && memcmp(file.data(), want.data(), want.size()) == 0);
+		fclose(f);
+		remove("/tmp/perseus_sanitize_e.bin");
+		CHECK(perseus_vrx_close(v) == 0);
+	}
+}
+
 int main()
 {
 	scenario_vrx_stats();
 	scenario_trampoline();
 	scenario_two_handles();
 	scenario_edges();
+	scenario_host_delivery();
 	printf("host_stress: all scenarios passed\n");
 	return 0;
 }

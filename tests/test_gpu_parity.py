@@ -642,15 +642,19 @@ def collect_stream(pg, h, run):
     return blocks
 
 
+SLAB_ROUTES = {"direct": 0, "staged": 0xFFFFFFFF}      # perseus_gpu_config.direct_bytes: small slabs read over the link by the kernel / copied first
+
+
+@pytest.mark.parametrize("route", list(SLAB_ROUTES))
 @pytest.mark.parametrize("buffersize,ep", [(6144, 512), (12288, 512), (510, 510), (510 * 32, 510)])
-def test_callback_trampoline_driven_by_virtual_receiver(pg, coracle, buffersize, ep):
+def test_callback_trampoline_driven_by_virtual_receiver(pg, coracle, buffersize, ep, route):
     """perseus_vrx_* plays perseus_start_async_input + the libusb queue (8-slot pageable ring, in-order
     callbacks, buffer reused right after return); the registered callback IS perseus_gpu_input_callback,
     passed as a C function pointer exactly as a libperseus-sdr user would."""
     ntransfers = 203
     slab = 48 * 1000                                   # not a multiple of the transfer: slabs split transfers
     with pg.PerseusGpu(device=0, stream_flags=pg.OUT_INT32 | pg.OUT_FLOAT, slab_bytes=slab, nslabs=3, nstreams=2,
-                       max_latency_us=0xFFFFFFFF) as h:    # slabs are counted below: size-bounded only
+                       max_latency_us=0xFFFFFFFF, direct_bytes=SLAB_ROUTES[route]) as h:    # slabs are counted below: size-bounded only
         outs_i, outs_f = [], []
 
         def sink(blk, extra):
@@ -700,23 +704,105 @@ def test_callback_with_dropped_transfers_leaves_a_gap_like_the_reference(pg, cor
         assert np.array_equal(np.concatenate(got), coracle.unpack(kept, O.MODE_I32).view(np.uint32).reshape(-1))
 
 
+@pytest.mark.parametrize("route", list(SLAB_ROUTES))
 @pytest.mark.parametrize("fmt,mode,refmode", [("OUT_INT32", O.MODE_I32, O.MODE_I32), ("OUT_FLOAT", O.MODE_F32, O.MODE_F32)])
-def test_stream_file_is_byte_identical_to_perseustest_output(pg, coracle, tmp_path, fmt, mode, refmode):
+def test_stream_file_is_byte_identical_to_perseustest_output(pg, coracle, tmp_path, fmt, mode, refmode, route):
     """`perseustest -o file [-p]` writes a raw headerless stream of 8-byte samples (perseustest.c:337-343,457,499).
     The GPU path's file sink must produce the same bytes; compared with what the reference's own callbacks
     fwrite (oracle/_ref) when that library travelled here, else with the restated oracle."""
     path = tmp_path / "perseusdata"
     ntransfers = 97
-    with pg.PerseusGpu(device=0, stream_flags=getattr(pg, fmt), slab_bytes=6144 * 10, nslabs=3) as h:
+    with pg.PerseusGpu(device=0, stream_flags=getattr(pg, fmt), slab_bytes=6144 * 10, nslabs=3, direct_bytes=SLAB_ROUTES[route]) as h:
         h.stream_to_file(str(path))
         v = pg.VirtualReceiver(sample_rate=250000, seed=11)
         v.run(6144, *h.callback, ntransfers)
         h.flush()
         h.stream_to_file(None)
         v.close()
-        assert h.stats()["d2h_bytes"] == ntransfers * 8192
+        st = h.stats()
+        assert st["d2h_bytes"] == ntransfers * 8192 and st["host_blocks"] == st["slabs"] == 10
     wire = coracle.synth_random(ntransfers * 6144, seed=11)
     want = O.Ref().unpack(wire, refmode, chunk=6144) if O.Ref.available() else coracle.unpack(wire, mode)
+    assert path.read_bytes() == want.tobytes()
+
+
+def collect_host_blocks(got):
+    """A host sink that copies each block out of the pinned memory it is only lent for the call."""
+    def sink(blk, extra):
+        b = blk.contents
+        cp = lambda p: np.ctypeslib.as_array((C.c_uint32 * (2 * b.nsamples)).from_address(p)).copy() if p else None
+        got.append((b.first_sample, b.nsamples, cp(b.i32), cp(b.f32)))
+    return sink
+
+
+@pytest.mark.parametrize("route", list(SLAB_ROUTES))
+@pytest.mark.parametrize("fmtname", ["OUT_INT32", "OUT_FLOAT", "both"])
+def test_host_sink_gets_every_block_in_stream_order(pg, coracle, route, fmtname):
+    """The consumer that stays on the CPU: unpacked samples handed over in pinned host memory, once per slab, in stream
+    order although the slabs rotate over two CUDA streams -- what the reference's callbacks hold when they fwrite
+    (perseustest.c:457,499).  Both slab routes: read over the link by the kernel and stored straight into host memory,
+    or staged through HBM by the copy engines."""
+    fmt = pg.OUT_INT32 | pg.OUT_FLOAT if fmtname == "both" else getattr(pg, fmtname)
+    ntransfers, slab = 157, 48 * 700
+    got = []
+    with pg.PerseusGpu(device=0, stream_flags=fmt, slab_bytes=slab, nslabs=3, nstreams=2, max_latency_us=0xFFFFFFFF,
+                       direct_bytes=SLAB_ROUTES[route]) as h:
+        h.set_host_sink(collect_host_blocks(got))
+        v = pg.VirtualReceiver(sample_rate=1_000_000, seed=91)
+        v.run(6144, *h.callback, ntransfers)
+        h.flush()
+        v.close()
+        st = h.stats()
+        h.set_host_sink(None)
+    wire = coracle.synth_random(ntransfers * 6144, seed=91)
+    ns = wire.size // 6
+    nfmt = 2 if fmtname == "both" else 1
+    assert st["host_blocks"] == st["slabs"] == len(got) == -(-wire.size // slab) and st["d2h_bytes"] == ns * 8 * nfmt
+    assert [g[0] for g in got] == list(np.cumsum([0] + [g[1] for g in got[:-1]])) and sum(g[1] for g in got) == ns
+    for idx, bit, mode in ((2, pg.OUT_INT32, O.MODE_I32), (3, pg.OUT_FLOAT, O.MODE_F32)):
+        if fmt & bit:
+            assert np.array_equal(np.concatenate([g[idx] for g in got]), coracle.unpack(wire, mode).view(np.uint32).reshape(-1))
+        else:
+            assert all(g[idx] is None for g in got)
+
+
+def test_host_sink_is_served_without_a_flush(pg, coracle):
+    """Delivery is driven by the device, not by the next call into the library: one full slab, nobody calls anything."""
+    import time
+    wire = coracle.synth_random(6144 * 2, seed=5).reshape(2, 6144)
+    got = []
+    with pg.PerseusGpu(device=0, stream_flags=pg.OUT_FLOAT, slab_bytes=6144, nslabs=4) as h:
+        h.set_host_sink(collect_host_blocks(got))
+        h.input_callback(wire[0].ctypes.data, 6144)       # allocates the slabs (tens of ms): not timed
+        h.flush()
+        t0 = time.perf_counter()
+        h.input_callback(wire[1].ctypes.data, 6144)
+        while len(got) < 2 and time.perf_counter() - t0 < 1.0:
+            time.sleep(0.0002)
+        dt = time.perf_counter() - t0
+        assert len(got) == 2 and dt < 0.05, dt
+        assert np.array_equal(got[1][3], coracle.unpack(wire[1], O.MODE_F32).view(np.uint32).reshape(-1))
+
+
+def test_device_sink_host_sink_and_file_together(pg, coracle, tmp_path):
+    """All three consumers of one stream see the same samples (with a device sink the slabs always land in HBM)."""
+    path = tmp_path / "perseusdata"
+    got, dev = [], []
+    with pg.PerseusGpu(device=0, stream_flags=pg.OUT_FLOAT, slab_bytes=6144 * 3, nslabs=3) as h:
+        def sink(blk, extra):
+            h.sync()
+            dev.append(h.to_host(blk.contents.dev_f32, blk.contents.nsamples * 8, np.uint32))
+        h.set_sink(sink)
+        h.set_host_sink(collect_host_blocks(got))
+        h.stream_to_file(str(path))
+        v = pg.VirtualReceiver(sample_rate=500_000, seed=8)
+        v.run(6144, *h.callback, 20)
+        h.flush()
+        h.stream_to_file(None)
+        v.close()
+    want = coracle.unpack(coracle.synth_random(20 * 6144, seed=8), O.MODE_F32)
+    assert np.array_equal(np.concatenate(dev), want.view(np.uint32).reshape(-1))
+    assert np.array_equal(np.concatenate([g[3] for g in got]), want.view(np.uint32).reshape(-1))
     assert path.read_bytes() == want.tobytes()
 
 

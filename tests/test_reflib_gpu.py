@@ -101,10 +101,14 @@ def test_cfg1_through_the_reference_library_paced_at_95k(pg, coracle, reflib, tm
             assert 38 <= n <= 56, n                              # 0.5 s at 92.8 transfers/s
         time.sleep(0.08)                                         # nothing arrives any more: the watchdog (50 ms) submits the tail
         st = h.stats()
-        assert st["callbacks"] == n and st["samples"] == n * 1024 and st["watchdog_submits"] >= 1, st
+        # perseus_input_queue_cancel clears callback_fn on the application thread (perseus-in.c:131) while the poll thread may be
+        # completing one more transfer: the fake device has counted it, the reference's handler no longer delivers it
+        # (perseus-in.c:204-207).  The reference itself decides which of the two happens.
+        ncb = st["callbacks"]
+        assert n - 1 <= ncb <= n and st["samples"] == ncb * 1024 and st["watchdog_submits"] >= 1, (n, st)
         h.flush()
         h.stream_to_file(None)
-    assert path.read_bytes() == reference_file(coracle.synth_random(n * 6144, seed=5), O.MODE_F32, 6144)
+    assert path.read_bytes() == reference_file(coracle.synth_random(ncb * 6144, seed=5), O.MODE_F32, 6144)
 
 
 DEMO = ROOT / "oracle" / "_ref" / "perseus_gpu_libperseus_demo"
