@@ -124,7 +124,10 @@ typedef struct perseus_gpu_config {
 	                             wants the samples (file / host sink, no device sink), stores them straight into pinned host
 	                             memory: the short way for the small, latency-bounded slabs of a real receiver.  Larger
 	                             slabs are copied by the copy engine.  (0 = 256 KiB; 0xFFFFFFFF = never)             */
-	uint32_t reserved[1];
+	uint32_t copy_threads;    /* perseus_gpu_unpack with PAGEABLE host buffers (malloc, mmap): threads, the caller included, that move
+	                             each chunk between the application's memory and pinned bounce buffers while the copy engines
+	                             work on the neighbouring chunks  (0 = min(8, cores/2); 1 = the caller alone; 0xFFFFFFFF = hand
+	                             pageable pointers to the CUDA runtime, which stages them on the calling thread)           */
 } perseus_gpu_config;
 
 /* perseus_gpu_config.options */
@@ -143,7 +146,9 @@ int perseus_gpu_open(perseus_gpu **h, const perseus_gpu_config *cfg);
 int perseus_gpu_close(perseus_gpu *h);
 
 /* Bulk unpack: the whole of user_data_callback_c_u / _c_f for one buffer of any size.
- *   buf      nbytes of wire data; device, pinned-host or pageable-host memory (detected).
+ *   buf      nbytes of wire data; device, pinned-host or pageable-host memory (detected).  Pageable memory is
+ *            staged through pinned bounce buffers by cfg->copy_threads threads; a call with pageable OUTPUTS has
+ *            completed them when it returns, PERSEUS_GPU_ASYNC or not.
  *   out_i32  2*(nbytes/6) int32, or NULL;  out_f32  2*(nbytes/6) float, or NULL;
  *            device or host memory (detected).  Host pointers are staged through the
  *            device in cfg->chunk_bytes pieces with copies and kernels overlapped.

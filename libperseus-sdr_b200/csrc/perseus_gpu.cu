@@ -6,6 +6,7 @@
 // (buffer valid only during the call, return value ignored, strictly serial, in ring order);
 // the error convention mirrors perseus-sdr.h:317-366 + perseuserr.c:36-42.
 #include "../../include/perseus-gpu.h"
+#include "copy_pool.h"
 #include "kernels.h"
 
 #include <atomic>
@@ -100,6 +101,12 @@ struct perseus_gpu {
 	uint8_t *stage_in[kMaxStageSlots]{};
 	uint8_t *stage_out[kMaxStageSlots][2]{};
 	cudaEvent_t ev_in[kMaxStageSlots]{}, ev_k[kMaxStageSlots]{}, ev_out[kMaxStageSlots]{};
+	// PAGEABLE host buffers are staged through pinned bounce buffers by the caller and the pool's helper threads
+	// (copy_threads participants; 0 = leave pageable memory to the CUDA runtime, which stages it on the calling thread alone)
+	int copy_threads = 0;
+	pg::CopyPool *pool = nullptr;
+	uint8_t *bounce_in[kMaxStageSlots]{};
+	uint8_t *bounce_out[kMaxStageSlots][2]{};
 	// streaming (callback) path
 	unsigned stream_fmt = 0;
 	size_t slab_bytes = 0;
@@ -240,6 +247,21 @@ int bind(perseus_gpu *h)
 {
 	if (!h) return fail(PERSEUS_GPU_NULLHANDLE, "null handle");
 	CU(h, cudaSetDevice(h->device));
+	return 0;
+}
+
+int ensure_bounce(perseus_gpu *h, bool in, bool i32, bool f32)
+{
+	if (!(in || i32 || f32)) return 0;
+	if (!h->pool) {
+		h->pool = new (std::nothrow) pg::CopyPool(h->copy_threads - 1);
+		if (!h->pool) return fail(PERSEUS_GPU_NOMEM, "out of memory");
+	}
+	for (int s = 0; s < h->nslots; ++s) {
+		if (in && !h->bounce_in[s]) CU(h, cudaHostAlloc(&h->bounce_in[s], h->chunk_bytes, cudaHostAllocDefault));
+		if (i32 && !h->bounce_out[s][0]) CU(h, cudaHostAlloc(&h->bounce_out[s][0], h->chunk_bytes / 6 * 8, cudaHostAllocDefault));
+		if (f32 && !h->bounce_out[s][1]) CU(h, cudaHostAlloc(&h->bounce_out[s][1], h->chunk_bytes / 6 * 8, cudaHostAllocDefault));
+	}
 	return 0;
 }
 
@@ -416,29 +438,10 @@ int submit_slab(perseus_gpu *h)
 	return 0;
 }
 
-// Transfer -> pinned slab.  The slab is written once by this thread and then only read by the DMA engine, so the
-// copy uses non-temporal stores: no read-for-ownership of the destination lines, about twice the bandwidth of
+// Transfer -> pinned slab.  The slab is written once by this thread and then only read by the device, so the copy uses
+// non-temporal stores (pg::copy_nontemporal): no read-for-ownership of the destination lines, about twice the bandwidth of
 // memcpy for 6144-byte pieces on one core (the callback is single-threaded by contract, perseus-sdr.c:736-770).
-inline void copy_to_slab(uint8_t *dst, const uint8_t *src, size_t n)
-{
-#if defined(__SSE2__)
-	size_t head = (16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15;
-	if (head > n) head = n;
-	memcpy(dst, src, head);
-	dst += head; src += head; n -= head;
-	for (; n >= 64; n -= 64, src += 64, dst += 64) {
-		const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src));
-		const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + 16));
-		const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + 32));
-		const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + 48));
-		_mm_stream_si128(reinterpret_cast<__m128i *>(dst), a);
-		_mm_stream_si128(reinterpret_cast<__m128i *>(dst + 16), b);
-		_mm_stream_si128(reinterpret_cast<__m128i *>(dst + 32), c);
-		_mm_stream_si128(reinterpret_cast<__m128i *>(dst + 48), d);
-	}
-#endif
-	memcpy(dst, src, n);
-}
+inline void copy_to_slab(uint8_t *dst, const uint8_t *src, size_t n) { pg::copy_nontemporal(dst, src, n); }
 
 inline uint64_t monotonic_ns()
 {
@@ -832,6 +835,11 @@ int perseus_gpu_open(perseus_gpu **out, const perseus_gpu_config *ucfg)
 	h->slab_bytes = (size_t)slab;
 	h->max_latency_ns = cfg.max_latency_us == 0xFFFFFFFFu ? 0 : (uint64_t)(cfg.max_latency_us ? cfg.max_latency_us : 50000u) * 1000ull;
 	h->chunk_bytes = (size_t)chunk;
+	{
+		const unsigned hw = std::thread::hardware_concurrency();
+		const unsigned autot = hw >= 4 ? (hw / 2 > 8 ? 8 : hw / 2) : 1;
+		h->copy_threads = cfg.copy_threads == 0xFFFFFFFFu ? 0 : (int)(cfg.copy_threads ? (cfg.copy_threads > 64 ? 64 : cfg.copy_threads) : autot);
+	}
 	h->direct_bytes = cfg.direct_bytes == 0xFFFFFFFFu ? 0 : cfg.direct_bytes ? (size_t)cfg.direct_bytes : kDefaultDirectBytes;
 	h->asym = membarrier_available();
 	auto bail = [&](int code) {   // free what exists, keep the message of the original failure
@@ -889,6 +897,9 @@ int perseus_gpu_close(perseus_gpu *h)
 				if (h->ev_in[s]) cudaEventDestroy(h->ev_in[s]);
 				if (h->ev_k[s]) cudaEventDestroy(h->ev_k[s]);
 				if (h->ev_out[s]) cudaEventDestroy(h->ev_out[s]);
+				if (h->bounce_in[s]) cudaFreeHost(h->bounce_in[s]);
+				if (h->bounce_out[s][0]) cudaFreeHost(h->bounce_out[s][0]);
+				if (h->bounce_out[s][1]) cudaFreeHost(h->bounce_out[s][1]);
 			}
 			if (h->d_scratch) cudaFree(h->d_scratch);
 			if (h->d_sums) cudaFree(h->d_sums);
@@ -908,6 +919,7 @@ int perseus_gpu_close(perseus_gpu *h)
 			if (fclose(h->fout) != 0 && !rc) rc = fail(PERSEUS_GPU_IOERROR, "closing stream file failed");
 		}
 	}
+	delete h->pool;   // joins the helper threads
 	delete h;
 	return rc;
 }
@@ -958,19 +970,42 @@ int64_t perseus_gpu_unpack(perseus_gpu *h, const void *buf, size_t nbytes, void 
 		// Three-stage pipeline over `nslots` staging slots: copy-in on s_in, kernel (+ checksums) on streams[0], copy-out
 		// on s_out, ordered per slot by events.  The copy engines of both directions and the SMs each work on a
 		// different chunk at the same time; neither copy stream ever waits behind a copy of the other direction.
+		// PAGEABLE host buffers get two more stages at the ends: the caller and the handle's helper threads move each chunk
+		// between the application's memory and a pinned bounce buffer of the slot while the engines work on the neighbours.
 		const bool host_out = (out_i32 && !oi_dev) || (out_f32 && !of_dev);
+		const bool in_page = min_ == Mem::PageableHost && h->copy_threads > 0;
+		const bool oi_page = out_i32 && mi == Mem::PageableHost && h->copy_threads > 0;
+		const bool of_page = out_f32 && mf == Mem::PageableHost && h->copy_threads > 0;
 		rc = ensure_staging(h, !in_dev, out_i32 && !oi_dev, out_f32 && !of_dev);
+		if (!rc) rc = ensure_bounce(h, in_page, oi_page, of_page);
 		if (rc) return rc;
 		const uint8_t *src = static_cast<const uint8_t *>(buf);
 		const size_t total = ns * 6;
+		struct { bool any; size_t o, on; } pend[kMaxStageSlots] = {};   // outputs waiting in a slot's bounce buffers
+		// bounce_out[s] -> the application's memory, once the copy-out that fills it has finished
+		auto drain = [&](int s) -> int {
+			if (!pend[s].any) return 0;
+			CU(h, cudaEventSynchronize(h->ev_out[s]));
+			if (oi_page) h->pool->copy(static_cast<uint8_t *>(out_i32) + pend[s].o, h->bounce_out[s][0], pend[s].on, false);
+			if (of_page) h->pool->copy(static_cast<uint8_t *>(out_f32) + pend[s].o, h->bounce_out[s][1], pend[s].on, false);
+			pend[s].any = false;
+			return 0;
+		};
 		for (size_t off = 0; off < total;) {
 			const int s = (int)(h->stage_seq++ % (uint64_t)h->nslots);
 			const size_t n = total - off < h->chunk_bytes ? total - off : h->chunk_bytes;
 			const size_t o = off / 6 * 8, on = n / 6 * 8;
+			if ((rc = drain(s))) return rc;                                   // the chunk that used this slot nslots chunks ago
 			const uint8_t *kin = src + off;
 			if (!in_dev) {
+				const uint8_t *hsrc = src + off;
+				if (in_page) {
+					CU(h, cudaEventSynchronize(h->ev_in[s]));                 // the copy-in that last read this bounce buffer is done
+					h->pool->copy(h->bounce_in[s], hsrc, n, true);
+					hsrc = h->bounce_in[s];
+				}
 				CU(h, cudaStreamWaitEvent(h->s_in, h->ev_k[s], 0));       // the kernel that last read this slot's input is done
-				CU(h, cudaMemcpyAsync(h->stage_in[s], src + off, n, cudaMemcpyHostToDevice, h->s_in));
+				CU(h, cudaMemcpyAsync(h->stage_in[s], hsrc, n, cudaMemcpyHostToDevice, h->s_in));
 				CU(h, cudaEventRecord(h->ev_in[s], h->s_in));
 				CU(h, cudaStreamWaitEvent(sk, h->ev_in[s], 0));
 				h->stats.h2d_bytes += n;
@@ -986,17 +1021,21 @@ int64_t perseus_gpu_unpack(perseus_gpu *h, const void *buf, size_t nbytes, void 
 			if (host_out) {
 				CU(h, cudaStreamWaitEvent(h->s_out, h->ev_k[s], 0));
 				if (out_i32 && !oi_dev) {
-					CU(h, cudaMemcpyAsync(static_cast<uint8_t *>(out_i32) + o, ki, on, cudaMemcpyDeviceToHost, h->s_out));
+					CU(h, cudaMemcpyAsync(oi_page ? h->bounce_out[s][0] : static_cast<uint8_t *>(out_i32) + o, ki, on, cudaMemcpyDeviceToHost, h->s_out));
 					h->stats.d2h_bytes += on;
 				}
 				if (out_f32 && !of_dev) {
-					CU(h, cudaMemcpyAsync(static_cast<uint8_t *>(out_f32) + o, kf, on, cudaMemcpyDeviceToHost, h->s_out));
+					CU(h, cudaMemcpyAsync(of_page ? h->bounce_out[s][1] : static_cast<uint8_t *>(out_f32) + o, kf, on, cudaMemcpyDeviceToHost, h->s_out));
 					h->stats.d2h_bytes += on;
 				}
 				CU(h, cudaEventRecord(h->ev_out[s], h->s_out));
+				if (oi_page || of_page) { pend[s].any = true; pend[s].o = o; pend[s].on = on; }
 			}
 			off += n;
 		}
+		// pageable outputs are complete when the call returns, PERSEUS_GPU_ASYNC or not (like the CUDA runtime's own pageable copies)
+		for (int k = 0; k < h->nslots; ++k)
+			if ((rc = drain((int)((h->stage_seq + (uint64_t)k) % (uint64_t)h->nslots)))) return rc;   // oldest chunk first
 	}
 	if (!(flags & PERSEUS_GPU_ASYNC)) {
 		rc = sync_locked(h);

@@ -250,6 +250,37 @@ static void scenario_host_delivery()
 	}
 }
 
+// F: pageable buffers through the pinned bounce buffers: helper threads of two handles at once, chunks large enough to be split
+static void scenario_pageable_bounce()
+{
+	auto work = [](int k) {
+		perseus_gpu_config cfg;
+		memset(&cfg, 0, sizeof cfg);
+		cfg.struct_size = sizeof cfg;
+		cfg.chunk_bytes = 12288 * 100;                   // 1.2 MB chunks: 4 slices of >= 256 KiB
+		cfg.stage_slots = 2 + k;
+		cfg.copy_threads = 3 + k;
+		perseus_gpu *h = nullptr;
+		CHECK(perseus_gpu_open(&h, &cfg) == 0);
+		std::vector<uint8_t> wire(12288 * 530 + 30 + k), oi(wire.size() / 6 * 8), of(wire.size() / 6 * 8), want(oi.size());
+		CHECK(perseus_synth_fill(wire.data(), wire.size(), PERSEUS_SYNTH_RANDOM, 70 + k, 0) == 0);
+		for (int r = 0; r < 6; ++r) {
+			memset(oi.data(), 0, oi.size());
+			memset(of.data(), 0, of.size());
+			const unsigned flags = (r & 1) ? PERSEUS_GPU_ASYNC : 0;      // pageable outputs are complete at return either way
+			CHECK(perseus_gpu_unpack(h, wire.data(), wire.size(), oi.data(), of.data(), flags) == (int64_t)(wire.size() / 6));
+			perseus_oracle_unpack(0, wire.data(), wire.size(), want.data());
+			CHECK(memcmp(oi.data(), want.data(), want.size()) == 0);
+			perseus_oracle_unpack(1, wire.data(), wire.size(), want.data());
+			CHECK(memcmp(of.data(), want.data(), want.size()) == 0);
+		}
+		CHECK(perseus_gpu_close(h) == 0);
+	};
+	std::thread a(work, 0), b(work, 1);
+	a.join();
+	b.join();
+}
+
 int main()
 {
 	scenario_vrx_stats();
@@ -257,6 +288,7 @@ int main()
 	scenario_two_handles();
 	scenario_edges();
 	scenario_host_delivery();
+	scenario_pageable_bounce();
 	printf("host_stress: all scenarios passed\n");
 	return 0;
 }

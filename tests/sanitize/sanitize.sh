@@ -10,7 +10,7 @@ OUT="${1:-$ROOT/profiles}"
 BUILD="$(mktemp -d)"
 CSRC="$ROOT/libperseus-sdr_b200/csrc"
 CXX=/usr/bin/g++        # the image exports CXX=/opt/gcc/bin/g++, a wrapper without the sanitizer runtimes
-SRCS="$ROOT/tests/sanitize/host_stress.cpp $ROOT/tests/sanitize/fake_cuda.cpp $CSRC/perseus_vrx.cpp $CSRC/perseus_host.cpp"
+SRCS="$ROOT/tests/sanitize/host_stress.cpp $ROOT/tests/sanitize/fake_cuda.cpp $CSRC/perseus_vrx.cpp $CSRC/perseus_host.cpp $CSRC/copy_pool.cpp"
 rc=0
 for san in tsan asan; do
 	case $san in

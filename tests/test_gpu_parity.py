@@ -323,6 +323,37 @@ def test_host_pointers_pageable_and_pinned(pg, coracle):
         h.host_free(pout)
 
 
+@pytest.mark.parametrize("threads", [0, 1, 5, 0xFFFFFFFF])
+def test_pageable_buffers_through_the_bounce_pipeline(pg, coracle, threads):
+    """Ordinary application memory (numpy = malloc) in and out: chunks large enough for the helper threads to split, a ragged
+    tail, more chunks than slots, mixed pointer kinds, misaligned pageable pointers, ASYNC; copy_threads = automatic, the
+    caller alone, five participants, and the CUDA runtime's own staging."""
+    chunk = 12288 * 90                                                # ~1.1 MB: 4 slices of >= 256 KiB
+    raw = coracle.synth_random(chunk * 7 + 6144 * 3 + 17 + 1, seed=29)
+    wire = raw[1:]                                                    # a pageable pointer that is not even 2-byte aligned
+    ns = wire.size // 6
+    want_i = coracle.unpack(wire, O.MODE_I32).view(np.uint32).reshape(-1)
+    want_f = coracle.unpack(wire, O.MODE_F32).view(np.uint32).reshape(-1)
+    with pg.PerseusGpu(device=0, chunk_bytes=chunk, stage_slots=3, copy_threads=threads) as h:
+        oi, of = np.zeros(ns * 2 + 1, np.uint32)[1:], np.zeros(ns * 2, np.uint32)          # out_i32 only 4-byte aligned
+        assert h.unpack(wire.ctypes.data, wire.size, oi.ctypes.data, of.ctypes.data, pg.ASYNC) == ns
+        assert np.array_equal(oi, want_i) and np.array_equal(of, want_f)                    # complete at return although ASYNC
+        with DevBuf(h, ns * 8) as df:                                                       # pageable in, device out
+            assert h.unpack(wire.ctypes.data, wire.size, None, df.p, pg.OUT_FLOAT | pg.CHECKSUM) == ns
+            assert h.get_checksums() == (0, coracle.checksum32(want_f))
+            assert np.array_equal(h.to_host(df.p, ns * 8, np.uint32), want_f)
+            of[:] = 0
+            assert h.unpack(df.p - 0 + 0, 0, None, of.ctypes.data, pg.OUT_FLOAT) == 0       # empty call: nothing touched
+            assert not of.any()
+        with DevBuf(h, wire.size) as din:                                                   # device in, pageable out
+            h.memcpy(din.p, wire.ctypes.data, wire.size)
+            oi[:] = 0
+            assert h.unpack(din.p, wire.size, oi.ctypes.data, None, pg.OUT_INT32) == ns
+            assert np.array_equal(oi, want_i)
+        st = h.stats()
+        assert st["h2d_bytes"] == 2 * ns * 6 and st["d2h_bytes"] == 3 * ns * 8 + 16        # + the two checksums read back
+
+
 def test_overlapped_checksum_flag(pg, coracle):
     """PERSEUS_GPU_CHECKSUM: per-piece checksums queued behind each piece's kernel add up to the oracle's checksum of the
     whole output, for the one-launch device path and the chunked host path, and restart with every call."""
