@@ -531,7 +531,7 @@ def ours(args):
         extra[name] = {"msamples_per_s": round(total_samples / (ms * 1e-3) / 1e6, 1), "ms_per_step": round(ms, 4),
                        "hbm_gbs_per_gpu": round(gbs, 1), "frac_of_peak": round(gbs / peak, 4)}
 
-    e2e = e2e_bal = e2e_rt = None
+    e2e = e2e_bal = e2e_rt = e2e_pageable = None
     if not args.no_e2e:
         # -- end to end: pinned host wire -> H2D -> unpack (outputs stay on device) -> D2H of the step's result
         e2e_steps = max(3, min(args.steps, args.e2e_steps))
@@ -674,6 +674,29 @@ def ours(args):
                 e2e_rt["pcie_d2h_gbs_all_ranks_at_once"] = round(d2h_conc, 2)
                 e2e_rt["frac_of_concurrent_d2h"] = round(d2h_rate / d2h_conc, 4)
             h.host_free(po_i); h.host_free(po_f)
+        # -- the same call fed from PAGEABLE memory (malloc / numpy / mmap: what an application that never heard of CUDA holds):
+        #    the handle's copy pool moves each chunk into pinned bounce buffers while the copy engine works on the previous one
+        if world == 1 and not args.no_pageable:
+            page = np.empty(nbytes, np.uint8)
+            C.memmove(page.ctypes.data, pin, nbytes)
+            sums_p = []
+
+            def page_step():
+                h.unpack(page.ctypes.data, nbytes, d_i32, d_f32, FUSED | pg.ASYNC | pg.CHECKSUM)
+                sums_p.append(h.get_checksums())
+
+            pg_steps = max(3, min(e2e_steps, 5))
+            ms_pg = timed(page_step, pg_steps, 2)
+            assert set(sums_p) == {sums[0]}, "pageable-fed result differs from the pinned-fed one"
+            with pg.PerseusGpu(device=local, copy_threads=pg.COPY_BY_RUNTIME) as h_rt:
+                ms_rt_stage = timed(lambda: h_rt.unpack(page.ctypes.data, nbytes, d_i32, d_f32, FUSED), 2, 1)
+            e2e_pageable = {"value": round(total_samples / (ms_pg * 1e-3) / 1e6, 1), "unit": UNIT, "ms_per_step": round(ms_pg, 3),
+                            "h2d_gbs_per_gpu": round(nbytes / (ms_pg * 1e-3) / 1e9, 2), "frac_of_pinned_e2e": round(ms_e2e / ms_pg, 4),
+                            "staged_by_cuda_runtime_msamples_per_s": round(total_samples / (ms_rt_stage * 1e-3) / 1e6, 1),
+                            "what": "perseus_gpu_unpack(PAGEABLE host wire -> device int32+float, CHECKSUM): default copy pool "
+                                    "(min(8, cores/2) threads incl. the caller) into pinned bounce buffers, overlapped with the copy engine; "
+                                    "beside it the same call with copy_threads = 0xFFFFFFFF (the CUDA runtime stages pageable memory itself)"}
+            del page
         if wc_rt is not None:
             wc_rt.cudaFreeHost(C.c_void_p(pin))
         else:
@@ -758,6 +781,8 @@ def ours(args):
                            h2d_bytes_per_step_note="average per GPU; shards differ in size, see transfers_per_rank")
     if e2e_rt:
         line["e2e_roundtrip"] = e2e_rt
+    if e2e_pageable:
+        line["e2e_pageable"] = e2e_pageable
     if e2e_cb:
         line["e2e_callback"] = e2e_cb
     if workloads:
@@ -801,6 +826,7 @@ def main():
     ap.add_argument("--slots", type=int, default=0, help="staging slots of the host-pointer pipeline (0 = library default, 3)")
     ap.add_argument("--no-workloads", action="store_true", help="skip the cfg3 / cfg4 sub-records")
     ap.add_argument("--no-roundtrip", action="store_true")
+    ap.add_argument("--no-pageable", action="store_true", help="skip the pageable-memory end-to-end leg (N = 1)")
     ap.add_argument("--no-e2e", action="store_true", help="skip every host-fed leg (the line then has e2e: null)")
     ap.add_argument("--no-single", action="store_true", help="skip the one-format kernels")
     ap.add_argument("--no-balanced", action="store_true", help="skip the link-weighted sharding of the end-to-end leg (N > 1)")
@@ -818,7 +844,7 @@ def main():
         ap.add_argument(f"--{k}", type=int, default=0)
     args = ap.parse_args()
     if args.headline_only:
-        args.no_probe = args.no_roundtrip = args.no_cpu = args.no_callback = args.no_workloads = args.no_balanced = True
+        args.no_probe = args.no_roundtrip = args.no_pageable = args.no_cpu = args.no_callback = args.no_workloads = args.no_balanced = True
         args.no_e2e = args.no_single = True
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3                                   # timing rule: at least 3 warm-up steps
