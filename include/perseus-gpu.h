@@ -52,7 +52,8 @@
 extern "C" {
 #endif
 
-#define PERSEUS_GPU_ABI_VERSION 2
+#define PERSEUS_GPU_ABI_VERSION 3   /* 3: host sink, perseus_gpu_config.direct_bytes / copy_threads (were reserved, 0 = default),
+                                       perseus_gpu_stats.host_blocks (was reserved): binary compatible with 2 */
 
 /* Same signature as perseus_input_callback (perseus-sdr.h:81): a pointer of either type converts to the
  * other without a cast.  Declared under its own name so this header never collides with perseus-sdr.h. */

@@ -750,7 +750,9 @@ int64_t plan_run_locked(perseus_gpu *h, perseus_gpu_plan *p, unsigned flags)
 
 extern "C" {
 
-const char *perseus_gpu_version(void) { return "perseus-gpu abi 2, sm_100a, " __DATE__; }
+#define PG_STR2(x) #x
+#define PG_STR(x) PG_STR2(x)
+const char *perseus_gpu_version(void) { return "perseus-gpu abi " PG_STR(PERSEUS_GPU_ABI_VERSION) ", sm_100a, " __DATE__; }
 
 int perseus_gpu_device_count(void)
 {
