@@ -19,6 +19,8 @@ KEYS = [
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
     "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
     "smsp__average_warp_latency_issue_stalled_membar.ratio",
+    # launches that read / write pinned host memory themselves (the streaming path's direct route): 32-byte sectors over the link
+    "syslts__t_sectors_srcunit_tex_aperture_sysmem_op_read_lookup_miss.sum", "syslts__t_sectors_srcunit_tex_aperture_sysmem_op_write_lookup_miss.sum",
 ]
 
 
