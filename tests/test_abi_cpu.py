@@ -60,14 +60,17 @@ def test_header_coexists_with_the_reference_header(order):
 def test_struct_layouts_match_header(pg):
     """ctypes mirrors vs the C compiler's view of the structs."""
     with tempfile.TemporaryDirectory() as td:
-        open(f"{td}/s.c", "w").write('#include <stdio.h>\n#include "perseus-gpu.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+        open(f"{td}/s.c", "w").write('#include <stdio.h>\n#include "perseus-gpu.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                                      "sizeof(perseus_gpu_config),sizeof(perseus_gpu_tuning),sizeof(perseus_gpu_seg),sizeof(perseus_gpu_block),"
                                      "sizeof(perseus_gpu_stats),sizeof(perseus_vrx_config),sizeof(perseus_vrx_stats),"
-                                     "offsetof(perseus_gpu_config,tuning));return 0;}\n")
+                                     "offsetof(perseus_gpu_config,tuning),sizeof(perseus_gpu_host_block),offsetof(perseus_gpu_config,direct_bytes),"
+                                     "offsetof(perseus_gpu_config,copy_threads),offsetof(perseus_gpu_stats,host_blocks));return 0;}\n")
         subprocess.run(["gcc", "-I", str(ROOT / "include"), f"{td}/s.c", "-o", f"{td}/s"], check=True)
         sizes = [int(x) for x in subprocess.run([f"{td}/s"], capture_output=True, text=True, check=True).stdout.split()]
     assert sizes == [C.sizeof(pg.Config), C.sizeof(pg.Tuning), C.sizeof(pg.Seg), C.sizeof(pg.Block), C.sizeof(pg.Stats),
-                     C.sizeof(pg.VrxConfig), C.sizeof(pg.VrxStats), pg.Config.tuning.offset]
+                     C.sizeof(pg.VrxConfig), C.sizeof(pg.VrxStats), pg.Config.tuning.offset, C.sizeof(pg.HostBlock),
+                     pg.Config.direct_bytes.offset, pg.Config.copy_threads.offset, pg.Stats.host_blocks.offset]
+    assert C.sizeof(pg.Config) == 88 and C.sizeof(pg.Stats) == 96          # ABI 2 sizes: the ABI 3 fields took reserved space
 
 
 def test_no_fallback_without_device(pg):

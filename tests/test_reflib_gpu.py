@@ -98,7 +98,7 @@ def test_cfg1_through_the_reference_library_paced_at_95k(pg, coracle, reflib, tm
             time.sleep(0.5)
             assert reflib.L.perseus_stop_async_input(d) == 0
             n = reflib.state()["completed_ok"]
-            assert 38 <= n <= 56, n                              # 0.5 s at 92.8 transfers/s
+            assert 35 <= n <= 90, n                              # 0.5 s (more if the box is busy) at 92.8 transfers/s
         time.sleep(0.08)                                         # nothing arrives any more: the watchdog (50 ms) submits the tail
         st = h.stats()
         # perseus_input_queue_cancel clears callback_fn on the application thread (perseus-in.c:131) while the poll thread may be
