@@ -52,8 +52,9 @@
 extern "C" {
 #endif
 
-#define PERSEUS_GPU_ABI_VERSION 3   /* 3: host sink, perseus_gpu_config.direct_bytes / copy_threads (were reserved, 0 = default),
-                                       perseus_gpu_stats.host_blocks (was reserved): binary compatible with 2 */
+#define PERSEUS_GPU_ABI_VERSION 3   /* 3: host sink, perseus_gpu_config.direct_bytes / copy_threads (were reserved, 0 = default) and
+                                       eager_gap_us (appended: struct_size), perseus_gpu_stats.host_blocks (was reserved): callers
+                                       built against 2 keep working */
 
 /* Same signature as perseus_input_callback (perseus-sdr.h:81): a pointer of either type converts to the
  * other without a cast.  Declared under its own name so this header never collides with perseus-sdr.h. */
@@ -111,9 +112,9 @@ typedef struct perseus_gpu_config {
 	uint64_t slab_bytes;      /* bytes per slab, rounded down to a multiple of 48 (0 = 8 MiB)   */
 	uint32_t nstreams;        /* CUDA streams the streaming path rotates its slabs over, 1..8 (0 = 2) */
 	uint32_t max_latency_us;  /* streaming path: a partly filled slab is submitted once its oldest transfer has
-	                             waited this long, checked at every callback (0 = 50 000 us; 0xFFFFFFFF = only
-	                             when full).  At 95 kS/s a transfer arrives every 10.8 ms, so slabs are
-	                             time-bounded, not size-bounded, on a real receiver.                */
+	                             waited this long, checked at every callback and by the watchdog (0 = 50 000 us;
+	                             0xFFFFFFFF = only when full).  See also eager_gap_us: at a real receiver's rates
+	                             transfers do not wait at all.                                         */
 	uint64_t chunk_bytes;     /* host<->device staging chunk for perseus_gpu_unpack with host pointers, rounded down to a
 	                             multiple of 12288 (whole pages in and out; of 48 below that)  (0 = 32 MiB)  */
 	perseus_gpu_tuning tuning;
@@ -129,6 +130,14 @@ typedef struct perseus_gpu_config {
 	                             each chunk between the application's memory and pinned bounce buffers while the copy engines
 	                             work on the neighbouring chunks  (0 = min(8, cores/2); 1 = the caller alone; 0xFFFFFFFF = hand
 	                             pageable pointers to the CUDA runtime, which stages them on the calling thread)           */
+	uint32_t eager_gap_us;    /* streaming path: a transfer that arrives after perseus_gpu_input_callback has been idle for longer
+	                             than this is submitted at once instead of waiting for its slab to fill or to age: the stream
+	                             is slower than the GPU path (any real receiver: a transfer every 0.5 ms at 2 MS/s, every
+	                             10.8 ms at 95 kS/s), so every transfer is in device memory ~30 us after its callback; transfers
+	                             that arrive back to back (replayed recordings, bursts) still fill slabs.  Only with a latency
+	                             bound (max_latency_us != 0xFFFFFFFF).  (0 = 100 us; 0xFFFFFFFF = never: slabs go out full or
+	                             over age only)                                                                            */
+	uint32_t reserved2[3];    /* the struct may grow: struct_size tells the library which fields the caller knows     */
 } perseus_gpu_config;
 
 /* perseus_gpu_config.options */

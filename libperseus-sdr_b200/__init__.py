@@ -50,7 +50,7 @@ class Config(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("stream_flags", C.c_uint32), ("nslabs", C.c_uint32),
                 ("slab_bytes", C.c_uint64), ("nstreams", C.c_uint32), ("max_latency_us", C.c_uint32), ("chunk_bytes", C.c_uint64),
                 ("tuning", Tuning), ("options", C.c_uint32), ("stage_slots", C.c_uint32), ("direct_bytes", C.c_uint32),
-                ("copy_threads", C.c_uint32)]
+                ("copy_threads", C.c_uint32), ("eager_gap_us", C.c_uint32), ("reserved2", C.c_uint32 * 3)]
 
 
 class Seg(C.Structure):
@@ -71,6 +71,7 @@ class HostBlock(C.Structure):
 
 HOST_SINK = C.CFUNCTYPE(None, C.POINTER(HostBlock), C.c_void_p)
 DIRECT_NEVER = 0xFFFFFFFF
+EAGER_NEVER = 0xFFFFFFFF              # Config.eager_gap_us: slabs go out full or over age only
 COPY_BY_RUNTIME = 0xFFFFFFFF          # Config.copy_threads: leave pageable buffers to the CUDA runtime
 
 
@@ -231,13 +232,14 @@ class PerseusGpu:
 
     def __init__(self, device: int = 0, stream_flags: int = 0, nslabs: int = 0, slab_bytes: int = 0, nstreams: int = 0,
                  chunk_bytes: int = 0, max_latency_us: int = 0, options: int = 0, stage_slots: int = 0, direct_bytes: int = 0,
-                 copy_threads: int = 0, **tuning):
+                 copy_threads: int = 0, eager_gap_us: int = 0, **tuning):
         L = lib()
         cfg = Config()
         cfg.struct_size = C.sizeof(Config)
         cfg.device, cfg.stream_flags, cfg.nslabs, cfg.slab_bytes = device, stream_flags, nslabs, slab_bytes
         cfg.nstreams, cfg.chunk_bytes, cfg.max_latency_us = nstreams, chunk_bytes, max_latency_us
         cfg.options, cfg.stage_slots, cfg.direct_bytes, cfg.copy_threads = options, stage_slots, direct_bytes, copy_threads
+        cfg.eager_gap_us = eager_gap_us
         for k, v in tuning.items():
             setattr(cfg.tuning, k, v)
         self.h = C.c_void_p()

@@ -75,6 +75,7 @@ static void scenario_trampoline()
 	cfg.slab_bytes = 6144 * 5;
 	cfg.nslabs = 3;
 	cfg.max_latency_us = 300;
+	cfg.eager_gap_us = 0xFFFFFFFFu;    // slabs by size and age only: this scenario wants the watchdog busy (E runs the eager path)
 	perseus_gpu *h = nullptr;
 	CHECK(perseus_gpu_open(&h, &cfg) == 0);
 	Collected col;

@@ -70,7 +70,7 @@ def test_struct_layouts_match_header(pg):
     assert sizes == [C.sizeof(pg.Config), C.sizeof(pg.Tuning), C.sizeof(pg.Seg), C.sizeof(pg.Block), C.sizeof(pg.Stats),
                      C.sizeof(pg.VrxConfig), C.sizeof(pg.VrxStats), pg.Config.tuning.offset, C.sizeof(pg.HostBlock),
                      pg.Config.direct_bytes.offset, pg.Config.copy_threads.offset, pg.Stats.host_blocks.offset]
-    assert C.sizeof(pg.Config) == 88 and C.sizeof(pg.Stats) == 96          # ABI 2 sizes: the ABI 3 fields took reserved space
+    assert C.sizeof(pg.Config) == 88 + 16 and C.sizeof(pg.Stats) == 96     # ABI 2 sizes + the appended eager_gap_us / reserved2
 
 
 def test_no_fallback_without_device(pg):
@@ -81,6 +81,21 @@ def test_no_fallback_without_device(pg):
         pg.PerseusGpu(device=0)
     assert e.value.code in (pg.ERR["NODEVICE"], pg.ERR["CUDAERR"])
     assert e.value.msg
+
+
+def test_config_struct_size_is_checked_before_anything_else(pg):
+    """The config struct grows by struct_size: an ABI-2 caller's 88 bytes are accepted (the call then fails for lack of a device
+    here, not for its size), sizes the library cannot know are refused."""
+    L, h = pg.lib(), C.c_void_p()
+    for size, refused in ((88, False), (C.sizeof(pg.Config), False), (4, True), (C.sizeof(pg.Config) + 8, True)):
+        cfg = pg.Config()
+        cfg.struct_size = size
+        rc = L.perseus_gpu_open(C.byref(h), C.byref(cfg))
+        if rc == 0:                                                    # a GPU box: the handle opened
+            assert not refused
+            L.perseus_gpu_close(h)
+        else:
+            assert (rc == pg.ERR["ERRPARAM"] and b"struct_size" in L.perseus_gpu_errorstr()) == refused, (size, rc)
 
 
 def test_null_handle_errors(pg):

@@ -743,7 +743,8 @@ def test_stream_file_is_byte_identical_to_perseustest_output(pg, coracle, tmp_pa
     fwrite (oracle/_ref) when that library travelled here, else with the restated oracle."""
     path = tmp_path / "perseusdata"
     ntransfers = 97
-    with pg.PerseusGpu(device=0, stream_flags=getattr(pg, fmt), slab_bytes=6144 * 10, nslabs=3, direct_bytes=SLAB_ROUTES[route]) as h:
+    with pg.PerseusGpu(device=0, stream_flags=getattr(pg, fmt), slab_bytes=6144 * 10, nslabs=3, direct_bytes=SLAB_ROUTES[route],
+                       eager_gap_us=pg.EAGER_NEVER) as h:                 # slabs are counted below
         h.stream_to_file(str(path))
         v = pg.VirtualReceiver(sample_rate=250000, seed=11)
         v.run(6144, *h.callback, ntransfers)
@@ -882,7 +883,8 @@ def test_streaming_latency_bound_submits_partial_slabs(pg, coracle):
     """A real receiver delivers a 6144-byte transfer every 10.8 ms at 95 kS/s: slabs must go out on time, not when full."""
     import time
     wire = coracle.synth_random(6144 * 6, seed=17).reshape(6, 6144)
-    with pg.PerseusGpu(device=0, stream_flags=pg.OUT_FLOAT, slab_bytes=8 << 20, max_latency_us=2000, options=pg.OPT_NO_WATCHDOG) as h:
+    with pg.PerseusGpu(device=0, stream_flags=pg.OUT_FLOAT, slab_bytes=8 << 20, max_latency_us=2000, options=pg.OPT_NO_WATCHDOG,
+                       eager_gap_us=pg.EAGER_NEVER) as h:                 # this test is about the age check alone
         blocks = []
         h.set_sink(lambda blk, extra: blocks.append((blk.contents.first_sample, blk.contents.nsamples, blk.contents.dev_f32)))
         for k in range(6):
@@ -904,6 +906,36 @@ def test_streaming_latency_bound_submits_partial_slabs(pg, coracle):
         assert blocks == [3 * 1024]
 
 
+def test_slow_stream_goes_out_transfer_by_transfer_fast_stream_fills_slabs(pg, coracle):
+    """perseus_gpu_config.eager_gap_us: a transfer that arrives after the callback has been idle (a real receiver: one every
+    0.5-10.8 ms) is submitted at once, with the handle's DEFAULT 8 MiB slabs and 50 ms bound; the same handle fed back to back
+    (a replayed recording) batches into slabs again."""
+    import time
+    wire = coracle.synth_random(6144 * 12, seed=41).reshape(12, 6144)
+    got = []
+    with pg.PerseusGpu(device=0, stream_flags=pg.OUT_INT32) as h:
+        h.set_host_sink(collect_host_blocks(got))
+        h.input_callback(wire[0].ctypes.data, 6144)       # first callback ever: allocations, and no idle time to go by
+        h.flush()
+        for k in range(1, 12):
+            time.sleep(0.002)
+            h.input_callback(wire[k].ctypes.data, 6144)
+            t0 = time.perf_counter()
+            while len(got) < k + 1 and time.perf_counter() - t0 < 0.5:
+                time.sleep(0.0001)
+            assert len(got) == k + 1, (k, len(got))       # in host memory without a flush, a poll, or the 50 ms bound
+        st = h.stats()
+        assert st["slabs"] == 12 and st["watchdog_submits"] == 0 and [g[1] for g in got] == [1024] * 12
+        assert np.array_equal(np.concatenate([g[2] for g in got]), coracle.unpack(wire.reshape(-1), O.MODE_I32).view(np.uint32).reshape(-1))
+        # back to back: ~3000 transfers (18 MB) from the virtual receiver's loop -> three slabs, give or take a scheduling hiccup
+        h.set_host_sink(None)
+        v = pg.VirtualReceiver(sample_rate=2_000_000, seed=6)
+        v.run(6144, *h.callback, 3000)
+        h.flush()
+        v.close()
+        assert 3 <= h.stats()["slabs"] - 12 <= 8, h.stats()
+
+
 def test_latency_bound_holds_without_a_following_callback(pg, coracle):
     """The stream stalls after three transfers (USB error, or the tail before perseus_stop_async_input): the partial slab
     must still reach the device within max_latency_us -- by the handle's watchdog thread, or by perseus_gpu_poll when the
@@ -912,7 +944,8 @@ def test_latency_bound_holds_without_a_following_callback(pg, coracle):
     wire = coracle.synth_random(6144 * 3, seed=23).reshape(3, 6144)
     want = coracle.unpack(wire.reshape(-1), O.MODE_F32).view(np.uint32).reshape(-1)
     bound = 0.020
-    with pg.PerseusGpu(device=0, stream_flags=pg.OUT_FLOAT, slab_bytes=8 << 20, max_latency_us=int(bound * 1e6)) as h:
+    with pg.PerseusGpu(device=0, stream_flags=pg.OUT_FLOAT, slab_bytes=8 << 20, max_latency_us=int(bound * 1e6),
+                       eager_gap_us=pg.EAGER_NEVER) as h:                 # a burst that stops: the watchdog's case
         h.input_callback(wire[0].ctypes.data, 6144)       # first callback of a handle allocates its slabs (tens of ms): not timed
         h.flush()
         blocks = []
@@ -935,7 +968,7 @@ def test_latency_bound_holds_without_a_following_callback(pg, coracle):
         h.flush()
         assert [(b[1], b[2]) for b in blocks] == [(1024, 3072), (4096, 1024)]
     with pg.PerseusGpu(device=0, stream_flags=pg.OUT_FLOAT, slab_bytes=8 << 20, max_latency_us=int(bound * 1e6),
-                       options=pg.OPT_NO_WATCHDOG) as h:
+                       options=pg.OPT_NO_WATCHDOG, eager_gap_us=pg.EAGER_NEVER) as h:
         blocks = []
         h.set_sink(lambda blk, extra: blocks.append((blk.contents.first_sample, blk.contents.nsamples, blk.contents.dev_f32)))
         for k in range(3):
@@ -970,7 +1003,9 @@ def test_cfg1_95k_paced_float_file_equals_reference(pg, coracle, tmp_path):
         v.close()
         n = st["delivered"]
         assert 40 <= n <= 95 and 80 < st["ksamples_per_s"] < 110, st       # 0.6 s (more if the box is busy) at 92.8 transfers/s
-        assert mid["slabs"] >= 8 and mid["callbacks"] == n, mid            # ~one slab per 50 ms, long before any flush
+        # a transfer every 10.8 ms: each one goes out on arrival (eager_gap_us), long before any flush or age bound -- only the very
+        # first waits for the second (the handle has no idle time to go by yet)
+        assert n - 2 <= mid["slabs"] <= n and mid["callbacks"] == n and mid["watchdog_submits"] == 0, mid
     wire = coracle.synth_random(n * 6144, seed=95)
     assert path.read_bytes() == O.Ref().unpack(wire, O.MODE_F32, chunk=6144).tobytes()
 
@@ -1018,7 +1053,7 @@ def test_sink_on_the_watchdog_thread_may_use_its_handle(pg, coracle):
     """The sink runs on whichever thread submits the slab -- here the watchdog -- and may call the handle's plumbing from there."""
     import time
     wire = coracle.synth_random(6144 * 2, seed=77).reshape(2, 6144)
-    with pg.PerseusGpu(device=0, stream_flags=pg.OUT_FLOAT, max_latency_us=5000) as h:
+    with pg.PerseusGpu(device=0, stream_flags=pg.OUT_FLOAT, max_latency_us=5000, eager_gap_us=pg.EAGER_NEVER) as h:
         got, seen = [], []
 
         def sink(blk, extra):

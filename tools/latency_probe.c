@@ -86,8 +86,46 @@ static int run(int host_mode, unsigned direct, size_t slab)
 	return perseus_gpu_close(h) < 0;
 }
 
-int main(void)
+/* The DEFAULT handle (8 MiB slabs, 50 ms bound, eager_gap_us = 100) fed like a real receiver: one 6144-byte transfer every
+ * `period_us`.  Latency of each transfer = callback start -> host sink sees its block (nobody flushes or polls). */
+static int run_paced(unsigned period_us)
 {
+	perseus_gpu_config cfg;
+	memset(&cfg, 0, sizeof cfg);
+	cfg.struct_size = sizeof cfg;
+	cfg.stream_flags = PERSEUS_GPU_OUT_FLOAT;
+	perseus_gpu *h = NULL;
+	if (perseus_gpu_open(&h, &cfg) < 0 || perseus_gpu_set_host_sink(h, host_sink, NULL) < 0) { fprintf(stderr, "open: %s\n", perseus_gpu_errorstr()); return 1; }
+	static unsigned char xfer[XFER];
+	perseus_synth_fill(xfer, XFER, PERSEUS_SYNTH_RANDOM, PERSEUS_SYNTH_SEED, 0);
+	perseus_gpu_input_callback(xfer, XFER, h);
+	perseus_gpu_flush(h);
+	static double lat[REPS];
+	for (int r = -10; r < REPS; ++r) {
+		const double until = now_us() + period_us;
+		while (now_us() < until) { }
+		const unsigned long long seen = atomic_load(&g_blocks);
+		const double t0 = now_us();
+		perseus_gpu_input_callback(xfer, XFER, h);
+		const double t1 = now_us();
+		while (atomic_load(&g_blocks) == seen && now_us() - t0 < 2e5) { }
+		if (atomic_load(&g_blocks) == seen) { fprintf(stderr, "paced: a transfer was not delivered within 0.2 s\n"); return 1; }
+		if (r >= 0) lat[r] = now_us() - t0;
+		(void)t1;
+	}
+	qsort(lat, REPS, sizeof lat[0], cmp);
+	perseus_gpu_stats st;
+	perseus_gpu_get_stats(h, &st);
+	printf("{\"mode\": \"paced_default_handle_host_sink\", \"period_us\": %u, \"median_us\": %.1f, \"p95_us\": %.1f, \"min_us\": %.1f, \"slabs\": %llu, "
+	       "\"callbacks\": %llu, \"watchdog_submits\": %llu}\n", period_us, lat[REPS / 2], lat[REPS * 95 / 100], lat[0],
+	       (unsigned long long)st.slabs, (unsigned long long)st.callbacks, (unsigned long long)st.watchdog_submits);
+	fflush(stdout);
+	return perseus_gpu_close(h) < 0;
+}
+
+int main(int argc, char **argv)
+{
+	if (argc > 1 && !strcmp(argv[1], "paced")) return run_paced(512) || run_paced(10779);   /* 2 MS/s and 95 kS/s transfer periods */
 	static const size_t slabs[] = {XFER, 2 * XFER, 8 * XFER, 32 * XFER, 128 * XFER, 512 * XFER, 1365 * XFER};
 	for (int host_mode = 0; host_mode < 2; ++host_mode)
 		for (size_t i = 0; i < sizeof slabs / sizeof slabs[0]; ++i)
