@@ -31,7 +31,7 @@ static void usage(void)
 	        "-b ............ buffer size in bytes (default 1024)\n"
 	        "-t ............ duration in seconds, paced at the sample rate (default: not paced, see -N)\n"
 	        "-N ............ number of transfers to replay as fast as possible (default 1000)\n"
-	        "-o ............ output file name (default perseusdata)\n"
+	        "-o ............ output file name (default perseusdata; - = standard output, as perseustest)\n"
 	        "-p ............ I/Q samples emitted as floating point instead of 32 bit integers\n"
 	        "-g ............ CUDA device ordinal (default 0)\n"
 	        "-h ............ this help\n");

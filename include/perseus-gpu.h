@@ -250,7 +250,8 @@ int perseus_gpu_set_host_sink(perseus_gpu *h, perseus_gpu_host_sink sink, void *
 
 /* Also writes the stream to `path` exactly as `perseustest -o path [-p]` would: a raw,
  * headerless sequence of {int32 I,int32 Q} (or {float I,float Q} when the handle streams
- * floats), 8 bytes per sample (perseustest.c:337-343,457,499).  path == NULL stops.  Blocks are written as they complete (same
+ * floats), 8 bytes per sample (perseustest.c:337-343,457,499).  path "-" is standard output, as there (perseustest.c:98,337): a consumer on a
+ * pipe receives the stream as it is unpacked.  path == NULL stops.  Blocks are written as they complete (same
  * delivery as the host sink); perseus_gpu_flush / close make the file complete. */
 int perseus_gpu_stream_to_file(perseus_gpu *h, const char *path);
 

@@ -128,6 +128,7 @@ struct perseus_gpu {
 	perseus_gpu_host_sink host_sink = nullptr;
 	void *host_sink_extra = nullptr;
 	FILE *fout = nullptr;
+	bool fout_is_stdout = false;                 // path "-" (perseustest.c:98,337): flushed, never closed
 	std::atomic<int> io_error{0};                // deliver_slab could not write the file: surfaced at the next retire / flush
 	std::atomic<uint64_t> host_blocks{0};        // blocks deliver_slab has handed over
 	size_t direct_bytes = 0;                     // slabs up to this size are unpacked straight from the pinned slab (no H2D copy)
@@ -928,7 +929,7 @@ int perseus_gpu_close(perseus_gpu *h)
 			cudaGetLastError();
 		}
 		if (h->fout) {
-			if (fclose(h->fout) != 0 && !rc) rc = fail(PERSEUS_GPU_IOERROR, "closing stream file failed");
+			if ((h->fout_is_stdout ? fflush(h->fout) : fclose(h->fout)) != 0 && !rc) rc = fail(PERSEUS_GPU_IOERROR, "closing stream file failed");
 		}
 	}
 	delete h->pool;   // joins the helper threads
@@ -1190,13 +1191,14 @@ int perseus_gpu_stream_to_file(perseus_gpu *h, const char *path)
 	if (h->fout) {
 		FILE *f = h->fout;
 		h->fout = nullptr;
-		if (fclose(f) != 0) return fail(PERSEUS_GPU_IOERROR, "closing stream file failed");
+		if ((h->fout_is_stdout ? fflush(f) : fclose(f)) != 0) return fail(PERSEUS_GPU_IOERROR, "closing stream file failed");
 	}
 	if (!path) return 0;
 	const unsigned f = h->stream_fmt;
 	if ((f & PERSEUS_GPU_OUT_INT32) && (f & (PERSEUS_GPU_OUT_FLOAT | PERSEUS_GPU_OUT_FLOAT_POW2)))
 		return fail(PERSEUS_GPU_ERRPARAM, "a stream file holds one format (perseustest -p selects it); open the handle with a single stream format");
-	h->fout = fopen(path, "wb");
+	h->fout_is_stdout = strcmp(path, "-") == 0;   // perseustest -o - : the stream goes to standard output, for a consumer on a pipe
+	h->fout = h->fout_is_stdout ? stdout : fopen(path, "wb");
 	if (!h->fout) return fail(PERSEUS_GPU_IOERROR, "cannot open %s for writing", path);
 	return 0;
 }

@@ -55,6 +55,16 @@ def test_example_output_file_equals_reference_callbacks(replay_bin, tmp_path, co
 
 
 @pytest.mark.gpu
+def test_example_streams_to_standard_output_like_perseustest_dash(replay_bin, coracle):
+    """`perseustest -o -` leaves fout = stdout (perseustest.c:98,337) for a consumer on a pipe; so does the GPU path."""
+    env = dict(os.environ, LD_LIBRARY_PATH=f"{LIBDIR}:{os.environ.get('LD_LIBRARY_PATH', '')}")
+    r = subprocess.run([str(replay_bin), "-s", "2000000", "-n", "6", "-b", "1024", "-N", "77", "-o", "-", "-p"], capture_output=True, env=env, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == coracle.unpack(coracle.synth_random(77 * 6144), O.MODE_F32).tobytes()
+    assert b"Bye" in r.stderr and not os.path.exists("-")
+
+
+@pytest.mark.gpu
 def test_example_rejects_illegal_buffer_sizes_like_the_reference(replay_bin, tmp_path):
     r = run(replay_bin, "-n", "5", "-b", "1024", "-N", "3", "-o", str(tmp_path / "x"))    # 5120 is not a multiple of 6144
     assert r.returncode == 1 and "integer multiple of 6144" in r.stderr                   # perseus-sdr.c:672
