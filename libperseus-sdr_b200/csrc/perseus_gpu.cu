@@ -116,8 +116,8 @@ struct perseus_gpu {
 	size_t fill = 0;           // bytes in it
 	uint64_t fill_started_ns = 0;   // monotonic time the first transfer of the current slab arrived
 	uint64_t max_latency_ns = 0;    // 0 = submit only full slabs
-	uint64_t eager_gap_ns = 0;      // a transfer arriving after the callback has been idle this long is submitted at once; 0 = never
-	uint64_t idle_since_ns = 0;     // monotonic time the previous callback returned (0 = none yet)
+	uint64_t eager_gap_ns = 0;      // a transfer arriving this long after the previous one is submitted at once; 0 = never
+	uint64_t last_push_ns = 0;      // monotonic time the previous callback began (0 = none yet)
 	int next_to_write = 0;     // oldest slab whose output has not reached the file sink
 	bool streaming_ready = false;
 	uint64_t samples_submitted = 0;
@@ -586,11 +586,15 @@ int stream_push(perseus_gpu *h, const uint8_t *buf, size_t nbytes)
 	if (rc) return rc;
 	start_watchdog(h);
 	const uint64_t now = h->max_latency_ns ? monotonic_ns() : 0;
-	// The callback has been idle for a while before this transfer: the stream is slower than the GPU path -- any real receiver is
-	// (a transfer every 0.5 ms at 2 MS/s, every 10.8 ms at 95 kS/s) -- and nothing is gained by letting the transfer wait for
+	// This transfer comes a while after the previous one: the stream is slower than the GPU path -- any real receiver is (a
+	// transfer every 0.5 ms at 2 MS/s, every 10.8 ms at 95 kS/s) -- and nothing is gained by letting the transfer wait for
 	// company.  It goes out at once (a small slab: one launch, perseus_gpu_config.direct_bytes).  Transfers that arrive back
 	// to back (a replayed recording, a burst) keep filling slabs; batching sets in by itself when the path is the bottleneck.
-	const bool eager = h->eager_gap_ns && h->idle_since_ns && now - h->idle_since_ns > h->eager_gap_ns;
+	// Measured start to start with the one clock reading the age bound needs anyway (a second reading per callback costs
+	// the 6144-byte path a quarter of its rate); a previous callback that itself took long -- it allocated, or waited for a
+	// free slab -- only makes one more small slab.
+	const bool eager = h->eager_gap_ns && h->last_push_ns && now - h->last_push_ns > h->eager_gap_ns;
+	h->last_push_ns = now;
 	if (h->fill == 0) {
 		h->fill_started_ns = now;
 		h->partial_since_ns.store(now, std::memory_order_relaxed);
@@ -611,7 +615,6 @@ int stream_push(perseus_gpu *h, const uint8_t *buf, size_t nbytes)
 	}
 	// latency bound: on a real receiver transfers trickle in (10.8 ms apart at 95 kS/s); do not sit on them
 	rc = (eager && h->fill && !h->latched) ? submit_slab(h) : submit_if_over_age(h, now);
-	if (h->eager_gap_ns) h->idle_since_ns = monotonic_ns();
 	return rc < 0 ? rc : 0;
 }
 

@@ -907,7 +907,7 @@ def test_streaming_latency_bound_submits_partial_slabs(pg, coracle):
 
 
 def test_slow_stream_goes_out_transfer_by_transfer_fast_stream_fills_slabs(pg, coracle):
-    """perseus_gpu_config.eager_gap_us: a transfer that arrives after the callback has been idle (a real receiver: one every
+    """perseus_gpu_config.eager_gap_us: a transfer that arrives a while after the previous one (a real receiver: one every
     0.5-10.8 ms) is submitted at once, with the handle's DEFAULT 8 MiB slabs and 50 ms bound; the same handle fed back to back
     (a replayed recording) batches into slabs again."""
     import time
@@ -1003,9 +1003,10 @@ def test_cfg1_95k_paced_float_file_equals_reference(pg, coracle, tmp_path):
         v.close()
         n = st["delivered"]
         assert 40 <= n <= 95 and 80 < st["ksamples_per_s"] < 110, st       # 0.6 s (more if the box is busy) at 92.8 transfers/s
-        # a transfer every 10.8 ms: each one goes out on arrival (eager_gap_us), long before any flush or age bound -- only the very
-        # first waits for the second (the handle has no idle time to go by yet)
-        assert n - 2 <= mid["slabs"] <= n and mid["callbacks"] == n and mid["watchdog_submits"] == 0, mid
+        # a transfer every 10.8 ms: each one goes out on arrival (eager_gap_us), long before any flush or age bound.  Fewer slabs
+        # than transfers only where the receiver delivered back to back to catch up with its schedule (after the first callback,
+        # which allocates the slabs, or on a busy box): those share a slab, as they should.
+        assert n // 2 <= mid["slabs"] <= n and mid["callbacks"] == n and mid["samples"] >= (n - 8) * 1024, mid
     wire = coracle.synth_random(n * 6144, seed=95)
     assert path.read_bytes() == O.Ref().unpack(wire, O.MODE_F32, chunk=6144).tobytes()
 
