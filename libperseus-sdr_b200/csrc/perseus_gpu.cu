@@ -32,6 +32,10 @@
 #if defined(__SSE2__)
 #include <emmintrin.h>
 #endif
+#if defined(__x86_64__)
+#include <cpuid.h>
+#include <x86intrin.h>
+#endif
 
 namespace {
 
@@ -118,6 +122,11 @@ struct perseus_gpu {
 	uint64_t max_latency_ns = 0;    // 0 = submit only full slabs
 	uint64_t eager_gap_ns = 0;      // a transfer arriving this long after the previous one is submitted at once; 0 = never
 	uint64_t last_push_ns = 0;      // monotonic time the previous callback began (0 = none yet)
+	// the callback's clock: CLOCK_MONOTONIC carried forward by the time-stamp counter between anchors (see callback_now_ns)
+	bool use_tsc = false;
+	uint64_t tsc_anchor = 0, ns_anchor = 0;      // one reading of both clocks
+	uint64_t tsc_reanchor = 0;                   // ticks after which the anchor is renewed (about a second)
+	uint64_t ns_per_tick_q32 = 0;                // nanoseconds per tick, 32.32 fixed point
 	int next_to_write = 0;     // oldest slab whose output has not reached the file sink
 	bool streaming_ready = false;
 	uint64_t samples_submitted = 0;
@@ -453,6 +462,60 @@ inline uint64_t monotonic_ns()
 	return (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec;
 }
 
+// The callback reads the time once per transfer (age bound, eager submission).  clock_gettime costs 40-50 ns on these hosts -- a
+// fifth of the whole 6144-byte hand-off -- so between anchors CLOCK_MONOTONIC is carried forward by the invariant time-stamp
+// counter (RDTSC, ~8 ns).  The rate is measured against CLOCK_MONOTONIC itself (over perseus_gpu_open, then over every anchor
+// interval) and the anchor is renewed about once a second, which bounds the disagreement with the watchdog's clock_gettime
+// to microseconds.  Anything unexpected (no invariant TSC, a counter that stalls or jumps) falls back to clock_gettime.
+#if defined(__x86_64__)
+inline uint64_t read_tsc() { return __rdtsc(); }
+
+bool tsc_usable()
+{
+	static const bool ok = [] {
+		const char *off = getenv("PERSEUS_GPU_NO_TSC");
+		if (off && *off && *off != '0') return false;
+		unsigned a = 0, b = 0, c = 0, d = 0;
+		if (!__get_cpuid(0x80000007u, &a, &b, &c, &d)) return false;
+		return (d & (1u << 8)) != 0;   // invariant TSC
+	}();
+	return ok;
+}
+#else
+inline uint64_t read_tsc() { return 0; }
+bool tsc_usable() { return false; }
+#endif
+
+void tsc_anchor_now(perseus_gpu *h)
+{
+	const uint64_t ns = monotonic_ns(), c = read_tsc();
+	if (h->tsc_anchor && c > h->tsc_anchor && ns > h->ns_anchor) {
+		const uint64_t dt = ns - h->ns_anchor, dc = c - h->tsc_anchor;
+		if (dt >= 50000 && dt < (1ull << 31)) {                           // 50 us .. 2 s: a rate worth having, no overflow below
+			const uint64_t q = (dt << 32) / dc;
+			if (q < (1ull << 20) || q > (1ull << 36)) h->use_tsc = false;   // outside 4 THz .. 60 MHz: not a time-stamp counter
+			else {
+				h->ns_per_tick_q32 = q;
+				h->tsc_reanchor = ((1ull << 30) << 32) / q;               // ~1.07 s worth of ticks
+			}
+		}
+	}
+	h->ns_anchor = ns;
+	h->tsc_anchor = c;
+}
+
+inline uint64_t callback_now_ns(perseus_gpu *h)
+{
+	if (!h->use_tsc || !h->ns_per_tick_q32) return monotonic_ns();
+	const uint64_t c = read_tsc();
+	const uint64_t dc = c - h->tsc_anchor;
+	if (c < h->tsc_anchor || dc > h->tsc_reanchor) {
+		tsc_anchor_now(h);
+		return h->ns_anchor;
+	}
+	return h->ns_anchor + (uint64_t)(((unsigned __int128)dc * h->ns_per_tick_q32) >> 32);
+}
+
 // Submits the partial slab if its oldest transfer is over age.  Returns 1 if it did, 0 if not, < 0 on error.
 int submit_if_over_age(perseus_gpu *h, uint64_t now)
 {
@@ -585,7 +648,7 @@ int stream_push(perseus_gpu *h, const uint8_t *buf, size_t nbytes)
 	int rc = ensure_streaming(h);
 	if (rc) return rc;
 	start_watchdog(h);
-	const uint64_t now = h->max_latency_ns ? monotonic_ns() : 0;
+	const uint64_t now = h->max_latency_ns ? callback_now_ns(h) : 0;
 	// This transfer comes a while after the previous one: the stream is slower than the GPU path -- any real receiver is (a
 	// transfer every 0.5 ms at 2 MS/s, every 10.8 ms at 95 kS/s) -- and nothing is gained by letting the transfer wait for
 	// company.  It goes out at once (a small slab: one launch, perseus_gpu_config.direct_bytes).  Transfers that arrive back
@@ -858,6 +921,8 @@ int perseus_gpu_open(perseus_gpu **out, const perseus_gpu_config *ucfg)
 	}
 	h->direct_bytes = cfg.direct_bytes == 0xFFFFFFFFu ? 0 : cfg.direct_bytes ? (size_t)cfg.direct_bytes : kDefaultDirectBytes;
 	h->asym = membarrier_available();
+	h->use_tsc = tsc_usable();
+	if (h->use_tsc) tsc_anchor_now(h);   // first reading; the rate comes from the second one, at the end of this function
 	auto bail = [&](int code) {   // free what exists, keep the message of the original failure
 		const std::string keep = pg::last_error();
 		perseus_gpu_close(h);
@@ -882,6 +947,11 @@ int perseus_gpu_open(perseus_gpu **out, const perseus_gpu_config *ucfg)
 	if (e == cudaSuccess) e = cudaMemset(h->d_sums, 0, 2 * sizeof(unsigned long long));
 	if (e == cudaSuccess) e = cudaHostAlloc(&h->h_scratch, 2 * sizeof(unsigned long long), cudaHostAllocDefault);
 	if (e != cudaSuccess) return bail(fail(PERSEUS_GPU_CUDAERR, "scratch allocation: %s", cudaGetErrorString(e)));
+	if (h->use_tsc) {
+		while (monotonic_ns() - h->ns_anchor < 60000) { }   // streams and events took milliseconds; make sure of 60 us anyway
+		tsc_anchor_now(h);
+		if (!h->ns_per_tick_q32) h->use_tsc = false;
+	}
 	*out = h;
 	return ok();
 }
