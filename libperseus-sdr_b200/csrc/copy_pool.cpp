@@ -4,19 +4,23 @@
 #include <chrono>
 #include <cstring>
 #include <sched.h>
-#if defined(__SSE2__)
-#include <emmintrin.h>
+#include <cstdlib>
+#if defined(__x86_64__)
+#include <immintrin.h>
 #endif
 
 namespace pg {
 
-void copy_nontemporal(uint8_t *dst, const uint8_t *src, size_t n)
+// Three bodies of the same loop -- 16-, 32- and 64-byte non-temporal stores -- picked once from what the CPU has: one 64-byte
+// store fills a write-combining buffer that takes four 16-byte ones (about a tenth faster per core where it exists).
+#if defined(__x86_64__)
+namespace {
+
+using Body = size_t (*)(uint8_t *dst, const uint8_t *src, size_t n);   // copies whole blocks, returns the bytes it took
+
+size_t body_sse2(uint8_t *dst, const uint8_t *src, size_t n)
 {
-#if defined(__SSE2__)
-	size_t head = (16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15;
-	if (head > n) head = n;
-	memcpy(dst, src, head);
-	dst += head; src += head; n -= head;
+	const size_t n0 = n;
 	for (; n >= 64; n -= 64, src += 64, dst += 64) {
 		const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src));
 		const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + 16));
@@ -27,6 +31,68 @@ void copy_nontemporal(uint8_t *dst, const uint8_t *src, size_t n)
 		_mm_stream_si128(reinterpret_cast<__m128i *>(dst + 32), c);
 		_mm_stream_si128(reinterpret_cast<__m128i *>(dst + 48), d);
 	}
+	return n0 - n;
+}
+
+__attribute__((target("avx2"))) size_t body_avx2(uint8_t *dst, const uint8_t *src, size_t n)
+{
+	const size_t n0 = n;
+	for (; n >= 128; n -= 128, src += 128, dst += 128) {
+		const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src));
+		const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + 32));
+		const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + 64));
+		const __m256i d = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + 96));
+		_mm256_stream_si256(reinterpret_cast<__m256i *>(dst), a);
+		_mm256_stream_si256(reinterpret_cast<__m256i *>(dst + 32), b);
+		_mm256_stream_si256(reinterpret_cast<__m256i *>(dst + 64), c);
+		_mm256_stream_si256(reinterpret_cast<__m256i *>(dst + 96), d);
+	}
+	return n0 - n;
+}
+
+__attribute__((target("avx512f"))) size_t body_avx512(uint8_t *dst, const uint8_t *src, size_t n)
+{
+	const size_t n0 = n;
+	for (; n >= 256; n -= 256, src += 256, dst += 256) {
+		const __m512i a = _mm512_loadu_si512(src);
+		const __m512i b = _mm512_loadu_si512(src + 64);
+		const __m512i c = _mm512_loadu_si512(src + 128);
+		const __m512i d = _mm512_loadu_si512(src + 192);
+		_mm512_stream_si512(reinterpret_cast<__m512i *>(dst), a);
+		_mm512_stream_si512(reinterpret_cast<__m512i *>(dst + 64), b);
+		_mm512_stream_si512(reinterpret_cast<__m512i *>(dst + 128), c);
+		_mm512_stream_si512(reinterpret_cast<__m512i *>(dst + 192), d);
+	}
+	return n0 - n;
+}
+
+Body pick_body()
+{
+	const char *force = getenv("PERSEUS_GPU_NT_COPY");                 // tests / A-B: sse2, avx2 or avx512
+	__builtin_cpu_init();
+	const bool has512 = __builtin_cpu_supports("avx512f"), has2 = __builtin_cpu_supports("avx2");
+	if (force && !strcmp(force, "sse2")) return body_sse2;
+	if (force && !strcmp(force, "avx2") && has2) return body_avx2;
+	if (has512) return body_avx512;
+	if (has2) return body_avx2;
+	return body_sse2;
+}
+
+}  // namespace
+#endif
+
+void copy_nontemporal(uint8_t *dst, const uint8_t *src, size_t n)
+{
+#if defined(__x86_64__)
+	static const Body body = pick_body();
+	size_t head = (64 - (reinterpret_cast<uintptr_t>(dst) & 63)) & 63;   // the widest store wants a 64-byte aligned destination
+	if (head > n) head = n;
+	memcpy(dst, src, head);
+	dst += head; src += head; n -= head;
+	size_t done = body(dst, src, n);
+	dst += done; src += done; n -= done;
+	done = body_sse2(dst, src, n);                                       // what is left of a wider block, in 64-byte steps
+	dst += done; src += done; n -= done;
 #endif
 	memcpy(dst, src, n);
 }
@@ -61,7 +127,7 @@ void CopyPool::run_slice(const Job &j, int part)
 	const size_t len = j.n - a < per ? j.n - a : per;
 	if (j.nt) {
 		copy_nontemporal(j.dst + a, j.src + a, len);
-#if defined(__SSE2__)
+#if defined(__x86_64__)
 		_mm_sfence();   // this thread's non-temporal stores are visible before it reports the slice done
 #endif
 	} else {

@@ -13,6 +13,7 @@
 #include <vector>
 
 extern "C" size_t perseus_oracle_unpack(int mode, const uint8_t *in, size_t nbytes, void *out);
+namespace pg { void copy_nontemporal(uint8_t *dst, const uint8_t *src, size_t n); }   // csrc/copy_pool.h
 
 #define CHECK(c)                                                                          \
 	do {                                                                                  \
@@ -282,6 +283,23 @@ static void scenario_pageable_bounce()
 	b.join();
 }
 
+// G: the non-temporal copy (16/32/64-byte stores picked at run time; PERSEUS_GPU_NT_COPY forces one) at every destination and
+//    source phase and every length around its block sizes: exactly the bytes asked for, nothing outside
+static void scenario_nontemporal_copy()
+{
+	std::vector<uint8_t> src(4096 + 128), dst(4096 + 256), want(dst.size());
+	for (size_t i = 0; i < src.size(); ++i) src[i] = (uint8_t)(i * 131 + 7);
+	for (size_t doff = 0; doff < 70; doff += 3)
+		for (size_t soff = 0; soff < 5; ++soff)
+			for (size_t n : {0u, 1u, 15u, 63u, 64u, 65u, 127u, 128u, 200u, 255u, 256u, 257u, 510u, 511u, 767u, 1000u, 4000u}) {
+				memset(dst.data(), 0xEE, dst.size());
+				memset(want.data(), 0xEE, want.size());
+				memcpy(want.data() + 64 + doff, src.data() + soff, n);
+				pg::copy_nontemporal(dst.data() + 64 + doff, src.data() + soff, n);
+				CHECK(memcmp(dst.data(), want.data(), dst.size()) == 0);
+			}
+}
+
 int main()
 {
 	scenario_vrx_stats();
@@ -290,6 +308,7 @@ int main()
 	scenario_edges();
 	scenario_host_delivery();
 	scenario_pageable_bounce();
+	scenario_nontemporal_copy();
 	printf("host_stress: all scenarios passed\n");
 	return 0;
 }

@@ -24,8 +24,9 @@ for san in tsan asan; do
 		$CXX -std=c++17 -O1 -g $FLAGS -pthread -Wall -Wextra -Wno-tsan -I"$ROOT/tests/sanitize/fake_cuda" -I"$CSRC" \
 			-x c++ "$CSRC/perseus_gpu.cu" -x none $SRCS "$BUILD/oracle_$san.o" -o "$BUILD/host_stress_$san" &&
 		for nomb in 0 1; do   # the callback / owner hand-off has two implementations: sys_membarrier (asymmetric) and plain fences
-			echo "# PERSEUS_GPU_NO_MEMBARRIER=$nomb"
-			PERSEUS_GPU_NO_MEMBARRIER=$nomb TSAN_OPTIONS="halt_on_error=0 second_deadlock_stack=1" ASAN_OPTIONS="detect_leaks=1" "$BUILD/host_stress_$san"
+			echo "# PERSEUS_GPU_NO_MEMBARRIER=$nomb PERSEUS_GPU_NO_TSC=$nomb PERSEUS_GPU_NT_COPY=$([ $nomb = 1 ] && echo sse2 || echo widest)"
+			# ... and the callback's clock and the slab copy two each: TSC-carried / clock_gettime, widest / 16-byte stores
+			PERSEUS_GPU_NO_TSC=$nomb PERSEUS_GPU_NT_COPY=$([ $nomb = 1 ] && echo sse2) PERSEUS_GPU_NO_MEMBARRIER=$nomb TSAN_OPTIONS="halt_on_error=0 second_deadlock_stack=1" ASAN_OPTIONS="detect_leaks=1" "$BUILD/host_stress_$san"
 			status=$?
 			echo "# exit status $status"
 			[ $status -eq 0 ] || rc=1
