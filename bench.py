@@ -606,21 +606,36 @@ def ours(args):
         e2e_bal = None
         if world > 1 and not args.no_balanced:
             rates = sharding.allgather_float(own_rate["h2d"])
-            first_b, count_b = pg.shard_range_weighted(nbuf * world, rates, rank)
-            nb_b = count_b * BUF
-            ns_b = nb_b // 6
-            d_gen = h.dev_alloc(max(nb_b, 1))
-            h.generate(d_gen, nb_b, pg.SYNTH_RANDOM, pg.SYNTH_SEED, first_b * BUF)
-            pin_b = h.host_alloc(max(nb_b, 1))
-            h.memcpy(pin_b, d_gen, nb_b)
-            h.dev_free(d_gen)
-            d_ib, d_fb = h.dev_alloc(max(ns_b * 8, 1)), h.dev_alloc(max(ns_b * 8, 1))
-            sums_b = []
+            cap_b = (min(nbuf * world, nbuf * 2) + 16) * BUF                # no rank is ever given more than twice an equal share
+            d_gen = h.dev_alloc(cap_b)
+            pin_b = h.host_alloc(cap_b)
+            d_ib, d_fb = h.dev_alloc(cap_b // 6 * 8), h.dev_alloc(cap_b // 6 * 8)
+            history = []
+            for it in range(args.balance_passes + 1):
+                rates = [max(r, 1e-3) for r in rates]
+                lim = 2.0 * sum(rates) / world
+                rates = [min(r, lim) for r in rates]
+                first_b, count_b = pg.shard_range_weighted(nbuf * world, rates, rank)
+                nb_b = count_b * BUF
+                assert nb_b <= cap_b, (count_b, nbuf)
+                ns_b = nb_b // 6
+                h.generate(d_gen, nb_b, pg.SYNTH_RANDOM, pg.SYNTH_SEED, first_b * BUF)
+                h.memcpy(pin_b, d_gen, nb_b)
+                sums_b = []
 
-            def bal_step():
-                h.unpack(pin_b, nb_b, d_ib, d_fb, FUSED | pg.ASYNC | pg.CHECKSUM)
-                sums_b.append(h.get_checksums())
+                def bal_step():
+                    h.unpack(pin_b, nb_b, d_ib, d_fb, FUSED | pg.ASYNC | pg.CHECKSUM)
+                    sums_b.append(h.get_checksums())
 
+                history.append([round(r, 1) for r in rates])
+                if it == args.balance_passes:
+                    break
+                # a pass of all ranks at once with these shards; each rank's own bytes / own time are the next weights
+                bal_step()
+                barrier()
+                t0 = time.perf_counter()
+                bal_step()
+                rates = sharding.observed_rates(nb_b / 1e9, time.perf_counter() - t0)
             ms_bal = timed(bal_step, e2e_steps, 2)
             assert len(set(sums_b)) == 1 and sums_b[0] == (h.checksum(d_ib, ns_b * 2), h.checksum(d_fb, ns_b * 2))
             # a different sharding of the SAME recording: the shard checksums must add up to the same whole-recording checksum
@@ -629,10 +644,12 @@ def ours(args):
             e2e_bal = {"value": round(total_samples / (ms_bal * 1e-3) / 1e6, 1), "unit": UNIT, "ms_per_step": round(ms_bal, 3),
                        "h2d_bytes_per_step_all_gpus": int(nbytes * world), "d2h_bytes_per_step": 16,
                        "aggregate_h2d_gbs": round(nbytes * world / (ms_bal * 1e-3) / 1e9, 1),
-                       "link_gbs_per_rank": [round(r, 1) for r in rates], "transfers_per_rank": [int(c) for c in shares],
-                       "what": "the same call on the same N x cfg2 recording, sharded with perseus_gpu_shard_range_weighted by each rank's rate in the "
-                               "concurrent plain pinned copy measured just before; shard checksums add up to the equal-shard recording checksum"}
-            h.host_free(pin_b); h.dev_free(d_ib); h.dev_free(d_fb)
+                       "link_gbs_per_rank": history[-1], "weights_history": history, "transfers_per_rank": [int(c) for c in shares],
+                       "what": "the same call on the same N x cfg2 recording, sharded with perseus_gpu_shard_range_weighted: weights start from each "
+                               "rank's rate in the concurrent plain pinned copy measured just before and are refined over "
+                               f"{args.balance_passes} untimed pass(es) from each rank's own bytes / own time (shards that finish together see "
+                               "steady-state rates); shard checksums add up to the equal-shard recording checksum"}
+            h.host_free(pin_b); h.dev_free(d_gen); h.dev_free(d_ib); h.dev_free(d_fb)
 
         e2e_rt = None
         if not args.no_roundtrip:
@@ -830,6 +847,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip every host-fed leg (the line then has e2e: null)")
     ap.add_argument("--no-single", action="store_true", help="skip the one-format kernels")
     ap.add_argument("--no-balanced", action="store_true", help="skip the link-weighted sharding of the end-to-end leg (N > 1)")
+    ap.add_argument("--balance-passes", type=int, default=3, help="untimed passes that refine the shard weights from observed rates (N > 1)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-callback", action="store_true")
     ap.add_argument("--no-probe", action="store_true")

@@ -56,6 +56,14 @@ def allgather_float(x: float) -> list[float]:
     return [float(t.item()) for t in out]
 
 
+def observed_rates(units: float, seconds: float) -> list[float]:
+    """Every rank's units / seconds over the pass it just finished, in rank order: the shard weights of the next pass
+    (perseus_gpu_shard_range_weighted).  A rank that finishes early leaves the shared host path to the others, which flatters
+    THEIR rates, so weights taken from an unbalanced pass over-feed the slow ranks; once the shards finish together the
+    observed rates are the steady-state ones.  Two or three passes settle it."""
+    return allgather_float(units / max(seconds, 1e-9))
+
+
 def gather_ranges(first: int, count: int) -> list[tuple[int, int]]:
     """Every rank's (first, count), in rank order."""
     import torch

@@ -38,7 +38,10 @@ def _worker(rank, world, initfile, q):
         wfirst, wcount = pg.shard_range_weighted(NBUF, rates, rank)
         wwire = pg.synth_fill(wcount * 6144, pg.SYNTH_RANDOM, pg.SYNTH_SEED, wfirst * 6144)
         wtotal = sh.allreduce_sum_u64(co.checksum32(co.unpack(wwire, O.MODE_F32).reshape(-1), first_index=wfirst * 2048))
-        q.put((rank, ranges, total, slowest, big, rates, (wfirst, wcount), wtotal))
+        # weights refined from observed rates (bench.py --balance-passes): a simulated box in which the slow ranks share a path
+        # that speeds up once the fast ranks have finished -- the first measurement flatters them, the passes correct it
+        obs = sh.observed_rates(float(wcount), float(wcount) / (10.0 + 7.5 * rank))
+        q.put((rank, ranges, total, slowest, big, rates, (wfirst, wcount), wtotal, obs))
     finally:
         dist.destroy_process_group()
 
@@ -59,8 +62,9 @@ def test_shards_combine_over_gloo(world, coracle):
     whole = coracle.unpack(coracle.synth_random(NBUF * 6144, O.SYNTH_SEED), O.MODE_F32).reshape(-1)
     want = coracle.checksum32(whole)
     wranges = {}
-    for rank, ranges, total, slowest, big, rates, wrange, wtotal in res:
+    for rank, ranges, total, slowest, big, rates, wrange, wtotal, obs in res:
         assert rates == [10.0 + 7.5 * r for r in range(world)]
+        assert obs == pytest.approx(rates)                                 # units / seconds of every rank, in rank order
         assert wtotal == want                                             # another sharding of the same recording: same checksum
         wranges[rank] = wrange
         assert total == want                                              # checksum of checksums
@@ -76,6 +80,47 @@ def test_shards_combine_over_gloo(world, coracle):
         assert wranges[r][0] == pos
         pos += wranges[r][1]
     assert pos == NBUF and [wranges[r][1] for r in range(world)] == sorted(wranges[r][1] for r in range(world))
+
+
+def test_refined_weights_converge_to_equal_finish_times(pg):
+    """The host-fed 8-GPU box of profiles/r2_h2d_matrix_8gpu.md as a model: ranks 4-7 read host memory at 35.6 each; ranks 0-3 share
+    a path worth 82 while ranks 4-7 are busy and 115 once they are done.  Weights measured with equal work over-rate the slow
+    group (its tail runs alone, faster), so the first weighted shards leave it finishing last; re-measuring on the weighted
+    shards, as bench.py --balance-passes does, settles on the steady-state rates and the shards finish together."""
+    total = 8 * 174_762
+
+    def simulate(counts):
+        left = list(map(float, counts))
+        t, done = 0.0, [0.0] * 8
+        while any(x > 1e-6 for x in left):
+            fast_busy = any(left[k] > 1e-6 for k in range(4, 8))
+            slow = [k for k in range(4) if left[k] > 1e-6]
+            rate = [0.0] * 8
+            for k in slow:
+                rate[k] = (82.0 if fast_busy else 115.0) / len(slow)
+            for k in range(4, 8):
+                rate[k] = 35.6 if left[k] > 1e-6 else 0.0
+            dt = min(left[k] / rate[k] for k in range(8) if rate[k] > 0)
+            t += dt
+            for k in range(8):
+                if rate[k] > 0:
+                    left[k] -= rate[k] * dt
+                    if left[k] <= 1e-6:
+                        left[k], done[k] = 0.0, t
+        return done
+
+    equal = [total // 8] * 8
+    weights = [c / t for c, t in zip(equal, simulate(equal))]                       # the first measurement: equal work, all at once
+    assert weights[0] == pytest.approx(23.4, abs=0.3)                               # flattered: the steady-state rate is 20.5
+    finish = []
+    for _ in range(4):
+        counts = [pg.shard_range_weighted(total, weights, s)[1] for s in range(8)]
+        times = simulate(counts)
+        finish.append(max(times))
+        weights = [c / t for c, t in zip(counts, times)]
+    ideal = total / (82.0 + 4 * 35.6)
+    assert finish[0] > 1.03 * ideal                                                 # cf. profiles/r2_bench_n8.json before the passes: 211 of ~224 GB/s
+    assert finish[-1] == pytest.approx(ideal, rel=2e-3) and finish == sorted(finish, reverse=True)
 
 
 def test_weighted_shard_planner(pg):
