@@ -236,8 +236,8 @@ int perseus_gpu_set_sink(perseus_gpu *h, perseus_gpu_sink sink, void *extra);
 
 /* A block of unpacked samples in (pinned) HOST memory: what the reference's callbacks have in hand when they fwrite
  * (perseustest.c:457,499), for applications whose consumer stays on the CPU.  The host sink is called once per slab, in
- * stream order, as soon as the slab's samples have arrived in host memory -- no flush needed -- on a thread of the CUDA
- * runtime, NOT under the handle's lock: it must not call perseus_gpu_* on this handle nor any CUDA function, and the
+ * stream order, as soon as the slab's samples have arrived in host memory -- no flush needed -- on the handle's delivery
+ * thread, NOT under the handle's lock: it must not call perseus_gpu_* on this handle (a flush waits for the sink), and the
  * pointers are valid only during the call.  Setting or clearing the sink flushes the stream first.  */
 typedef struct perseus_gpu_host_block {
 	uint64_t    first_sample;  /* index of the block's first complex sample since open */

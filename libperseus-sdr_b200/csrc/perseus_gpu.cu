@@ -55,8 +55,10 @@ struct Slab {
 	uint8_t *dev_f32 = nullptr;
 	uint8_t *host_out[2] = {nullptr, nullptr};   // pinned copies of the outputs (int32, float): only with a file / host sink
 	cudaEvent_t unpacked = nullptr;   // recorded behind the slab's kernel (and whatever the device sink queued): host delivery waits for it
-	cudaEvent_t done = nullptr;    // recorded after the slab's last operation
-	perseus_gpu *owner = nullptr;  // for deliver_slab, which only gets the slab
+	cudaEvent_t done = nullptr;    // recorded after the slab's last device operation (sleeping waits: back-pressure)
+	cudaEvent_t ready = nullptr;   // the same point, for the delivery thread (spinning wait: lowest latency)
+	uint64_t dlv_seq = 0;          // host delivery: this slab's place in the delivery order
+	bool to_deliver = false;       // host delivery was queued for this use of the slab
 	uint64_t first_sample = 0;
 	uint64_t nsamples = 0;
 	size_t file_bytes = 0;         // bytes deliver_slab writes to the file sink
@@ -133,13 +135,25 @@ struct perseus_gpu {
 	perseus_gpu_sink sink = nullptr;
 	void *sink_extra = nullptr;
 	// host delivery (file sink, host sink): written by the owner only while nothing is in flight (after a flush), read by
-	// deliver_slab on the CUDA runtime's callback thread
+	// deliver_slab on the handle's delivery thread
 	perseus_gpu_host_sink host_sink = nullptr;
 	void *host_sink_extra = nullptr;
 	FILE *fout = nullptr;
 	bool fout_is_stdout = false;                 // path "-" (perseustest.c:98,337): flushed, never closed
 	std::atomic<int> io_error{0};                // deliver_slab could not write the file: surfaced at the next retire / flush
 	std::atomic<uint64_t> host_blocks{0};        // blocks deliver_slab has handed over
+	// The delivery thread: takes slabs in submission order, waits (spinning) for each one's outputs to have reached pinned host
+	// memory, writes the file / calls the host sink.  A thread of the handle's own rather than cudaLaunchHostFunc because the
+	// runtime dispatches host functions 0.15 ms late (measured, profiles/r2_latency_probe.jsonl); this one is usually there
+	// before the data is.  dlv_mu guards the three counters below and pairs with the two condition variables.
+	std::thread dlv_thread;
+	std::mutex dlv_mu;
+	std::condition_variable dlv_cv;              // delivery thread: something was submitted / stop
+	std::condition_variable dlv_done_cv;         // owner: something was delivered
+	uint64_t dlv_submitted = 0, dlv_delivered = 0;
+	std::atomic<uint64_t> dlv_submitted_hint{0}; // = dlv_submitted, for the thread's short spin before it sleeps
+	int dlv_ring[kMaxSlabs]{};                   // slab index of delivery number n at [n % kMaxSlabs]
+	bool dlv_started = false, dlv_stop = false;
 	size_t direct_bytes = 0;                     // slabs up to this size are unpacked straight from the pinned slab (no H2D copy)
 	// latency watchdog (started with the first callback unless PERSEUS_GPU_OPT_NO_WATCHDOG)
 	std::thread watchdog;
@@ -326,7 +340,6 @@ int ensure_streaming(perseus_gpu *h)
 	const bool want_f32 = h->stream_fmt & (PERSEUS_GPU_OUT_FLOAT | PERSEUS_GPU_OUT_FLOAT_POW2);
 	for (int k = 0; k < h->nslabs; ++k) {
 		Slab &s = h->slabs[k];
-		s.owner = h;
 		// each guarded, so a call that failed half way (out of memory) can be retried without leaking
 		if (!s.host) CU(h, cudaHostAlloc(&s.host, h->slab_bytes, cudaHostAllocDefault));
 		if (!s.dev_in) CU(h, cudaMalloc(&s.dev_in, h->slab_bytes));
@@ -336,18 +349,17 @@ int ensure_streaming(perseus_gpu *h)
 		// thread (perseus-sdr.c:749-753) -- and must sleep, not spin
 		if (!s.done) CU(h, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming | cudaEventBlockingSync));
 		if (!s.unpacked) CU(h, cudaEventCreateWithFlags(&s.unpacked, cudaEventDisableTiming));
+		if (!s.ready) CU(h, cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
 	}
 	h->streaming_ready = true;
 	return 0;
 }
 
-// Host delivery of one slab, queued on s_dlv behind the slab's outputs reaching pinned host memory: runs on the CUDA runtime's
-// callback thread, slabs strictly in stream order.  Does what the reference's callbacks do with their samples -- fwrite them
-// (perseustest.c:457,499) -- and/or hands them to the application's host sink.  No CUDA call is allowed here.
-void CUDART_CB deliver_slab(void *p)
+// Host delivery of one slab, once its outputs have reached pinned host memory; slabs strictly in submission order.  Does what the
+// reference's callbacks do with their samples -- fwrite them (perseustest.c:457,499) -- and/or hands them to the application's
+// host sink.
+void deliver_slab(perseus_gpu *h, Slab *s)
 {
-	Slab *s = static_cast<Slab *>(p);
-	perseus_gpu *h = s->owner;
 	if (h->fout && s->file_bytes && !h->io_error.load(std::memory_order_relaxed)) {
 		if (fwrite(s->host_out[s->file_fmt], 1, s->file_bytes, h->fout) != s->file_bytes) h->io_error.store(1, std::memory_order_relaxed);
 	}
@@ -359,18 +371,89 @@ void CUDART_CB deliver_slab(void *p)
 	h->host_blocks.fetch_add(1, std::memory_order_relaxed);
 }
 
-// Retires the `count` oldest slabs in ring order: waits until each one's last operation (kernel, or host delivery) is done.
+void delivery_main(perseus_gpu *h)
+{
+	cudaSetDevice(h->device);
+	std::unique_lock<std::mutex> lk(h->dlv_mu);
+	for (;;) {
+		if (h->dlv_delivered == h->dlv_submitted) {
+			if (h->dlv_stop) return;
+			// transfers of a stream usually follow each other closely: look for the next slab a little while before sleeping
+			const uint64_t seen = h->dlv_submitted;
+			lk.unlock();
+			const auto until = std::chrono::steady_clock::now() + std::chrono::microseconds(100);
+			while (h->dlv_submitted_hint.load(std::memory_order_acquire) == seen && std::chrono::steady_clock::now() < until) sched_yield();
+			lk.lock();
+			h->dlv_cv.wait(lk, [&] { return h->dlv_stop || h->dlv_delivered != h->dlv_submitted; });
+			continue;
+		}
+		Slab *s = &h->slabs[h->dlv_ring[h->dlv_delivered % kMaxSlabs]];
+		lk.unlock();
+		// a spinning wait (the event is not BlockingSync): the thread is on the data as soon as the copy engine / the kernel is done
+		if (cudaEventSynchronize(s->ready) != cudaSuccess) {
+			cudaGetLastError();
+			h->io_error.store(2, std::memory_order_relaxed);   // the owner meets the CUDA error itself at its next call; do not deliver garbage
+		} else {
+			deliver_slab(h, s);
+		}
+		lk.lock();
+		h->dlv_delivered++;
+		h->dlv_done_cv.notify_all();
+	}
+}
+
+// Hands the slab just submitted to the delivery thread (started with the first one).  Owner only.
+int queue_delivery(perseus_gpu *h, Slab &s, int index)
+{
+	if (!h->dlv_started) {
+		h->dlv_started = true;
+		try {
+			h->dlv_thread = std::thread(delivery_main, h);
+		} catch (...) {
+			h->dlv_started = false;
+			return fail(PERSEUS_GPU_NOMEM, "cannot start the delivery thread");
+		}
+	}
+	{
+		std::lock_guard<std::mutex> lk(h->dlv_mu);
+		s.dlv_seq = h->dlv_submitted;
+		h->dlv_ring[h->dlv_submitted % kMaxSlabs] = index;
+		h->dlv_submitted++;
+		h->dlv_submitted_hint.store(h->dlv_submitted, std::memory_order_release);
+	}
+	h->dlv_cv.notify_one();
+	s.to_deliver = true;
+	return 0;
+}
+
+void stop_delivery(perseus_gpu *h)   // after a flush: nothing is queued
+{
+	{
+		std::lock_guard<std::mutex> lk(h->dlv_mu);
+		h->dlv_stop = true;
+	}
+	h->dlv_cv.notify_all();
+	if (h->dlv_thread.joinable()) h->dlv_thread.join();
+}
+
+// Retires the `count` oldest slabs in ring order: waits until each one's device work is done and, with a file / host sink,
+// until it has been delivered.  Both waits sleep (this may be the reference's SCHED_FIFO thread in back-pressure).
 int retire_slabs(perseus_gpu *h, int count)
 {
 	for (int n = 0; n < count; ++n) {
 		Slab &s = h->slabs[h->next_to_write];
 		if (s.busy) {
 			CU(h, cudaEventSynchronize(s.done));
+			if (s.to_deliver) {
+				std::unique_lock<std::mutex> lk(h->dlv_mu);
+				h->dlv_done_cv.wait(lk, [&] { return h->dlv_delivered > s.dlv_seq; });
+				s.to_deliver = false;
+			}
 			s.busy = false;
 		}
 		h->next_to_write = (h->next_to_write + 1) % h->nslabs;
 	}
-	if (h->io_error.exchange(0, std::memory_order_relaxed)) return fail(PERSEUS_GPU_IOERROR, "short write to stream file");
+	if (h->io_error.exchange(0, std::memory_order_relaxed) == 1) return fail(PERSEUS_GPU_IOERROR, "short write to stream file");
 	return 0;
 }
 
@@ -415,19 +498,23 @@ int submit_slab(perseus_gpu *h)
 		h->sink(&b, h->sink_extra);
 	}
 	if (host_delivery) {
-		// every slab's copy-out and hand-over go through the ONE delivery stream, so blocks reach the host in stream order
-		// whichever of the handle's streams unpacked them
-		CU(h, cudaEventRecord(s.unpacked, st));
-		CU(h, cudaStreamWaitEvent(h->s_dlv, s.unpacked, 0));
-		for (int k = 0; k < 2; ++k) {
-			if (!produced[k]) continue;
-			if (!direct_out) CU(h, cudaMemcpyAsync(s.host_out[k], k ? s.dev_f32 : s.dev_i32, ns * 8, cudaMemcpyDeviceToHost, h->s_dlv));
-			h->stats.d2h_bytes += ns * 8;
+		// copy-outs go through the ONE delivery stream (the copy engine takes them in order anyway); the delivery thread takes the
+		// slabs in submission order, so blocks reach the host in stream order whichever of the handle's streams unpacked them
+		cudaStream_t last = st;
+		if (!direct_out) {
+			CU(h, cudaEventRecord(s.unpacked, st));
+			CU(h, cudaStreamWaitEvent(h->s_dlv, s.unpacked, 0));
+			for (int k = 0; k < 2; ++k)
+				if (produced[k]) CU(h, cudaMemcpyAsync(s.host_out[k], k ? s.dev_f32 : s.dev_i32, ns * 8, cudaMemcpyDeviceToHost, h->s_dlv));
+			last = h->s_dlv;
 		}
+		h->stats.d2h_bytes += ns * 8 * ((produced[0] ? 1 : 0) + (produced[1] ? 1 : 0));
 		s.file_fmt = produced[0] ? 0 : 1;   // a stream file holds one format (perseus_gpu_stream_to_file checks)
 		s.file_bytes = h->fout ? ns * 8 : 0;
-		CU(h, cudaLaunchHostFunc(h->s_dlv, deliver_slab, &s));
-		CU(h, cudaEventRecord(s.done, h->s_dlv));
+		CU(h, cudaEventRecord(s.ready, last));
+		CU(h, cudaEventRecord(s.done, last));
+		rc = queue_delivery(h, s, h->cur);
+		if (rc) return rc;
 	} else {
 		CU(h, cudaEventRecord(s.done, st));
 	}
@@ -712,8 +799,8 @@ int flush_locked(perseus_gpu *h)
 		// costs ~0.2 ms of wake-up latency.  flush is called by the application and wants the result now: spin on the
 		// streams first, after which every slab event is already complete and draining never sleeps.
 		for (int s = 0; s < h->nstreams; ++s) cudaStreamSynchronize(h->streams[s]);
-		cudaStreamSynchronize(h->s_dlv);   // every block has been written / handed to the host sink
-		rc = retire_slabs(h, h->nslabs);
+		cudaStreamSynchronize(h->s_dlv);
+		rc = retire_slabs(h, h->nslabs);   // ... and every block has been written / handed to the host sink
 		if (rc) latch(h, rc);
 		h->next_to_write = h->cur;       // nothing in flight: the next slab submitted is the oldest
 		if (h->fout) fflush(h->fout);
@@ -965,6 +1052,7 @@ int perseus_gpu_close(perseus_gpu *h)
 		Entry en(h, false);
 		if (cudaSetDevice(h->device) == cudaSuccess) {
 			rc = flush_locked(h);
+			stop_delivery(h);
 			for (int k = 0; k < kMaxSlabs; ++k) {
 				Slab &s = h->slabs[k];
 				if (s.host) cudaFreeHost(s.host);
@@ -975,6 +1063,7 @@ int perseus_gpu_close(perseus_gpu *h)
 				if (s.dev_f32) cudaFree(s.dev_f32);
 				if (s.done) cudaEventDestroy(s.done);
 				if (s.unpacked) cudaEventDestroy(s.unpacked);
+				if (s.ready) cudaEventDestroy(s.ready);
 			}
 			for (int s = 0; s < kMaxStageSlots; ++s) {
 				if (h->stage_in[s]) cudaFree(h->stage_in[s]);
@@ -1001,6 +1090,7 @@ int perseus_gpu_close(perseus_gpu *h)
 			if (h->s_dlv) cudaStreamDestroy(h->s_dlv);
 			cudaGetLastError();
 		}
+		stop_delivery(h);   // also when the device could not be bound above: the thread must be gone before the handle is
 		if (h->fout) {
 			if ((h->fout_is_stdout ? fflush(h->fout) : fclose(h->fout)) != 0 && !rc) rc = fail(PERSEUS_GPU_IOERROR, "closing stream file failed");
 		}

@@ -1003,10 +1003,11 @@ def test_cfg1_95k_paced_float_file_equals_reference(pg, coracle, tmp_path):
         v.close()
         n = st["delivered"]
         assert 40 <= n <= 95 and 80 < st["ksamples_per_s"] < 110, st       # 0.6 s (more if the box is busy) at 92.8 transfers/s
-        # a transfer every 10.8 ms: each one goes out on arrival (eager_gap_us), long before any flush or age bound.  Fewer slabs
-        # than transfers only where the receiver delivered back to back to catch up with its schedule (after the first callback,
-        # which allocates the slabs, or on a busy box): those share a slab, as they should.
-        assert n // 2 <= mid["slabs"] <= n and mid["callbacks"] == n and mid["samples"] >= (n - 8) * 1024, mid
+        # a transfer every 10.8 ms goes out on arrival (eager_gap_us), long before any flush or age bound; transfers the receiver's
+        # pacing thread delivers back to back to catch up with its schedule (after the first callback, which allocates the slabs;
+        # whenever the box oversleeps) share a slab, as they should -- how many do is the box's business, so only the age bound's
+        # floor is asserted here (test_slow_stream_goes_out_transfer_by_transfer... pins the eager path with its own pacing)
+        assert 8 <= mid["slabs"] <= n and mid["callbacks"] == n and mid["samples"] >= (n - 8) * 1024, mid
     wire = coracle.synth_random(n * 6144, seed=95)
     assert path.read_bytes() == O.Ref().unpack(wire, O.MODE_F32, chunk=6144).tobytes()
 
