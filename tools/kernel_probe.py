@@ -26,6 +26,8 @@ def main():
     ap.add_argument("--buffers", type=int, default=NBUF)
     ap.add_argument("--in-offset", type=int, default=0, help="misalign the wire pointer by this many bytes (exercises the direct kernel)")
     ap.add_argument("--sweep", action="store_true")
+    ap.add_argument("--out-skew", type=int, default=0, help="move the float output this many bytes (multiple of 16) further from the int32 output: "
+                    "does the distance between the two write streams matter to the DRAM?")
     ap.add_argument("--fine", action="store_true", help="few CTAs/SM, all tile sizes, every ring depth, 3 repeats each")
     for k in ("variant", "tile", "stages", "ctas", "store"):
         ap.add_argument(f"--{k}", type=int, default=0)
@@ -39,8 +41,8 @@ def main():
     with pg.PerseusGpu(device=0) as h:
         n = a.buffers * BUF
         ns = n // 6
-        d_in0, d_i, d_f = h.dev_alloc(n + 64), h.dev_alloc(ns * 8), h.dev_alloc(ns * 8)
-        d_in = d_in0 + a.in_offset
+        d_in0, d_i, d_f0 = h.dev_alloc(n + 64), h.dev_alloc(ns * 8), h.dev_alloc(ns * 8 + a.out_skew)
+        d_in, d_f = d_in0 + a.in_offset, d_f0 + a.out_skew
         h.generate(d_in, n)
         fmts = {"i32": (pg.OUT_INT32, d_i, None, 14), "f32": (pg.OUT_FLOAT, None, d_f, 14), "pow2": (pg.OUT_FLOAT_POW2, None, d_f, 14),
                 "both": (pg.OUT_INT32 | pg.OUT_FLOAT, d_i, d_f, 22)}
@@ -64,7 +66,7 @@ def main():
             h.sync()
             ms = h.event_elapsed_ms(0, 1) / a.reps
             gbs = bps * ns / (ms * 1e-3) / 1e9
-            return {"fmt": fmt, **h.get_tuning(), "ms": round(ms, 4), "gbs": round(gbs, 1), "frac": round(gbs / peak, 4),
+            return {"fmt": fmt, **h.get_tuning(), "out_skew": a.out_skew, "f32_minus_i32": d_f - d_i, "ms": round(ms, 4), "gbs": round(gbs, 1), "frac": round(gbs / peak, 4),
                     "gsamples_s": round(ns / ms / 1e6, 1)}
 
         if a.fine:
@@ -87,7 +89,7 @@ def main():
                     r = run(fmt, variant=pg.VARIANT_STREAM, tile_bytes=tile, stages=stages, ctas_per_sm=ctas, store_mode=store)
                     if r:
                         print(json.dumps(r), flush=True)
-        for p in (d_in0, d_i, d_f):
+        for p in (d_in0, d_i, d_f0):
             h.dev_free(p)
 
 
