@@ -768,22 +768,32 @@ int stream_push(perseus_gpu *h, const uint8_t *buf, size_t nbytes)
 	return rc < 0 ? rc : 0;
 }
 
-int sync_locked(perseus_gpu *h)
+// Waits for the streams of the streaming path (the slab streams and the delivery stream) and / or of the bulk host-pointer
+// pipeline (streams[0] runs its kernels, s_in / s_out its copies); CUDA errors are latched.
+void wait_streams(perseus_gpu *h, bool streaming, bool bulk, bool launch_stream_done = false)
 {
 	cudaStream_t all[kMaxStreams + 3];
 	int n = 0;
-	for (int s = 0; s < h->nstreams; ++s) all[n++] = h->streams[s];
-	all[n++] = h->s_in;
-	all[n++] = h->s_out;
-	all[n++] = h->s_dlv;
+	for (int s = 0; s < h->nstreams; ++s)
+		if (streaming || (bulk && s == 0 && !launch_stream_done)) all[n++] = h->streams[s];
+	if (bulk) {
+		all[n++] = h->s_in;
+		all[n++] = h->s_out;
+	}
+	if (streaming) all[n++] = h->s_dlv;
 	for (int s = 0; s < n; ++s) {
 		if (!all[s]) continue;
 		cudaError_t e = cudaStreamSynchronize(all[s]);
 		if (e != cudaSuccess) {
-			fail(PERSEUS_GPU_CUDAERR, "stream %d: %s", s, cudaGetErrorString(e));
+			fail(PERSEUS_GPU_CUDAERR, "stream synchronisation: %s", cudaGetErrorString(e));
 			latch(h, PERSEUS_GPU_CUDAERR);
 		}
 	}
+}
+
+int sync_locked(perseus_gpu *h)
+{
+	wait_streams(h, true, true);
 	return surface_latched(h);
 }
 
@@ -797,13 +807,14 @@ int flush_locked(perseus_gpu *h)
 		}
 		// The slab events are BlockingSync (a back-pressure wait must sleep, see ensure_streaming), and a sleeping wait
 		// costs ~0.2 ms of wake-up latency.  flush is called by the application and wants the result now: spin on the
-		// streams first, after which every slab event is already complete and draining never sleeps.
-		for (int s = 0; s < h->nstreams; ++s) cudaStreamSynchronize(h->streams[s]);
-		cudaStreamSynchronize(h->s_dlv);
+		// streams first, after which every slab event is already complete and retiring never sleeps on the device.
+		wait_streams(h, true, false);
 		rc = retire_slabs(h, h->nslabs);   // ... and every block has been written / handed to the host sink
 		if (rc) latch(h, rc);
 		h->next_to_write = h->cur;       // nothing in flight: the next slab submitted is the oldest
 		if (h->fout) fflush(h->fout);
+		wait_streams(h, false, true, true);   // whatever the bulk pipeline still has queued (streams[0] was waited for above)
+		return surface_latched(h);
 	}
 	return sync_locked(h);
 }
