@@ -28,6 +28,14 @@ def shard_bin(tmp_path_factory):
     return out
 
 
+@pytest.fixture(scope="module")
+def hostsink_bin(tmp_path_factory):
+    out = tmp_path_factory.mktemp("bin") / "perseus_gpu_hostsink"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", str(ROOT / "include"),
+                    str(ROOT / "examples" / "perseus_gpu_hostsink.c"), "-L", str(LIBDIR), "-lperseus_gpu", "-o", str(out)], check=True)
+    return out
+
+
 def run(binary, *args):
     env = dict(os.environ, LD_LIBRARY_PATH=f"{LIBDIR}:{os.environ.get('LD_LIBRARY_PATH', '')}")
     return subprocess.run([str(binary), *args], capture_output=True, text=True, env=env, timeout=120)
@@ -62,6 +70,27 @@ def test_example_streams_to_standard_output_like_perseustest_dash(replay_bin, co
     assert r.returncode == 0, r.stderr
     assert r.stdout == coracle.unpack(coracle.synth_random(77 * 6144), O.MODE_F32).tobytes()
     assert b"Bye" in r.stderr and not os.path.exists("-")
+
+
+def test_hostsink_example_builds_as_c99(hostsink_bin):
+    r = run(hostsink_bin, "-h")
+    assert r.returncode == 0 and "perseus_gpu_hostsink" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("args,n", [(("-N", "333"), 333), (("-s", "2000000", "-t", "1"), None)])
+def test_hostsink_example_meters_exactly_what_the_reference_callbacks_would_hold(hostsink_bin, coracle, args, n):
+    """examples/perseus_gpu_hostsink.c: a CPU consumer (level meter) fed by the host sink -- as fast as possible and paced like a
+    2 MS/s receiver.  Its exact integer totals must equal those of the oracle's int32 unpack of the same wire stream."""
+    r = run(hostsink_bin, *args)
+    assert r.returncode == 0, r.stderr
+    got = dict(zip(r.stdout.split()[0::2], map(int, r.stdout.split()[1::2])))
+    if n is None:
+        n = got["samples"] // 1024
+        assert 1500 <= n <= 3000, got                      # 1 s (more on a busy box) at 1953 transfers/s
+    want = coracle.unpack(coracle.synth_random(n * 6144), O.MODE_I32).view(np.int32).reshape(-1, 2).astype(np.int64)
+    assert got["samples"] == n * 1024 and got["out_of_order"] == 0 and 1 <= got["blocks"] <= n
+    assert (got["sum_i"], got["sum_q"], got["peak"]) == (int(want[:, 0].sum()), int(want[:, 1].sum()), int(np.abs(want).max()))
 
 
 @pytest.mark.gpu
