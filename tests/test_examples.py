@@ -72,9 +72,13 @@ def test_example_streams_to_standard_output_like_perseustest_dash(replay_bin, co
     assert b"Bye" in r.stderr and not os.path.exists("-")
 
 
-def test_hostsink_example_builds_as_c99(hostsink_bin):
+def test_hostsink_example_builds_as_c99_and_fails_loudly_without_a_gpu(hostsink_bin):
+    import torch
     r = run(hostsink_bin, "-h")
     assert r.returncode == 0 and "perseus_gpu_hostsink" in r.stderr
+    if not torch.cuda.is_available():
+        r = run(hostsink_bin, "-N", "4")
+        assert r.returncode == 1 and "perseus_gpu_open" in r.stderr           # no CPU fallback
 
 
 @pytest.mark.gpu
