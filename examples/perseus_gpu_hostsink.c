@@ -72,7 +72,7 @@ int main(int argc, char **argv)
 	gcfg.device = device;
 	gcfg.stream_flags = PERSEUS_GPU_OUT_INT32;
 	gcfg.slab_bytes = 1u << 20;
-	if (perseus_gpu_open(&gpu, &gcfg) < 0 || perseus_gpu_set_host_sink(gpu, level_meter, &m) < 0) {
+	if (perseus_gpu_open(&gpu, &gcfg) < 0 || perseus_gpu_set_host_sink(gpu, level_meter, &m) < 0 || perseus_gpu_prepare(gpu) < 0) {
 		fprintf(stderr, "perseus_gpu_open: %s\n", perseus_gpu_errorstr());
 		return 1;
 	}

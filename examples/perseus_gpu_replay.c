@@ -74,6 +74,12 @@ int main(int argc, char **argv)
 		return 1;
 	}
 
+	if (perseus_gpu_prepare(gpu) < 0) {   /* allocate and warm up now, not inside the first callback on the receiver's thread */
+		fprintf(stderr, "perseus_gpu_prepare: %s\n", perseus_gpu_errorstr());
+		perseus_gpu_close(gpu);
+		return 1;
+	}
+
 	perseus_vrx *rx = NULL;
 	perseus_vrx_config vcfg;
 	memset(&vcfg, 0, sizeof vcfg);

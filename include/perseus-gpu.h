@@ -209,6 +209,13 @@ int     perseus_gpu_plan_destroy(perseus_gpu *h, perseus_gpu_plan *plan);
  * in perseus_gpu_stats.dropped_callbacks / dropped_bytes until flush/sync/close reports it. */
 int perseus_gpu_input_callback(void *buf, int buf_size, void *extra);
 
+/* Optional: does now what the streaming path would otherwise do inside its FIRST callback -- pinned slabs, device buffers,
+ * events, the pinned output copies when a file / host sink is set, the first (code-loading) kernel launch, the watchdog: tens of
+ * milliseconds -- so that the first transfers of a real receiver are not held up on libperseus-sdr's poll thread (its ring of 8
+ * transfers covers 4 ms at 2 MS/s, perseus-sdr.c:683).  Call after perseus_gpu_set_host_sink / perseus_gpu_stream_to_file and
+ * before perseus_start_async_input. */
+int perseus_gpu_prepare(perseus_gpu *h);
+
 /* Latency bound without a following callback.  A partly filled slab is submitted once its oldest
  * transfer has waited cfg.max_latency_us.  That is checked at every callback and, because a stream
  * can stall (USB error, the last transfers before perseus_stop_async_input), also by a small

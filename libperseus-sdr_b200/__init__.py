@@ -136,6 +136,7 @@ def lib() -> C.CDLL:
         "perseus_gpu_stream_to_file": (ci, [vp, C.c_char_p]),
         "perseus_gpu_flush": (ci, [vp]),
         "perseus_gpu_poll": (ci, [vp]),
+        "perseus_gpu_prepare": (ci, [vp]),
         "perseus_gpu_get_stats": (ci, [vp, P(Stats)]),
         "perseus_gpu_autotune": (ci, [vp, P(C.c_double), P(C.c_double)]),
         "perseus_gpu_get_geometry": (ci, [vp, C.c_uint, P(ci), P(ci), P(ci)]),
@@ -311,6 +312,10 @@ class PerseusGpu:
 
     def flush(self) -> None:
         check(self.L.perseus_gpu_flush(self.h))
+
+    def prepare(self) -> None:
+        """Allocates and warms up the streaming path now instead of inside the first callback."""
+        check(self.L.perseus_gpu_prepare(self.h))
 
     def poll(self) -> int:
         """Submits the partial slab if it is over age; returns how many slabs that submitted (0 or 1)."""

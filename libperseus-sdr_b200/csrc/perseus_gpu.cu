@@ -402,18 +402,24 @@ void delivery_main(perseus_gpu *h)
 	}
 }
 
-// Hands the slab just submitted to the delivery thread (started with the first one).  Owner only.
+int start_delivery(perseus_gpu *h)   // owner only
+{
+	if (h->dlv_started) return 0;
+	h->dlv_started = true;
+	try {
+		h->dlv_thread = std::thread(delivery_main, h);
+	} catch (...) {
+		h->dlv_started = false;
+		return fail(PERSEUS_GPU_NOMEM, "cannot start the delivery thread");
+	}
+	return 0;
+}
+
+// Hands the slab just submitted to the delivery thread (started with the first one, or by perseus_gpu_prepare).  Owner only.
 int queue_delivery(perseus_gpu *h, Slab &s, int index)
 {
-	if (!h->dlv_started) {
-		h->dlv_started = true;
-		try {
-			h->dlv_thread = std::thread(delivery_main, h);
-		} catch (...) {
-			h->dlv_started = false;
-			return fail(PERSEUS_GPU_NOMEM, "cannot start the delivery thread");
-		}
-	}
+	int rc = start_delivery(h);
+	if (rc) return rc;
 	{
 		std::lock_guard<std::mutex> lk(h->dlv_mu);
 		s.dlv_seq = h->dlv_submitted;
@@ -1323,6 +1329,32 @@ int perseus_gpu_input_callback(void *buf, int buf_size, void *extra)
 	if (h->others_want.load(std::memory_order_relaxed) != 0) _mm_sfence();
 #endif
 	h->cb_active.store(0, std::memory_order_release);
+	return 0;
+}
+
+int perseus_gpu_prepare(perseus_gpu *h)
+{
+	Entry en(h);
+	if (en.rc) return en.rc;
+	int rc = ensure_streaming(h);
+	if (rc) return rc;
+	if (h->fout || h->host_sink) {
+		const bool produced[2] = {(h->stream_fmt & PERSEUS_GPU_OUT_INT32) != 0,
+		                          (h->stream_fmt & (PERSEUS_GPU_OUT_FLOAT | PERSEUS_GPU_OUT_FLOAT_POW2)) != 0};
+		for (int k = 0; k < h->nslabs; ++k)
+			for (int f = 0; f < 2; ++f)
+				if (produced[f] && !h->slabs[k].host_out[f]) CU(h, cudaHostAlloc(&h->slabs[k].host_out[f], h->slab_bytes / 6 * 8, cudaHostAllocDefault));
+		if ((rc = start_delivery(h))) return rc;
+	}
+	// the first launch of a kernel loads its code: do that here, on two samples of slab 0 (nothing is delivered or counted)
+	Slab &s = h->slabs[0];
+	memset(s.host, 0, 12);
+	int n = 0;
+	cudaError_t e = pg::launch_unpack(s.host, 12, s.dev_i32, s.dev_f32, h->stream_fmt, h->tune, h->sm_count, h->streams[0], &n);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(h->streams[0]);
+	if (e != cudaSuccess) return fail(PERSEUS_GPU_CUDAERR, "warm-up launch failed: %s", cudaGetErrorString(e));
+	h->stats.kernel_launches += (uint64_t)n;
+	start_watchdog(h);
 	return 0;
 }
 

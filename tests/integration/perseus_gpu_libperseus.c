@@ -67,6 +67,7 @@ int main(int argc, char **argv)
 	cfg.stream_flags = use_float ? PERSEUS_GPU_OUT_FLOAT : PERSEUS_GPU_OUT_INT32;
 	if (perseus_gpu_open(&gpu, &cfg) < 0) { fprintf(stderr, "perseus-gpu: %s\n", perseus_gpu_errorstr()); return 1; }
 	if (perseus_gpu_stream_to_file(gpu, fname) < 0) { fprintf(stderr, "perseus-gpu: %s\n", perseus_gpu_errorstr()); return 1; }
+	if (perseus_gpu_prepare(gpu) < 0) { fprintf(stderr, "perseus-gpu: %s\n", perseus_gpu_errorstr()); return 1; }   /* not on the poll thread */
 
 	/* was: perseus_start_async_input(descr, nb*bs, user_data_callback_c_u, fout) */
 	if (perseus_start_async_input(descr, (uint32_t)(nb * bs), perseus_gpu_input_callback, gpu) < 0) {

@@ -212,6 +212,7 @@ static void scenario_host_delivery()
 		Collected col;
 		CHECK(perseus_gpu_set_host_sink(h, host_sink, &col) == 0);
 		CHECK(perseus_gpu_stream_to_file(h, "/tmp/perseus_sanitize_e.bin") == 0);
+		CHECK(perseus_gpu_prepare(h) == 0 && perseus_gpu_prepare(h) == 0);   // allocations, warm-up launch, helper threads: now, not in the first callback
 		perseus_vrx_config vc;
 		memset(&vc, 0, sizeof vc);
 		vc.struct_size = sizeof vc;

@@ -906,6 +906,29 @@ def test_streaming_latency_bound_submits_partial_slabs(pg, coracle):
         assert blocks == [3 * 1024]
 
 
+def test_prepare_takes_the_allocations_out_of_the_first_callback(pg, coracle):
+    """perseus_gpu_prepare: the first callback of a real receiver must not stall libperseus-sdr's poll thread for the tens of
+    milliseconds pinned allocations and the first kernel launch take (8 transfers of ring cover 4 ms at 2 MS/s)."""
+    import time
+    wire = coracle.synth_random(6144 * 3, seed=52).reshape(3, 6144)
+    got = []
+    with pg.PerseusGpu(device=0, stream_flags=pg.OUT_INT32 | pg.OUT_FLOAT) as h:         # default slabs: 4 x 8 MiB pinned + device buffers
+        h.set_host_sink(collect_host_blocks(got))
+        h.prepare()
+        assert h.stats()["samples"] == 0 and h.stats()["slabs"] == 0                     # the warm-up launch delivers and counts nothing
+        times = []
+        for k in range(3):
+            t0 = time.perf_counter()
+            h.input_callback(wire[k].ctypes.data, 6144)
+            times.append(time.perf_counter() - t0)
+            time.sleep(0.001)
+        h.flush()
+        assert max(times) < 0.003, times                                                  # typically 5-20 us each; unprepared: tens of ms
+        assert np.array_equal(np.concatenate([g[2] for g in got]), coracle.unpack(wire.reshape(-1), O.MODE_I32).view(np.uint32).reshape(-1))
+        assert np.array_equal(np.concatenate([g[3] for g in got]), coracle.unpack(wire.reshape(-1), O.MODE_F32).view(np.uint32).reshape(-1))
+        h.prepare()                                                                        # idempotent
+
+
 def test_slow_stream_goes_out_transfer_by_transfer_fast_stream_fills_slabs(pg, coracle):
     """perseus_gpu_config.eager_gap_us: a transfer that arrives a while after the previous one (a real receiver: one every
     0.5-10.8 ms) is submitted at once, with the handle's DEFAULT 8 MiB slabs and 50 ms bound; the same handle fed back to back
