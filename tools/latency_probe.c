@@ -123,8 +123,40 @@ static int run_paced(unsigned period_us)
 	return perseus_gpu_close(h) < 0;
 }
 
+/* How long the FIRST callback of a handle takes -- on a real receiver that is time spent on libperseus-sdr's poll thread while
+ * the ring of 8 transfers fills up -- with and without perseus_gpu_prepare(); default handle, host sink set. */
+static int run_first(int prepare)
+{
+	perseus_gpu_config cfg;
+	memset(&cfg, 0, sizeof cfg);
+	cfg.struct_size = sizeof cfg;
+	cfg.stream_flags = PERSEUS_GPU_OUT_FLOAT;
+	perseus_gpu *h = NULL;
+	if (perseus_gpu_open(&h, &cfg) < 0 || perseus_gpu_set_host_sink(h, host_sink, NULL) < 0) { fprintf(stderr, "open: %s\n", perseus_gpu_errorstr()); return 1; }
+	static unsigned char xfer[XFER];
+	perseus_synth_fill(xfer, XFER, PERSEUS_SYNTH_RANDOM, PERSEUS_SYNTH_SEED, 0);
+	double tp = 0.0;
+	if (prepare) {
+		const double t = now_us();
+		if (perseus_gpu_prepare(h) < 0) { fprintf(stderr, "prepare: %s\n", perseus_gpu_errorstr()); return 1; }
+		tp = now_us() - t;
+	}
+	double t[3];
+	for (int k = 0; k < 3; ++k) {
+		const double t0 = now_us();
+		perseus_gpu_input_callback(xfer, XFER, h);
+		t[k] = now_us() - t0;
+		const double until = now_us() + 512;
+		while (now_us() < until) { }
+	}
+	printf("{\"mode\": \"first_callbacks\", \"prepared\": %s, \"prepare_us\": %.0f, \"callback_us\": [%.1f, %.1f, %.1f]}\n", prepare ? "true" : "false", tp,
+	       t[0], t[1], t[2]);
+	return perseus_gpu_close(h) < 0;
+}
+
 int main(int argc, char **argv)
 {
+	if (argc > 1 && !strcmp(argv[1], "first")) return run_first(0) || run_first(1) || run_first(0) || run_first(1);
 	if (argc > 1 && !strcmp(argv[1], "paced")) return run_paced(512) || run_paced(10779);   /* 2 MS/s and 95 kS/s transfer periods */
 	static const size_t slabs[] = {XFER, 2 * XFER, 8 * XFER, 32 * XFER, 128 * XFER, 512 * XFER, 1365 * XFER};
 	for (int host_mode = 0; host_mode < 2; ++host_mode)
