@@ -1,0 +1,109 @@
+"""TEST INFRASTRUCTURE ONLY: run with PERSEUS_GPU_LIB pointing at the host-simulation build (tests/hostsim/build.sh).
+Randomised streaming scenarios through the product's host layer -- slab ring, both slab routes, eager submission, age bound and
+watchdog, device sink, host sink (delivery thread), file sink, interleaved flush / poll / stats calls, every legal transfer size
+-- with the sample arithmetic done by the CPU oracle behind the CUDA stand-in.  What is under test is the plumbing: every consumer
+must see exactly the unpack of the concatenated transfers, in order, whatever the timing does.
+
+    PERSEUS_GPU_LIB=/tmp/hostsim.so python tests/hostsim/fuzz_streaming.py <seed> <scenarios>
+"""
+import ctypes as C
+import os
+import random
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+import __graft_entry__ as G  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+pg = G.load_package()
+co = O.COracle()
+assert "hostsim" in str(pg.LIB_PATH), "this script drives the host-simulation build only"
+
+
+def scenario(rng, idx, tmp):
+    fmt = rng.choice([pg.OUT_INT32, pg.OUT_FLOAT, pg.OUT_FLOAT_POW2, pg.OUT_INT32 | pg.OUT_FLOAT])
+    one_format = fmt in (pg.OUT_INT32, pg.OUT_FLOAT, pg.OUT_FLOAT_POW2)
+    cfg = dict(stream_flags=fmt, slab_bytes=48 * rng.randint(3, 700), nslabs=rng.randint(2, 5), nstreams=rng.randint(1, 3),
+               direct_bytes=rng.choice([0, pg.DIRECT_NEVER, 48 * 40]), eager_gap_us=rng.choice([0, pg.EAGER_NEVER, 30]),
+               max_latency_us=rng.choice([0, 0xFFFFFFFF, 300]), options=rng.choice([0, pg.OPT_NO_WATCHDOG]))
+    use_dev, use_host, use_file = rng.random() < 0.5, rng.random() < 0.7, one_format and rng.random() < 0.5
+    sizes = [rng.choice([6144, 12288] + [510 * k for k in (1, 2, 7, 32)]) for _ in range(rng.randint(1, 60))]
+    wire = co.synth_random(sum(sizes), seed=1000 + idx)
+    dev, host = [], []
+    path = os.path.join(tmp, f"s{idx}.bin")
+    with pg.PerseusGpu(device=0, **cfg) as h:
+        def dev_sink(blk, extra):
+            b = blk.contents
+            h.sync()                                    # re-enters the handle from its own sink (allowed for the device sink)
+            dev.append((b.first_sample, h.to_host(b.dev_i32 or b.dev_f32, b.nsamples * 8, np.uint32)))
+
+        def host_sink(blk, extra):
+            b = blk.contents
+            host.append((b.first_sample, np.ctypeslib.as_array((C.c_uint32 * (2 * b.nsamples)).from_address(b.i32 or b.f32)).copy(),
+                         bool(b.i32), bool(b.f32)))
+
+        if use_dev:
+            h.set_sink(dev_sink)
+        if use_host:
+            h.set_host_sink(host_sink)
+        if use_file:
+            h.stream_to_file(path)
+        if rng.random() < 0.3:
+            h.prepare()
+        off = 0
+        for n in sizes:
+            h.input_callback(wire[off:].ctypes.data, n)
+            off += n
+            r = rng.random()
+            if r < 0.08:
+                h.flush()
+            elif r < 0.16:
+                h.poll()
+            elif r < 0.24:
+                h.stats()
+            elif r < 0.34:
+                time.sleep(rng.choice([0.0, 0.0001, 0.0006]))
+        if rng.random() < 0.5:
+            time.sleep(0.001)                           # let the watchdog / the delivery thread do the last part on their own
+        h.flush()
+        st = h.stats()
+        if use_file:
+            h.stream_to_file(None)
+    ns = wire.size // 6
+    first_mode = O.MODE_I32 if fmt & pg.OUT_INT32 else O.MODE_F32_POW2 if fmt & pg.OUT_FLOAT_POW2 else O.MODE_F32
+    want = co.unpack(wire, first_mode).view(np.uint32).reshape(-1)
+    assert st["callbacks"] == len(sizes) and st["samples"] == ns and st["dropped_callbacks"] == 0, (cfg, st)
+    for name, blocks in (("device sink", dev if use_dev else None), ("host sink", host if use_host else None)):
+        if blocks is None:
+            continue
+        pos = 0
+        for b in blocks:
+            assert b[0] == pos, (name, cfg, "blocks out of order")
+            pos += b[1].size // 2
+        assert pos == ns and np.array_equal(np.concatenate([b[1] for b in blocks]), want), (name, cfg)
+    if use_host:
+        assert all(b[2] == bool(fmt & pg.OUT_INT32) and b[3] == bool(fmt & (pg.OUT_FLOAT | pg.OUT_FLOAT_POW2)) for b in host)
+        assert st["host_blocks"] == st["slabs"] == len(host), (cfg, st)
+    if use_file:
+        assert Path(path).read_bytes() == want.tobytes(), ("file", cfg)
+    return st["slabs"]
+
+
+def main():
+    seed, count = int(sys.argv[1]), int(sys.argv[2])
+    rng = random.Random(seed)
+    slabs = 0
+    with tempfile.TemporaryDirectory() as tmp:
+        for k in range(count):
+            slabs += scenario(rng, k, tmp)
+    print(f"fuzz_streaming: {count} scenarios passed ({slabs} slabs)")
+
+
+if __name__ == "__main__":
+    main()

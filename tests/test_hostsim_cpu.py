@@ -1,0 +1,46 @@
+"""The product's HOST layer driven from Python on a box without a GPU: tests/hostsim/build.sh compiles perseus_gpu.cu's host code,
+perseus_vrx.cpp, perseus_host.cpp and copy_pool.cpp against the CUDA stand-in of tests/sanitize/fake_cuda (its "kernels" call the CPU
+oracle) into a shared library with the product's C ABI; two randomised drivers then hammer the plumbing -- the streaming path
+(slab ring, both slab routes, eager submission, age bound, watchdog, delivery thread, all three sinks) and perseus_gpu_unpack's
+staging pipeline (pointer kinds, chunks, slots, copy pool) -- and compare every byte every consumer sees with the oracle's unpack.
+Nothing here is the product: the product's kernels are tested on the B200 (-m gpu)."""
+import os
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+
+@pytest.fixture(scope="module")
+def hostsim(tmp_path_factory):
+    if not shutil.which("g++"):
+        pytest.skip("no g++")
+    out = tmp_path_factory.mktemp("hostsim") / "libperseus_gpu_hostsim.so"
+    subprocess.run([str(ROOT / "tests" / "hostsim" / "build.sh"), str(out)], check=True, timeout=600)
+    return out
+
+
+def drive(hostsim, script, *args, env_extra=None):
+    env = dict(os.environ, PERSEUS_GPU_LIB=str(hostsim), **(env_extra or {}))
+    r = subprocess.run([sys.executable, str(ROOT / "tests" / "hostsim" / script), *map(str, args)], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    return r.stdout
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_streaming_plumbing_against_the_oracle(hostsim, seed):
+    assert "600 scenarios passed" in drive(hostsim, "fuzz_streaming.py", seed, 600)
+
+
+def test_streaming_plumbing_with_the_fallback_handoff_clock_and_copy(hostsim):
+    """the fence hand-off instead of sys_membarrier, clock_gettime instead of the TSC, 16-byte stores"""
+    env = {"PERSEUS_GPU_NO_MEMBARRIER": "1", "PERSEUS_GPU_NO_TSC": "1", "PERSEUS_GPU_NT_COPY": "sse2"}
+    assert "400 scenarios passed" in drive(hostsim, "fuzz_streaming.py", 21, 400, env_extra=env)
+
+
+@pytest.mark.parametrize("seed", [31, 32])
+def test_bulk_pipeline_plumbing_against_the_oracle(hostsim, seed):
+    assert "300 handles passed" in drive(hostsim, "fuzz_bulk.py", seed, 300)
