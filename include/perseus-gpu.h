@@ -133,7 +133,7 @@ typedef struct perseus_gpu_config {
 	uint32_t eager_gap_us;    /* streaming path: a transfer that arrives more than this long after the previous one (callback start to
 	                             callback start) is submitted at once instead of waiting for its slab to fill or to age: the stream
 	                             is slower than the GPU path (any real receiver: a transfer every 0.5 ms at 2 MS/s, every
-	                             10.8 ms at 95 kS/s), so every transfer is in device memory ~30 us after its callback; transfers
+	                             10.8 ms at 95 kS/s), so every transfer is in device memory -- and at the host sink -- 15-30 us after its callback; transfers
 	                             that arrive back to back (replayed recordings, bursts) still fill slabs.  Only with a latency
 	                             bound (max_latency_us != 0xFFFFFFFF).  (0 = 100 us; 0xFFFFFFFF = never: slabs go out full or
 	                             over age only)                                                                            */
@@ -219,7 +219,7 @@ int perseus_gpu_prepare(perseus_gpu *h);
 /* Latency bound without a following callback.  A partly filled slab is submitted once its oldest
  * transfer has waited cfg.max_latency_us.  That is checked at every callback and, because a stream
  * can stall (USB error, the last transfers before perseus_stop_async_input), also by a small
- * watchdog thread the handle starts with its first callback (period = max_latency_us / 4,
+ * watchdog thread the handle starts with its first callback (it sleeps until the partial slab's deadline;
  * PERSEUS_GPU_OPT_NO_WATCHDOG disables it).  Applications that prefer to drive it themselves call
  * perseus_gpu_poll() from any thread: it submits the partial slab if it is over age and returns the
  * number of slabs it submitted (0 or 1), or a negative error. */
