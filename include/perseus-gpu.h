@@ -29,7 +29,7 @@
  * latency watchdog may all touch the same handle; they serialise.  Ownership is recursive: a
  * sink may call the synchronous plumbing (sync, memcpy, get_stats) of its own handle, but not
  * flush/close/unpack.  perseus_gpu_input_callback itself takes no lock in the common case
- * (the hand-off uses sys_membarrier, csrc/perseus_gpu.cu), so it costs nothing next to its
+ * (the hand-off uses sys_membarrier, csrc/handle.h), so it costs nothing next to its
  * copy; entry points called while a handle is streaming pay one membarrier (~us).  Every entry
  * point that takes a handle leaves the CALLING thread's current CUDA device set to the
  * handle's device (cudaSetDevice, not restored).

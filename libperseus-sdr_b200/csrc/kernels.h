@@ -1,4 +1,4 @@
-// Internal interface between the C-ABI layer (perseus_gpu.cu) and the sm_100a kernels
+// Internal interface between the C-ABI layer (handle.cu, stream_path.cu, bulk_path.cu) and the sm_100a kernels
 // (unpack_kernels.cu).  Not installed; the public surface is include/perseus-gpu.h.
 #pragma once
 #include <cuda_runtime.h>

@@ -1,5 +1,5 @@
 // TEST INFRASTRUCTURE ONLY (tests/sanitize/): a stand-in for <cuda_runtime.h> so that the HOST code of
-// libperseus-sdr_b200/csrc/perseus_gpu.cu -- handle lock, slab ring, latency watchdog, staging pipeline bookkeeping --
+// libperseus-sdr_b200/csrc/{handle,stream_path,bulk_path}.cu -- handle lock, slab ring, latency watchdog, staging pipeline bookkeeping --
 // can be compiled with a plain C++ compiler and run under ThreadSanitizer / AddressSanitizer (tests/sanitize/sanitize.sh).
 // "Device" memory is host memory; copies and kernels complete before the call returns; host functions (cudaLaunchHostFunc) run
 // on a thread of their own, in order, and events / stream synchronisation wait for the ones queued before them.

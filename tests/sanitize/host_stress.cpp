@@ -1,4 +1,4 @@
-// TEST INFRASTRUCTURE ONLY: drives the host layer of libperseus_gpu (perseus_gpu.cu's host code, perseus_vrx.cpp,
+// TEST INFRASTRUCTURE ONLY: drives the host layer of libperseus_gpu (handle.cu, stream_path.cu, bulk_path.cu, perseus_vrx.cpp,
 // perseus_host.cpp) from several threads at once so ThreadSanitizer / AddressSanitizer can see it.  Built by
 // tests/sanitize/sanitize.sh against tests/sanitize/fake_cuda (no GPU involved); results are also checked against the CPU oracle.
 #include "../../include/perseus-gpu.h"

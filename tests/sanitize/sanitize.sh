@@ -1,5 +1,5 @@
 #!/bin/bash
-# Host-layer sanitizer runs: builds the C-ABI host code -- perseus_gpu.cu's host side, perseus_vrx.cpp,
+# Host-layer sanitizer runs: builds the C-ABI host code -- handle.cu / stream_path.cu / bulk_path.cu (no kernels in them), perseus_vrx.cpp,
 # perseus_host.cpp -- with a plain C++ compiler against the CUDA stand-in in tests/sanitize/fake_cuda, once with
 # ThreadSanitizer and once with AddressSanitizer + UBSan, and runs tests/sanitize/host_stress.cpp under each.
 # No GPU involved; the device kernels have their own compute-sanitizer runs (profiles/sanitizer_*).
@@ -22,7 +22,7 @@ for san in tsan asan; do
 		echo "# $san: $CXX -O1 -g $FLAGS  (host layer of libperseus_gpu over tests/sanitize/fake_cuda; $(date -u +%FT%TZ))"
 		/usr/bin/gcc -O1 -g $FLAGS -fPIC -c "$ROOT/oracle/perseus_oracle.c" -o "$BUILD/oracle_$san.o" &&
 		$CXX -std=c++17 -O1 -g $FLAGS -pthread -Wall -Wextra -Wno-tsan -I"$ROOT/tests/sanitize/fake_cuda" -I"$CSRC" \
-			-x c++ "$CSRC/perseus_gpu.cu" -x none $SRCS "$BUILD/oracle_$san.o" -o "$BUILD/host_stress_$san" &&
+			-x c++ "$CSRC/handle.cu" "$CSRC/stream_path.cu" "$CSRC/bulk_path.cu" -x none $SRCS "$BUILD/oracle_$san.o" -o "$BUILD/host_stress_$san" &&
 		for nomb in 0 1; do   # the callback / owner hand-off has two implementations: sys_membarrier (asymmetric) and plain fences
 			echo "# PERSEUS_GPU_NO_MEMBARRIER=$nomb PERSEUS_GPU_NO_TSC=$nomb PERSEUS_GPU_NT_COPY=$([ $nomb = 1 ] && echo sse2 || echo widest)"
 			# ... and the callback's clock and the slab copy two each: TSC-carried / clock_gettime, widest / 16-byte stores

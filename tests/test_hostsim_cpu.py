@@ -1,4 +1,4 @@
-"""The product's HOST layer driven from Python on a box without a GPU: tests/hostsim/build.sh compiles perseus_gpu.cu's host code,
+"""The product's HOST layer driven from Python on a box without a GPU: tests/hostsim/build.sh compiles the C-ABI layer (handle.cu, stream_path.cu, bulk_path.cu),
 perseus_vrx.cpp, perseus_host.cpp and copy_pool.cpp against the CUDA stand-in of tests/sanitize/fake_cuda (its "kernels" call the CPU
 oracle) into a shared library with the product's C ABI; two randomised drivers then hammer the plumbing -- the streaming path
 (slab ring, both slab routes, eager submission, age bound, watchdog, delivery thread, all three sinks) and perseus_gpu_unpack's

@@ -1,4 +1,5 @@
-"""Host-layer thread hygiene: tests/sanitize/sanitize.sh builds perseus_gpu.cu's host code, perseus_vrx.cpp and
+"""Host-layer thread hygiene: tests/sanitize/sanitize.sh builds the C-ABI layer (handle.cu, stream_path.cu, bulk_path.cu), perseus_vrx.cpp,
+copy_pool.cpp and
 perseus_host.cpp with g++ against a CUDA stand-in (tests/sanitize/fake_cuda) under ThreadSanitizer and under
 AddressSanitizer+UBSan and runs the multi-threaded stress driver tests/sanitize/host_stress.cpp under both."""
 import shutil
