@@ -143,7 +143,6 @@ int64_t plan_run_locked(perseus_gpu *h, perseus_gpu_plan *p, unsigned flags)
 	return (int64_t)p->nsamples;
 }
 
-
 }  // namespace pgh
 
 using namespace pgh;
@@ -279,7 +278,6 @@ int perseus_gpu_get_checksums(perseus_gpu *h, uint64_t *sum_i32, uint64_t *sum_f
 	return 0;
 }
 
-
 // ---- batched ------------------------------------------------------------------------------------
 
 int perseus_gpu_plan_create(perseus_gpu *h, const perseus_gpu_seg *segs, int nseg, unsigned flags, perseus_gpu_plan **out)
@@ -318,7 +316,6 @@ int64_t perseus_gpu_unpack_batch(perseus_gpu *h, const perseus_gpu_seg *segs, in
 	destroy_plan(p);
 	return n;
 }
-
 
 int perseus_gpu_autotune(perseus_gpu *h, double *gbs_single, double *gbs_fused)
 {
@@ -527,6 +524,5 @@ int perseus_gpu_probe_pcie(perseus_gpu *h, int kind, size_t nbytes, size_t d2h_n
 	if (d2h_gbs) *d2h_gbs = best_down;
 	return 0;
 }
-
 
 }  // extern "C"

@@ -143,7 +143,6 @@ void tsc_anchor_now(perseus_gpu *h)
 	h->tsc_anchor = c;
 }
 
-
 // ---- ownership hand-off between the callback thread and everybody else (see struct perseus_gpu) ----------------------
 
 bool membarrier_available()
@@ -427,7 +426,6 @@ int perseus_gpu_get_tuning(perseus_gpu *h, perseus_gpu_tuning *t)
 	return 0;
 }
 
-
 // ---- plumbing ---------------------------------------------------------------------------------------
 
 void *perseus_gpu_dev_alloc(perseus_gpu *h, size_t nbytes)
@@ -521,6 +519,5 @@ int perseus_gpu_event_elapsed_ms(perseus_gpu *h, int a, int b, float *ms)
 	CU(h, cudaEventElapsedTime(ms, h->events[a], h->events[b]));
 	return 0;
 }
-
 
 }  // extern "C"

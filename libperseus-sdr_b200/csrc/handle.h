@@ -71,7 +71,6 @@ struct Slab {
 	bool busy = false;
 };
 
-
 }  // namespace pgh
 
 struct perseus_gpu {
@@ -237,7 +236,6 @@ inline uint64_t callback_now_ns(perseus_gpu *h)
 	return h->ns_anchor + (uint64_t)(((unsigned __int128)dc * h->ns_per_tick_q32) >> 32);
 }
 
-
 inline void light_barrier(const perseus_gpu *h)      // callback side
 {
 	if (h->asym) asm volatile("" ::: "memory");
@@ -275,6 +273,5 @@ struct Entry {
 	Entry(const Entry &) = delete;
 	Entry &operator=(const Entry &) = delete;
 };
-
 
 }  // namespace pgh

@@ -218,7 +218,6 @@ int submit_slab(perseus_gpu *h)
 	return 0;
 }
 
-
 // Transfer -> pinned slab.  The slab is written once by this thread and then only read by the device, so the copy uses
 // non-temporal stores (pg::copy_nontemporal): no read-for-ownership of the destination lines, about twice the bandwidth of
 // memcpy for 6144-byte pieces on one core (the callback is single-threaded by contract, perseus-sdr.c:736-770).
@@ -232,7 +231,6 @@ int submit_if_over_age(perseus_gpu *h, uint64_t now)
 	const int rc = submit_slab(h);
 	return rc ? rc : 1;
 }
-
 
 // perseus_stop_async_input): this thread sleeps until the partial slab's deadline and submits it.
 void watchdog_main(perseus_gpu *h)
