@@ -299,13 +299,15 @@ class PerseusGpu:
         return self.L.perseus_gpu_input_callback(buf, nbytes, self.h)
 
     def set_sink(self, fn) -> None:
-        self._sink = SINK(fn) if fn else C.cast(None, SINK)
-        check(self.L.perseus_gpu_set_sink(self.h, self._sink, None))
+        new = SINK(fn) if fn else C.cast(None, SINK)
+        check(self.L.perseus_gpu_set_sink(self.h, new, None))
+        self._sink = new
 
     def set_host_sink(self, fn) -> None:
         """fn(HostBlock pointer, extra) is called on a CUDA runtime thread, once per slab, in stream order."""
-        self._host_sink = HOST_SINK(fn) if fn else C.cast(None, HOST_SINK)
-        check(self.L.perseus_gpu_set_host_sink(self.h, self._host_sink, None))
+        new = HOST_SINK(fn) if fn else C.cast(None, HOST_SINK)
+        check(self.L.perseus_gpu_set_host_sink(self.h, new, None))   # flushes: the previous sink may still be called in here ...
+        self._host_sink = new                                         # ... so its trampoline is let go of only now
 
     def stream_to_file(self, path: str | None) -> None:
         check(self.L.perseus_gpu_stream_to_file(self.h, path.encode() if path else None))

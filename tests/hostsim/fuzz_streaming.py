@@ -56,10 +56,22 @@ def scenario(rng, idx, tmp):
             h.stream_to_file(path)
         if rng.random() < 0.3:
             h.prepare()
+        # some scenarios switch the host sink off and on again in mid-stream: setting it flushes, so the sink must receive
+        # exactly the samples pushed while it was set
+        toggling = use_host and not use_file and rng.random() < 0.25
+        host_on, on_from, intervals = use_host, 0, []
         off = 0
         for n in sizes:
             h.input_callback(wire[off:].ctypes.data, n)
             off += n
+            if toggling and rng.random() < 0.15:
+                if host_on:
+                    h.set_host_sink(None)
+                    intervals.append((on_from, off // 6))
+                else:
+                    h.set_host_sink(host_sink)
+                    on_from = off // 6
+                host_on = not host_on
             r = rng.random()
             if r < 0.08:
                 h.flush()
@@ -75,21 +87,28 @@ def scenario(rng, idx, tmp):
         st = h.stats()
         if use_file:
             h.stream_to_file(None)
+    if host_on:
+        intervals.append((on_from, wire.size // 6))
     ns = wire.size // 6
     first_mode = O.MODE_I32 if fmt & pg.OUT_INT32 else O.MODE_F32_POW2 if fmt & pg.OUT_FLOAT_POW2 else O.MODE_F32
     want = co.unpack(wire, first_mode).view(np.uint32).reshape(-1)
     assert st["callbacks"] == len(sizes) and st["samples"] == ns and st["dropped_callbacks"] == 0, (cfg, st)
-    for name, blocks in (("device sink", dev if use_dev else None), ("host sink", host if use_host else None)):
+    for name, blocks, spans in (("device sink", dev if use_dev else None, [(0, ns)]), ("host sink", host if use_host else None, intervals)):
         if blocks is None:
             continue
-        pos = 0
-        for b in blocks:
-            assert b[0] == pos, (name, cfg, "blocks out of order")
-            pos += b[1].size // 2
-        assert pos == ns and np.array_equal(np.concatenate([b[1] for b in blocks]), want), (name, cfg)
+        covered = []
+        for b in blocks:                                   # every block carries the samples its first_sample says it carries ...
+            first, n = b[0], b[1].size // 2
+            assert np.array_equal(b[1], want[2 * first:2 * (first + n)]), (name, cfg, "block content")
+            if covered and covered[-1][1] == first:
+                covered[-1] = (covered[-1][0], first + n)
+            else:
+                covered.append((first, first + n))
+        # ... in stream order, and together exactly the samples pushed while the sink was set
+        assert covered == [sp for sp in spans if sp[1] > sp[0]], (name, cfg, covered, spans)
     if use_host:
         assert all(b[2] == bool(fmt & pg.OUT_INT32) and b[3] == bool(fmt & (pg.OUT_FLOAT | pg.OUT_FLOAT_POW2)) for b in host)
-        assert st["host_blocks"] == st["slabs"] == len(host), (cfg, st)
+        assert st["host_blocks"] == len(host) and (toggling or st["host_blocks"] == st["slabs"]), (cfg, st)
     if use_file:
         assert Path(path).read_bytes() == want.tobytes(), ("file", cfg)
     return st["slabs"]
