@@ -232,6 +232,7 @@ int submit_if_over_age(perseus_gpu *h, uint64_t now)
 	return rc ? rc : 1;
 }
 
+// The latency bound must hold when no further callback comes (a stalled stream, the tail before
 // perseus_stop_async_input): this thread sleeps until the partial slab's deadline and submits it.
 void watchdog_main(perseus_gpu *h)
 {
