@@ -11,6 +11,7 @@ import os
 import random
 import sys
 import tempfile
+import threading
 import time
 from pathlib import Path
 
@@ -61,7 +62,23 @@ def scenario(rng, idx, tmp):
         toggling = use_host and not use_file and rng.random() < 0.25
         host_on, on_from, intervals = use_host, 0, []
         off = 0
-        for n in sizes:
+        if not toggling and rng.random() < 0.3:
+            # two threads on one handle: the receiver's thread calls back as fast as it can (lock-free fast path) while this one
+            # keeps taking the handle away from it (statistics, poll, flush, sync: each goes through the ownership hand-off)
+            def receiver():
+                o = 0
+                for n in sizes:
+                    h.input_callback(wire[o:].ctypes.data, n)
+                    o += n
+            t = threading.Thread(target=receiver)
+            t.start()
+            while t.is_alive():
+                rng.choice([h.stats, h.poll, h.flush, h.sync, lambda: h.get_geometry(fmt & 7)])()
+            t.join()
+            sizes_left = []
+        else:
+            sizes_left = sizes
+        for n in sizes_left:
             h.input_callback(wire[off:].ctypes.data, n)
             off += n
             if toggling and rng.random() < 0.15:
