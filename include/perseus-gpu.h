@@ -130,8 +130,8 @@ typedef struct perseus_gpu_config {
 	                             each chunk between the application's memory and pinned bounce buffers while the copy engines
 	                             work on the neighbouring chunks  (0 = min(8, cores/2); 1 = the caller alone; 0xFFFFFFFF = hand
 	                             pageable pointers to the CUDA runtime, which stages them on the calling thread)           */
-	uint32_t eager_gap_us;    /* streaming path: a transfer that arrives more than this long after the previous one (callback start to
-	                             callback start) is submitted at once instead of waiting for its slab to fill or to age: the stream
+	uint32_t eager_gap_us;    /* streaming path: a transfer that arrives more than this long after the previous callback returned
+	                             is submitted at once instead of waiting for its slab to fill or to age: the stream
 	                             is slower than the GPU path (any real receiver: a transfer every 0.5 ms at 2 MS/s, every
 	                             10.8 ms at 95 kS/s), so every transfer is in device memory -- and at the host sink -- 15-30 us after its callback; transfers
 	                             that arrive back to back (replayed recordings, bursts) still fill slabs.  Only with a latency

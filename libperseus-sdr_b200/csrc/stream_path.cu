@@ -289,11 +289,13 @@ int stream_push(perseus_gpu *h, const uint8_t *buf, size_t nbytes)
 	// transfer every 0.5 ms at 2 MS/s, every 10.8 ms at 95 kS/s) -- and nothing is gained by letting the transfer wait for
 	// company.  It goes out at once (a small slab: one launch, perseus_gpu_config.direct_bytes).  Transfers that arrive back
 	// to back (a replayed recording, a burst) keep filling slabs; batching sets in by itself when the path is the bottleneck.
-	// Measured start to start with the one clock reading the age bound needs anyway (a second reading per callback costs
-	// the 6144-byte path a quarter of its rate); a previous callback that itself took long -- it allocated, or waited for a
-	// free slab -- only makes one more small slab.
+	// The gap runs from the END of the previous callback: time that callback spent submitting a slab, or waiting for a free one,
+	// is the path's, not the stream's.  (Counted from its start, a path that has become the bottleneck -- a GPU busy with other
+	// work, a profiler that makes every launch take milliseconds -- would see every transfer arrive "late", submit each one
+	// alone and make itself slower still.)  A callback that only copied ended ~0.2 us after it began: its one clock reading
+	// serves; only a callback that submitted something reads the clock again.
 	const bool eager = h->eager_gap_ns && h->last_push_ns && now - h->last_push_ns > h->eager_gap_ns;
-	h->last_push_ns = now;
+	const uint64_t slabs_before = h->stats.slabs;
 	if (h->fill == 0) {
 		h->fill_started_ns = now;
 		h->partial_since_ns.store(now, std::memory_order_relaxed);
@@ -314,6 +316,7 @@ int stream_push(perseus_gpu *h, const uint8_t *buf, size_t nbytes)
 	}
 	// latency bound: on a real receiver transfers trickle in (10.8 ms apart at 95 kS/s); do not sit on them
 	rc = (eager && h->fill && !h->latched) ? submit_slab(h) : submit_if_over_age(h, now);
+	h->last_push_ns = (h->eager_gap_ns && h->stats.slabs != slabs_before) ? callback_now_ns(h) : now;
 	return rc < 0 ? rc : 0;
 }
 

@@ -145,6 +145,13 @@ cudaError_t launch_unpack(const void *in, size_t nbytes, void *out_i32, void *ou
 {
 	*launches = 0;
 	if (nbytes / 6 == 0) return cudaSuccess;
+	// PERSEUS_FAKE_LAUNCH_US: every launch takes this long on the calling thread -- a submission path that has become the
+	// bottleneck (a profiler serialising launches, a GPU busy elsewhere), for the tests of how the streaming path batches then
+	static const long slow_us = [] { const char *e = getenv("PERSEUS_FAKE_LAUNCH_US"); return e ? atol(e) : 0L; }();
+	if (slow_us > 0) {
+		const double until = now_ms() + slow_us * 1e-3;
+		while (now_ms() < until) { }
+	}
 	if (fmt & FMT_I32) perseus_oracle_unpack(0, static_cast<const uint8_t *>(in), nbytes, out_i32);
 	if (fmt & FMT_F32) perseus_oracle_unpack(1, static_cast<const uint8_t *>(in), nbytes, out_f32);
 	if (fmt & FMT_POW2) perseus_oracle_unpack(2, static_cast<const uint8_t *>(in), nbytes, out_f32);

@@ -44,3 +44,29 @@ def test_streaming_plumbing_with_the_fallback_handoff_clock_and_copy(hostsim):
 @pytest.mark.parametrize("seed", [31, 32])
 def test_bulk_pipeline_plumbing_against_the_oracle(hostsim, seed):
     assert "300 handles passed" in drive(hostsim, "fuzz_bulk.py", seed, 300)
+
+
+def test_a_slow_submission_path_batches_more_not_less(hostsim, tmp_path):
+    """Eager submission must not feed on itself: when every launch takes 0.3 ms (a profiler serialising launches, a GPU busy with
+    other work) back-to-back transfers still fill their slabs -- the gap that makes a transfer "late" runs from the END of the
+    previous callback, so the path's own time is not mistaken for the stream's.  (Measured from the start of the previous callback
+    every transfer after the first submission looked late and was launched alone: 2000 launches instead of 32; under ncu, where a
+    launch takes tens of milliseconds, the 174 762-transfer callback leg of bench.py did not finish.)"""
+    script = tmp_path / "slow.py"
+    script.write_text(
+        "import sys; sys.path.insert(0, %r)\n"
+        "import __graft_entry__ as G\n"
+        "pg = G.load_package()\n"
+        "with pg.PerseusGpu(device=0, stream_flags=pg.OUT_INT32, slab_bytes=6144 * 64, nslabs=3) as h:\n"
+        "    v = pg.VirtualReceiver(sample_rate=2_000_000, seed=3)\n"
+        "    v.run(6144, *h.callback, 2000)\n"
+        "    h.flush()\n"
+        "    v.close()\n"
+        "    st = h.stats()\n"
+        "    assert st['samples'] == 2000 * 1024, st\n"
+        "    print('slabs', st['slabs'])\n" % str(ROOT))
+    env = dict(os.environ, PERSEUS_GPU_LIB=str(hostsim), PERSEUS_FAKE_LAUNCH_US="300")
+    r = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    slabs = int(r.stdout.split()[-1])
+    assert 32 <= slabs <= 48, slabs                       # 2000 / 64 = 31.25 -> 32, plus a few cut by hiccups of the box
