@@ -2,7 +2,8 @@
 perseus_vrx.cpp, perseus_host.cpp and copy_pool.cpp against the CUDA stand-in of tests/sanitize/fake_cuda (its "kernels" call the CPU
 oracle) into a shared library with the product's C ABI; two randomised drivers then hammer the plumbing -- the streaming path
 (slab ring, both slab routes, eager submission, age bound, watchdog, delivery thread, all three sinks) and perseus_gpu_unpack's
-staging pipeline (pointer kinds, chunks, slots, copy pool) -- and compare every byte every consumer sees with the oracle's unpack.
+staging pipeline (pointer kinds, chunks, slots, copy pool) and the batched plans' tile maps -- and compare every byte every consumer
+sees with the oracle's unpack.
 Nothing here is the product: the product's kernels are tested on the B200 (-m gpu)."""
 import os
 import shutil
@@ -44,6 +45,11 @@ def test_streaming_plumbing_with_the_fallback_handoff_clock_and_copy(hostsim):
 @pytest.mark.parametrize("seed", [31, 32])
 def test_bulk_pipeline_plumbing_against_the_oracle(hostsim, seed):
     assert "300 handles passed" in drive(hostsim, "fuzz_bulk.py", seed, 300)
+
+
+@pytest.mark.parametrize("seed", [41, 42])
+def test_batched_plan_tile_maps_against_the_oracle(hostsim, seed):
+    assert "400 batches passed" in drive(hostsim, "fuzz_batch.py", seed, 400)
 
 
 def test_a_slow_submission_path_batches_more_not_less(hostsim, tmp_path):
