@@ -213,7 +213,7 @@ int perseus_gpu_input_callback(void *buf, int buf_size, void *extra);
  * events, the pinned output copies when a file / host sink is set, the first (code-loading) kernel launch, the watchdog: tens of
  * milliseconds -- so that the first transfers of a real receiver are not held up on libperseus-sdr's poll thread (its ring of 8
  * transfers covers 4 ms at 2 MS/s, perseus-sdr.c:683).  Call after perseus_gpu_set_host_sink / perseus_gpu_stream_to_file and
- * before perseus_start_async_input. */
+ * before perseus_start_async_input.  Harmless at any other time (in mid-stream it only allocates what is still missing). */
 int perseus_gpu_prepare(perseus_gpu *h);
 
 /* Latency bound without a following callback.  A partly filled slab is submitted once its oldest

@@ -435,14 +435,17 @@ int perseus_gpu_prepare(perseus_gpu *h)
 				if (produced[f] && !h->slabs[k].host_out[f]) CU(h, cudaHostAlloc(&h->slabs[k].host_out[f], h->slab_bytes / 6 * 8, cudaHostAllocDefault));
 		if ((rc = start_delivery(h))) return rc;
 	}
-	// the first launch of a kernel loads its code: do that here, on two samples of slab 0 (nothing is delivered or counted)
-	Slab &s = h->slabs[0];
-	memset(s.host, 0, 12);
-	int n = 0;
-	cudaError_t e = pg::launch_unpack(s.host, 12, s.dev_i32, s.dev_f32, h->stream_fmt, h->tune, h->sm_count, h->streams[0], &n);
-	if (e == cudaSuccess) e = cudaStreamSynchronize(h->streams[0]);
-	if (e != cudaSuccess) return fail(PERSEUS_GPU_CUDAERR, "warm-up launch failed: %s", cudaGetErrorString(e));
-	h->stats.kernel_launches += (uint64_t)n;
+	// The first launch of a kernel loads its code: do that here, on two samples' worth of slab 0 (nothing is delivered or
+	// counted).  Only while the stream has not begun -- afterwards slab 0 holds live data, and the code is loaded anyway.
+	if (h->stats.slabs == 0 && h->fill == 0 && h->stats.callbacks == 0) {
+		Slab &s = h->slabs[0];
+		memset(s.host, 0, 12);
+		int n = 0;
+		cudaError_t e = pg::launch_unpack(s.host, 12, s.dev_i32, s.dev_f32, h->stream_fmt, h->tune, h->sm_count, h->streams[0], &n);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(h->streams[0]);
+		if (e != cudaSuccess) return fail(PERSEUS_GPU_CUDAERR, "warm-up launch failed: %s", cudaGetErrorString(e));
+		h->stats.kernel_launches += (uint64_t)n;
+	}
 	start_watchdog(h);
 	return 0;
 }

@@ -73,7 +73,7 @@ def scenario(rng, idx, tmp):
             t = threading.Thread(target=receiver)
             t.start()
             while t.is_alive():
-                rng.choice([h.stats, h.poll, h.flush, h.sync, lambda: h.get_geometry(fmt & 7)])()
+                rng.choice([h.stats, h.poll, h.flush, h.sync, h.prepare, lambda: h.get_geometry(fmt & 7)])()
             t.join()
             sizes_left = []
         else:
@@ -94,8 +94,10 @@ def scenario(rng, idx, tmp):
                 h.flush()
             elif r < 0.16:
                 h.poll()
-            elif r < 0.24:
+            elif r < 0.22:
                 h.stats()
+            elif r < 0.24:
+                h.prepare()                             # in mid-stream: must not touch a slab that holds live data
             elif r < 0.34:
                 time.sleep(rng.choice([0.0, 0.0001, 0.0006]))
         if rng.random() < 0.5:

@@ -284,6 +284,84 @@ static void scenario_pageable_bounce()
 	b.join();
 }
 
+// H: randomised: a receiver thread calling back as fast as it can while the application thread switches the host sink off and on,
+//    polls, flushes, reads statistics, prepares -- three threads (with the delivery thread) on one handle, many short streams
+struct Spans {
+	std::mutex mu;
+	std::vector<std::pair<uint64_t, uint64_t>> got;      // [first, end) of every block, merged when contiguous
+	uint64_t words = 0, bad = 0;
+	const uint32_t *want = nullptr;
+};
+
+static void span_sink(const perseus_gpu_host_block *b, void *extra)
+{
+	Spans *sp = static_cast<Spans *>(extra);
+	std::lock_guard<std::mutex> lk(sp->mu);
+	const uint32_t *w = static_cast<const uint32_t *>(b->i32);
+	for (uint64_t k = 0; k < 2 * b->nsamples; ++k) sp->bad += w[k] != sp->want[2 * b->first_sample + k];
+	sp->words += 2 * b->nsamples;
+	if (!sp->got.empty() && sp->got.back().second == b->first_sample) sp->got.back().second += b->nsamples;
+	else sp->got.emplace_back(b->first_sample, b->first_sample + b->nsamples);
+}
+
+static void scenario_random_toggling()
+{
+	unsigned rs = 12345;
+	auto rnd = [&rs](unsigned n) { rs = rs * 1103515245u + 12345u; return (rs >> 16) % n; };
+	for (int it = 0; it < 40; ++it) {
+		const int ntransfers = 50 + (int)rnd(400);
+		std::vector<uint8_t> wire((size_t)ntransfers * 6144), want((size_t)ntransfers * 8192);
+		CHECK(perseus_synth_fill(wire.data(), wire.size(), PERSEUS_SYNTH_RANDOM, 1000 + it, 0) == 0);
+		perseus_oracle_unpack(0, wire.data(), wire.size(), want.data());
+		perseus_gpu_config cfg;
+		memset(&cfg, 0, sizeof cfg);
+		cfg.struct_size = sizeof cfg;
+		cfg.stream_flags = PERSEUS_GPU_OUT_INT32;
+		cfg.slab_bytes = 6144 * (1 + rnd(9)) + 48 * rnd(50);
+		cfg.nslabs = 2 + rnd(4);
+		cfg.nstreams = 1 + rnd(3);
+		cfg.max_latency_us = rnd(2) ? 200 : 0;
+		cfg.direct_bytes = rnd(2) ? 0 : 0xFFFFFFFFu;
+		cfg.eager_gap_us = rnd(2) ? 20 : 0xFFFFFFFFu;
+		perseus_gpu *h = nullptr;
+		CHECK(perseus_gpu_open(&h, &cfg) == 0);
+		Spans sp;
+		sp.want = reinterpret_cast<const uint32_t *>(want.data());
+		CHECK(perseus_gpu_set_host_sink(h, span_sink, &sp) == 0);
+		if (rnd(2)) CHECK(perseus_gpu_prepare(h) == 0);
+		std::atomic<bool> done{false};
+		std::thread receiver([&] {
+			for (int k = 0; k < ntransfers; ++k) {
+				perseus_gpu_input_callback(wire.data() + (size_t)k * 6144, 6144, h);
+				if (k % 37 == 0) std::this_thread::yield();
+			}
+			done.store(true);
+		});
+		bool on = true;
+		unsigned toggles = 0;
+		while (!done.load()) {
+			switch (rnd(6)) {
+			case 0: CHECK(perseus_gpu_set_host_sink(h, on ? nullptr : span_sink, &sp) == 0); on = !on; ++toggles; break;
+			case 1: CHECK(perseus_gpu_poll(h) >= 0); break;
+			case 2: CHECK(perseus_gpu_flush(h) == 0); break;
+			case 3: { perseus_gpu_stats st; CHECK(perseus_gpu_get_stats(h, &st) == 0 && st.host_blocks <= st.slabs); break; }
+			case 4: CHECK(perseus_gpu_prepare(h) == 0); break;
+			default: std::this_thread::yield();
+			}
+		}
+		receiver.join();
+		CHECK(perseus_gpu_flush(h) == 0);
+		perseus_gpu_stats st;
+		CHECK(perseus_gpu_get_stats(h, &st) == 0 && st.callbacks == (uint64_t)ntransfers && st.samples == (uint64_t)ntransfers * 1024);
+		CHECK(perseus_gpu_close(h) == 0);
+		// whatever the interleaving: every block carried the samples its first_sample says, blocks came in stream order, and with
+		// no toggling at all the sink saw the whole stream
+		CHECK(sp.bad == 0);
+		for (size_t k = 1; k < sp.got.size(); ++k) CHECK(sp.got[k].first > sp.got[k - 1].second);
+		if (toggles == 0) CHECK(sp.got.size() == 1 && sp.got[0].first == 0 && sp.got[0].second == (uint64_t)ntransfers * 1024);
+	}
+}
+
 // G: the non-temporal copy (16/32/64-byte stores picked at run time; PERSEUS_GPU_NT_COPY forces one) at every destination and
 //    source phase and every length around its block sizes: exactly the bytes asked for, nothing outside
 static void scenario_nontemporal_copy()
@@ -310,6 +388,7 @@ int main()
 	scenario_host_delivery();
 	scenario_pageable_bounce();
 	scenario_nontemporal_copy();
+	scenario_random_toggling();
 	printf("host_stress: all scenarios passed\n");
 	return 0;
 }
