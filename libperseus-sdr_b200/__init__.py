@@ -251,8 +251,10 @@ class PerseusGpu:
     # -- life cycle
     def close(self) -> None:
         if self.h:
-            h, self.h = self.h, C.c_void_p()
-            check(self.L.perseus_gpu_close(h))
+            try:
+                check(self.L.perseus_gpu_close(self.h))     # flushes: sinks may still be called in here, and may use this object
+            finally:
+                self.h = C.c_void_p()
 
     def __enter__(self):
         return self

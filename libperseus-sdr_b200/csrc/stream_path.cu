@@ -390,8 +390,20 @@ inline void callback_body(perseus_gpu *h, const uint8_t *buf, size_t n)
 		return;
 	}
 	h->stats.callbacks++;
+	const uint64_t before = h->samples_submitted * 6 + h->fill;   // bytes the stream has taken in so far
 	int rc = stream_push(h, buf, n);
-	if (rc) latch(h, rc);
+	if (rc) {
+		latch(h, rc);
+		// the failing transfer itself: whatever part of it did not make it into a slab is lost like the ones that follow
+		const uint64_t taken = h->samples_submitted * 6 + h->fill - before;
+		if (taken < n) {
+			h->stats.dropped_bytes += n - taken;
+			if (taken == 0) {
+				h->stats.callbacks--;
+				h->stats.dropped_callbacks++;
+			}
+		}
+	}
 }
 }  // namespace
 

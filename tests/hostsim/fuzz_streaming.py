@@ -61,6 +61,7 @@ def scenario(rng, idx, tmp):
         # exactly the samples pushed while it was set
         toggling = use_host and not use_file and rng.random() < 0.25
         host_on, on_from, intervals = use_host, 0, []
+        dev_on, dev_from, dev_spans, bulk_samples = use_dev, 0, [], 0
         off = 0
         if not toggling and rng.random() < 0.3:
             # two threads on one handle: the receiver's thread calls back as fast as it can (lock-free fast path) while this one
@@ -98,21 +99,47 @@ def scenario(rng, idx, tmp):
                 h.stats()
             elif r < 0.24:
                 h.prepare()                             # in mid-stream: must not touch a slab that holds live data
+            elif r < 0.28:
+                # a bulk call on the streaming handle (it shares streams[0] with the slabs): its own result must be right and the
+                # stream must not notice
+                nb = rng.choice([48, 6144, 6144 * 3 + 30])
+                bw = co.synth_random(nb, seed=7000 + idx)
+                out = np.zeros(nb // 6 * 2, np.uint32)
+                assert h.unpack(bw.ctypes.data, nb, out.ctypes.data, None, pg.OUT_INT32) == nb // 6
+                assert np.array_equal(out, co.unpack(bw, O.MODE_I32).view(np.uint32).reshape(-1)), ("bulk call in mid-stream", cfg)
+                bulk_samples += nb // 6
+            elif r < 0.31 and use_dev and not toggling:
+                # the device sink taken away and given back: the samples in between go unobserved by it, nothing else changes
+                # (with it gone, small slabs of a host-only stream may be stored straight into host memory)
+                if dev_on:
+                    h.flush()
+                    h.set_sink(None)
+                    dev_spans.append((dev_from, off // 6))
+                else:
+                    h.flush()
+                    h.set_sink(dev_sink)
+                    dev_from = off // 6
+                dev_on = not dev_on
             elif r < 0.34:
                 time.sleep(rng.choice([0.0, 0.0001, 0.0006]))
         if rng.random() < 0.5:
             time.sleep(0.001)                           # let the watchdog / the delivery thread do the last part on their own
-        h.flush()
+        closed_without_flush = rng.random() < 0.3
+        if not closed_without_flush:                    # otherwise: perseus_gpu_close flushes, delivers and closes the file
+            h.flush()
+            if use_file:
+                h.stream_to_file(None)
         st = h.stats()
-        if use_file:
-            h.stream_to_file(None)
+    if dev_on:
+        dev_spans.append((dev_from, wire.size // 6))
     if host_on:
         intervals.append((on_from, wire.size // 6))
     ns = wire.size // 6
     first_mode = O.MODE_I32 if fmt & pg.OUT_INT32 else O.MODE_F32_POW2 if fmt & pg.OUT_FLOAT_POW2 else O.MODE_F32
     want = co.unpack(wire, first_mode).view(np.uint32).reshape(-1)
-    assert st["callbacks"] == len(sizes) and st["samples"] == ns and st["dropped_callbacks"] == 0, (cfg, st)
-    for name, blocks, spans in (("device sink", dev if use_dev else None, [(0, ns)]), ("host sink", host if use_host else None, intervals)):
+    assert st["callbacks"] == len(sizes) and st["dropped_callbacks"] == 0, (cfg, st)
+    assert closed_without_flush or st["samples"] == ns + bulk_samples, (cfg, st)
+    for name, blocks, spans in (("device sink", dev if use_dev else None, dev_spans), ("host sink", host if use_host else None, intervals)):
         if blocks is None:
             continue
         covered = []
@@ -127,7 +154,7 @@ def scenario(rng, idx, tmp):
         assert covered == [sp for sp in spans if sp[1] > sp[0]], (name, cfg, covered, spans)
     if use_host:
         assert all(b[2] == bool(fmt & pg.OUT_INT32) and b[3] == bool(fmt & (pg.OUT_FLOAT | pg.OUT_FLOAT_POW2)) for b in host)
-        assert st["host_blocks"] == len(host) and (toggling or st["host_blocks"] == st["slabs"]), (cfg, st)
+        assert closed_without_flush or (st["host_blocks"] == len(host) and (toggling or st["host_blocks"] == st["slabs"])), (cfg, st)
     if use_file:
         assert Path(path).read_bytes() == want.tobytes(), ("file", cfg)
     return st["slabs"]

@@ -3,6 +3,7 @@
 // oracle (oracle/perseus_oracle.c) -- tests may; the product never links this file.
 #include "kernels.h"
 
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <cstdio>
@@ -66,9 +67,11 @@ struct HostFuncs {
 	}
 } g_hostfuncs;
 double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+std::atomic<long> g_fail_alloc_in{0};   // fake_cuda_fail_alloc_in(n): the n-th allocation from now fails once (0 = none)
 cudaError_t alloc(void **p, size_t n, cudaMemoryType kind)
 {
 	if (n > (size_t(1) << 40)) return cudaErrorMemoryAllocation;
+	if (g_fail_alloc_in.load() > 0 && g_fail_alloc_in.fetch_sub(1) == 1) return cudaErrorMemoryAllocation;
 	*p = malloc(n ? n : 1);
 	if (!*p) return cudaErrorMemoryAllocation;
 	std::lock_guard<std::mutex> lk(g_mu);
@@ -86,6 +89,9 @@ cudaError_t release(void *p)
 	return cudaSuccess;
 }
 }  // namespace
+
+// test hook (host-simulation build only): make the n-th device / pinned allocation from now fail, once
+extern "C" void fake_cuda_fail_alloc_in(long n) { g_fail_alloc_in.store(n); }
 
 cudaError_t cudaGetLastError() { return cudaSuccess; }
 const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : e == cudaErrorMemoryAllocation ? "out of memory" : "fake CUDA error"; }

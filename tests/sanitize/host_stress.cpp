@@ -14,6 +14,7 @@
 
 extern "C" size_t perseus_oracle_unpack(int mode, const uint8_t *in, size_t nbytes, void *out);
 namespace pg { void copy_nontemporal(uint8_t *dst, const uint8_t *src, size_t n); }   // csrc/copy_pool.h
+extern "C" void fake_cuda_fail_alloc_in(long n);                                        // tests/sanitize/fake_cuda.cpp
 
 #define CHECK(c)                                                                          \
 	do {                                                                                  \
@@ -178,7 +179,7 @@ static void scenario_edges()
 	CHECK(perseus_gpu_open(&h, &cfg) == 0);
 	for (int k = 0; k < 4; ++k) CHECK(perseus_gpu_input_callback(t.data(), 6144, h) == 0);
 	perseus_gpu_stats s;
-	CHECK(perseus_gpu_get_stats(h, &s) == 0 && s.callbacks == 1 && s.dropped_callbacks == 3 && s.dropped_bytes == 3 * 6144);
+	CHECK(perseus_gpu_get_stats(h, &s) == 0 && s.callbacks == 0 && s.dropped_callbacks == 4 && s.dropped_bytes == 4 * 6144);   // the failing one too
 	CHECK(perseus_gpu_flush(h) == PERSEUS_GPU_CUDAERR);
 	CHECK(perseus_gpu_flush(h) == 0);
 	CHECK(perseus_gpu_close(h) == 0);
@@ -362,6 +363,48 @@ static void scenario_random_toggling()
 	}
 }
 
+// I: error paths under the sanitizers: the n-th device / pinned allocation fails, for every n that a short life of a handle reaches
+//    (open, prepare, streaming with host sink + file, a bulk call on pageable memory, a batched plan, a probe).  Whatever fails must
+//    fail cleanly: an error code, no leak (LeakSanitizer at exit), no use of what was not allocated, and a close that still works.
+static void scenario_allocation_failures()
+{
+	std::vector<uint8_t> wire(6144 * 40 + 30), oi(wire.size() / 6 * 8), of(wire.size() / 6 * 8);
+	CHECK(perseus_synth_fill(wire.data(), wire.size(), PERSEUS_SYNTH_RANDOM, 77, 0) == 0);
+	int failed_calls = 0;
+	for (long n = 1; n <= 70; ++n) {
+		fake_cuda_fail_alloc_in(n);
+		perseus_gpu_config cfg;
+		memset(&cfg, 0, sizeof cfg);
+		cfg.struct_size = sizeof cfg;
+		cfg.stream_flags = PERSEUS_GPU_OUT_FLOAT;
+		cfg.slab_bytes = 6144 * 2;
+		cfg.nslabs = 2;
+		cfg.chunk_bytes = 12288 * 4;
+		cfg.copy_threads = 2;
+		perseus_gpu *h = nullptr;
+		if (perseus_gpu_open(&h, &cfg) != 0) { ++failed_calls; CHECK(h == nullptr); continue; }
+		Collected col;
+		failed_calls += perseus_gpu_set_host_sink(h, host_sink, &col) != 0;
+		failed_calls += perseus_gpu_stream_to_file(h, "/tmp/perseus_sanitize_i.bin") != 0;
+		failed_calls += perseus_gpu_prepare(h) != 0;
+		for (int k = 0; k < 7; ++k) perseus_gpu_input_callback(wire.data() + k * 6144, 6144, h);
+		failed_calls += perseus_gpu_flush(h) != 0;
+		failed_calls += perseus_gpu_unpack(h, wire.data(), wire.size(), oi.data(), of.data(), PERSEUS_GPU_CHECKSUM) < 0;
+		perseus_gpu_seg seg = {wire.data(), wire.size(), oi.data(), nullptr};
+		failed_calls += perseus_gpu_unpack_batch(h, &seg, 1, PERSEUS_GPU_OUT_INT32) < 0;
+		double gbs = 0;
+		failed_calls += perseus_gpu_probe_hbm(h, PERSEUS_GPU_PROBE_COPY, 1 << 20, 1, &gbs) != 0;
+		failed_calls += perseus_gpu_probe_pcie(h, PERSEUS_GPU_PCIE_DUPLEX, 1 << 20, 0, 1, &gbs, &gbs) != 0;
+		void *p = perseus_gpu_dev_alloc(h, 4096);
+		if (p) CHECK(perseus_gpu_dev_free(h, p) == 0);
+		else ++failed_calls;
+		perseus_gpu_close(h);                        // may report the latched failure; must free everything either way
+	}
+	fake_cuda_fail_alloc_in(0);
+	remove("/tmp/perseus_sanitize_i.bin");
+	CHECK(failed_calls >= 30);                       // the injected failures did land in API calls, not only in the void
+}
+
 // G: the non-temporal copy (16/32/64-byte stores picked at run time; PERSEUS_GPU_NT_COPY forces one) at every destination and
 //    source phase and every length around its block sizes: exactly the bytes asked for, nothing outside
 static void scenario_nontemporal_copy()
@@ -389,6 +432,7 @@ int main()
 	scenario_pageable_bounce();
 	scenario_nontemporal_copy();
 	scenario_random_toggling();
+	scenario_allocation_failures();
 	printf("host_stress: all scenarios passed\n");
 	return 0;
 }

@@ -52,6 +52,13 @@ def test_batched_plan_tile_maps_against_the_oracle(hostsim, seed):
     assert "400 batches passed" in drive(hostsim, "fuzz_batch.py", seed, 400)
 
 
+@pytest.mark.parametrize("seed", [51, 52])
+def test_error_paths_one_allocation_fails_somewhere(hostsim, seed):
+    """the failure is latched, reported once with its CUDA text, what is dropped is counted, what was delivered is right, the
+    handle keeps working (tests/sanitize runs the same idea under LeakSanitizer)"""
+    assert "500 scenarios passed" in drive(hostsim, "fuzz_errors.py", seed, 500)
+
+
 def test_a_slow_submission_path_batches_more_not_less(hostsim, tmp_path):
     """Eager submission must not feed on itself: when every launch takes 0.3 ms (a profiler serialising launches, a GPU busy with
     other work) back-to-back transfers still fill their slabs -- the gap that makes a transfer "late" runs from the END of the
@@ -76,3 +83,21 @@ def test_a_slow_submission_path_batches_more_not_less(hostsim, tmp_path):
     assert r.returncode == 0, r.stderr[-3000:]
     slabs = int(r.stdout.split()[-1])
     assert 32 <= slabs <= 48, slabs                       # 2000 / 64 = 31.25 -> 32, plus a few cut by hiccups of the box
+
+
+HOST_LAYER_TESTS = ("not (pcie_probe or autotune or c_program or gpu_program) and (trampoline or sink or stream_file or latency or cfg1 or "
+                    "slow_stream or prepare or callback or several or two_handles or hammers or reference or pageable or host_pointer or "
+                    "checksum_flag or checksum_totals or event_slots or stream_to_file or faults or poll_thread)")
+
+
+def test_host_layer_subset_of_the_gpu_suite_holds_against_the_simulation(hostsim):
+    """The -m gpu tests that exercise the HOST layer (trampoline, sinks, latency bounds, eager submission, cfg1 through the virtual
+    receiver and through the reference's own library, pageable staging, error latching ...) run here against the host-simulation
+    build: their expectations about the plumbing are checked on every CPU run, before a B200 is asked.  (Kernel parity tests need
+    the real device and are not part of this.)"""
+    env = dict(os.environ, PERSEUS_GPU_LIB=str(hostsim))
+    r = subprocess.run([sys.executable, "-m", "pytest", str(ROOT / "tests" / "test_gpu_parity.py"), str(ROOT / "tests" / "test_reflib_gpu.py"),
+                        "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider", "-k", HOST_LAYER_TESTS], env=env, capture_output=True, text=True, timeout=1200,
+                       cwd=str(ROOT))
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout
