@@ -101,3 +101,36 @@ def test_host_layer_subset_of_the_gpu_suite_holds_against_the_simulation(hostsim
                        cwd=str(ROOT))
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
     assert " passed" in r.stdout and "failed" not in r.stdout
+
+
+def test_c_examples_run_against_the_simulation(hostsim, tmp_path, coracle):
+    """examples/perseus_gpu_replay.c and perseus_gpu_hostsink.c, compiled as C99 and linked against the host-simulation build: the
+    whole flow of a C caller -- open, sinks, prepare, the virtual receiver calling back, flush, close -- on every CPU run.
+    (tests/test_examples.py runs them against the product library on the B200.)"""
+    import shutil as sh
+    import numpy as np
+    from oracle import oracle as O
+    libdir = tmp_path / "lib"
+    libdir.mkdir()
+    sh.copy(hostsim, libdir / "libperseus_gpu.so")
+    env = dict(os.environ, LD_LIBRARY_PATH=f"{libdir}:{os.environ.get('LD_LIBRARY_PATH', '')}")
+    bins = {}
+    for name in ("perseus_gpu_replay", "perseus_gpu_hostsink"):
+        bins[name] = tmp_path / name
+        subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", str(ROOT / "include"), str(ROOT / "examples" / f"{name}.c"),
+                        "-L", str(libdir), "-lperseus_gpu", "-o", str(bins[name])], check=True)
+    out = tmp_path / "perseusdata"
+    r = subprocess.run([str(bins["perseus_gpu_replay"]), "-s", "96000", "-n", "6", "-b", "1024", "-N", "211", "-o", str(out), "-p"], env=env,
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert out.read_bytes() == coracle.unpack(coracle.synth_random(211 * 6144), O.MODE_F32).tobytes()
+    r = subprocess.run([str(bins["perseus_gpu_replay"]), "-s", "2000000", "-N", "50", "-o", "-"], env=env, capture_output=True, timeout=120)
+    assert r.returncode == 0 and r.stdout == coracle.unpack(coracle.synth_random(50 * 6144), O.MODE_I32).tobytes()
+    for args, n in ((("-N", "333"), 333), (("-s", "2000000", "-t", "1"), None)):
+        r = subprocess.run([str(bins["perseus_gpu_hostsink"]), *args], env=env, capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stderr
+        got = dict(zip(r.stdout.split()[0::2], map(int, r.stdout.split()[1::2])))
+        n = n or got["samples"] // 1024
+        want = coracle.unpack(coracle.synth_random(n * 6144), O.MODE_I32).view(np.int32).reshape(-1, 2).astype(np.int64)
+        assert got["samples"] == n * 1024 and got["out_of_order"] == 0
+        assert (got["sum_i"], got["sum_q"], got["peak"]) == (int(want[:, 0].sum()), int(want[:, 1].sum()), int(np.abs(want).max()))
