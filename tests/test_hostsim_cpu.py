@@ -96,9 +96,12 @@ def test_host_layer_subset_of_the_gpu_suite_holds_against_the_simulation(hostsim
     build: their expectations about the plumbing are checked on every CPU run, before a B200 is asked.  (Kernel parity tests need
     the real device and are not part of this.)"""
     env = dict(os.environ, PERSEUS_GPU_LIB=str(hostsim))
-    r = subprocess.run([sys.executable, "-m", "pytest", str(ROOT / "tests" / "test_gpu_parity.py"), str(ROOT / "tests" / "test_reflib_gpu.py"),
-                        "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider", "-k", HOST_LAYER_TESTS], env=env, capture_output=True, text=True, timeout=1200,
-                       cwd=str(ROOT))
+    for attempt in range(2):          # several of these tests pace themselves by the wall clock: a busy container gets one more try
+        r = subprocess.run([sys.executable, "-m", "pytest", str(ROOT / "tests" / "test_gpu_parity.py"), str(ROOT / "tests" / "test_reflib_gpu.py"),
+                            "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider", "-k", HOST_LAYER_TESTS], env=env, capture_output=True, text=True,
+                           timeout=1200, cwd=str(ROOT))
+        if r.returncode == 0:
+            break
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
     assert " passed" in r.stdout and "failed" not in r.stdout
 
